@@ -33,7 +33,7 @@ extern "C" {
 #define OFDMGAN_D_NPARAMS 521             /* models/discriminator.py:61 */
 #define OFDMGAN_WROM_DEPTH 2048           /* rtl/ofdmGAN/weight_rom.v:14 */
 #define OFDMGAN_BROM_DEPTH 64             /* rtl/ofdmGAN/weight_rom.v:186 */
-#define OFDMGAN_MAX_STREAMS 16
+#define OFDMGAN_MAX_STREAMS 8
 #define OFDMGAN_MAX_SNR_BINS 16
 
 #define OFDMGAN_E_ARG (-1)                /* null pointer / bad enum / bad size */

@@ -1,0 +1,276 @@
+// Per-thread channel simulator: symbols -> IFFT in registers -> (CP) -> Rapp PA -> IQ imbalance -> Wiener phase noise
+// -> AWGN -> normalisation.  One frame per thread, every array index is a compile-time constant.
+//   utils/dataset.py:236-293 (SyntheticOFDMDataset.__getitem__), utils/ofdm_utils.py:105-109,163-193 (QPSK map),
+//   :281-329 (OFDMModulator.modulate), :394-421 (Rapp), :458-488 (IQ), :491-521 (phase noise), :675-708 (AWGN),
+//   benchmark_comparison.py:129-134 (separate normalisation)
+#pragma once
+#include "common.cuh"
+
+namespace og {
+
+// source layouts compiled into the simulator (anything else: OFDMGAN_E_UNSUPPORTED)
+enum { SRC_GAUSS = 0, SRC_Q16_CP0 = 1, SRC_Q16_CP2 = 2, SRC_Q8_CP0 = 3, SRC_Q8_CP2 = 4, SRC_COUNT = 5 };
+
+struct SimArgs {
+    ofdmgan_chan_cfg cfg;
+    PhiloxKeys keys;
+    uint64_t frame0;
+    int64_t B;
+    const float* sym;        // injected draws (device, nullable)
+    const uint32_t* bits;
+    const float* pn;
+    const float* snr_db;
+    const float* noise;
+    float* clean;            // outputs (device, nullable)
+    float* noisy;
+    float* snr_out;
+    int gen_kind;            // -1: no generator, else OFDMGAN_GEN_*
+    int wslot;               // weight slot of the generator image
+    float slope;
+    double* partials;        // [grid][n_snr][N_METHODS][COLS] per-CTA metric partials (nullable)
+    int n_snr;
+};
+
+// ---- radix-2 DIT inverse FFT, fully unrolled, unscaled: x[n] = sum_k X[k] e^{+j 2 pi k n / N} -------------
+template <int N>
+struct Tw;   // twiddles e^{+j 2 pi k / N}
+template <>
+struct Tw<16> {
+    static __device__ __forceinline__ float c(int k) {
+        constexpr float t[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                                0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+        return t[k];
+    }
+    static __device__ __forceinline__ float s(int k) {
+        constexpr float t[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                                1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+        return t[k];
+    }
+};
+
+__host__ __device__ constexpr int bitrev(int v, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// SIGN=+1: inverse (e^{+j}), SIGN=-1: forward (e^{-j}).  N in {8,16}; twiddle index scaled to the N=16 table.
+template <int N, int SIGN>
+__device__ __forceinline__ void fft_inplace(float (&re)[N], float (&im)[N]) {
+    constexpr int LOG = N == 16 ? 4 : 3;
+    float tr[N], ti[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { tr[i] = re[bitrev(i, LOG)]; ti[i] = im[bitrev(i, LOG)]; }
+#pragma unroll
+    for (int st = 1; st <= LOG; ++st) {
+        const int m = 1 << st, h = m >> 1;
+#pragma unroll
+        for (int base = 0; base < N; base += m)
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+                const int tw = j * (16 / m);                     // index into the 16-point table
+                const float wr = Tw<16>::c(tw), wi = (float)SIGN * Tw<16>::s(tw);
+                const int a = base + j, b = a + h;
+                float xr, xi;
+                if (tw == 0) { xr = tr[b]; xi = ti[b]; }
+                else if (tw == 4) { xr = -(float)SIGN * ti[b]; xi = (float)SIGN * tr[b]; }
+                else { xr = tr[b] * wr - ti[b] * wi; xi = tr[b] * wi + ti[b] * wr; }
+                tr[b] = tr[a] - xr; ti[b] = ti[a] - xi;
+                tr[a] = tr[a] + xr; ti[a] = ti[a] + xi;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { re[i] = tr[i]; im[i] = ti[i]; }
+}
+
+// ---- draws ------------------------------------------------------------------------------------------------
+// Philox block layout per frame (purpose 0): 0-7 symbol normals, 8-11 phase increments, 12 {snr uniform, payload
+// bits}, 13-20 noise normals.  See oracle/channel.c header.
+__device__ __forceinline__ void draw_normals(const SimArgs& a, uint64_t frame, uint32_t blk, float (&n)[4]) {
+    uint32_t x[4];
+    philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), blk, 0u, x);
+    normals_from_block(x, n);
+}
+
+__device__ __forceinline__ int snr_bin_of(const ofdmgan_chan_cfg& c, uint64_t frame) {
+    if (c.snr_mode != OFDMGAN_SNR_GRID) return 0;
+    return (int)((frame / (uint64_t)c.frames_per_snr) % (uint64_t)c.n_snr);
+}
+
+// QPSK symbol k of an OFDM symbol: pilot or the next two payload bits (MSB -> Re sign, LSB -> Im sign)
+__device__ __forceinline__ void qpsk_fill(const ofdmgan_chan_cfg& c, uint32_t bits, int& bitpos, int k, float& xr, float& xi) {
+    const bool pilot = c.pilot_spacing > 0 && (k % c.pilot_spacing) == 0;
+    if (pilot) { xr = c.pilot_re; xi = c.pilot_im; return; }
+    const uint32_t b1 = bitpos < 32 ? (bits >> (31 - bitpos)) & 1u : 0u;
+    const uint32_t b0 = bitpos < 31 ? (bits >> (30 - bitpos)) & 1u : 0u;
+    bitpos += 2;
+    xr = b1 ? -0.70710678118654752f : 0.70710678118654752f;
+    xi = b0 ? -0.70710678118654752f : 0.70710678118654752f;
+}
+
+// clean time-domain frame cr/ci[16]
+template <int SRC>
+__device__ __forceinline__ void tx_frame(const SimArgs& a, int64_t b, uint64_t frame, uint32_t bits, float (&cr)[16],
+                                         float (&ci)[16]) {
+    const ofdmgan_chan_cfg& c = a.cfg;
+    if (SRC == SRC_GAUSS) {
+        float Xr[16], Xi[16];
+        if (a.sym) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { Xr[k] = a.sym[b * 32 + k]; Xi[k] = a.sym[b * 32 + 16 + k]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float n[4];
+                draw_normals(a, frame, j, n);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) Xr[4 * j + t] = n[t];
+                draw_normals(a, frame, 4 + j, n);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) Xi[4 * j + t] = n[t];
+            }
+        }
+        fft_inplace<16, +1>(Xr, Xi);
+        // (1/sqrt2 per bin) * (ifft 1/N) * (sqrt(N) or N)
+        const float sc = 0.70710678118654752f * (c.ifft_scale == OFDMGAN_SCALE_N ? 1.0f : 0.25f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { cr[i] = Xr[i] * sc; ci[i] = Xi[i] * sc; }
+        return;
+    }
+    constexpr int N = (SRC == SRC_Q16_CP0 || SRC == SRC_Q16_CP2) ? 16 : 8;
+    constexpr int CP = (SRC == SRC_Q16_CP2 || SRC == SRC_Q8_CP2) ? 2 : 0;
+    constexpr int NSYM = (16 + N + CP - 1) / (N + CP);             // OFDM symbols started inside the frame
+    const float sc = c.ifft_scale == OFDMGAN_SCALE_N ? 1.0f : (N == 16 ? 0.25f : 0.35355339059327376f);
+    int bitpos = 0;
+#pragma unroll
+    for (int s = 0; s < NSYM; ++s) {
+        float Xr[N], Xi[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) qpsk_fill(c, bits, bitpos, k, Xr[k], Xi[k]);
+        fft_inplace<N, +1>(Xr, Xi);
+#pragma unroll
+        for (int i = 0; i < N + CP; ++i) {
+            const int pos = s * (N + CP) + i;
+            const int srcI = i < CP ? N - CP + i : i - CP;
+            if (pos < 16) { cr[pos] = Xr[srcI] * sc; ci[pos] = Xi[srcI] * sc; }
+        }
+    }
+}
+
+// impairments + AWGN on a copy of the clean frame -> nr/ni
+__device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint64_t frame, float snr_db,
+                                               const float (&cr)[16], const float (&ci)[16], float (&nr)[16],
+                                               float (&ni)[16]) {
+    const ofdmgan_chan_cfg& c = a.cfg;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { nr[i] = cr[i]; ni[i] = ci[i]; }
+    if (c.impair & OFDMGAN_IMPAIR_PA) {
+        const float invA2 = 1.0f / (c.pa_saturation * c.pa_saturation);
+        const float p = c.pa_smoothness, ninv2p = -0.5f / p;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float t = (nr[i] * nr[i] + ni[i] * ni[i]) * invA2;             // (|x|/A)^2
+            const float yp = p == 3.0f ? t * t * t : exp2f(p * __log2f(t));       // (|x|/A)^(2p)
+            const float gain = exp2f(ninv2p * __log2f(1.0f + yp));               // (1+.)^(-1/2p); phase preserved
+            nr[i] *= gain; ni[i] *= gain;
+        }
+    }
+    if (c.impair & OFDMGAN_IMPAIR_IQ) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ni[i] = c.iq_gain * (c.iq_cos * ni[i] + c.iq_sin * nr[i]);
+    }
+    if (c.impair & OFDMGAN_IMPAIR_PN) {
+        float th = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float n[4];
+            if (a.pn) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) n[t] = a.pn[b * 16 + 4 * j + t];
+            } else {
+                draw_normals(a, frame, 8 + j, n);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = 4 * j + t;
+                th = fmaf(c.pn_sigma, n[t], th);
+                const float red = fmaf(-6.283185307179586f, rintf(th * 0.15915494309189535f), th);
+                float s, co;
+                __sincosf(red, &s, &co);
+                const float xr = nr[i], xi = ni[i];
+                nr[i] = xr * co - xi * s;
+                ni[i] = xr * s + xi * co;
+            }
+        }
+    }
+    float P = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) P = fmaf(nr[i], nr[i], fmaf(ni[i], ni[i], P));
+    P *= 0.0625f;
+    // sigma = sqrt(P / 10^(snr/10) / 2)
+    const float sd = sqrtf(0.5f * P * exp2f(-0.33219280948873623f * snr_db));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float n[4], m[4];
+        if (a.noise) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { n[t] = a.noise[b * 32 + 4 * j + t]; m[t] = a.noise[b * 32 + 16 + 4 * j + t]; }
+        } else {
+            draw_normals(a, frame, 13 + j, n);
+            draw_normals(a, frame, 17 + j, m);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            nr[4 * j + t] = fmaf(sd, n[t], nr[4 * j + t]);
+            ni[4 * j + t] = fmaf(sd, m[t], ni[4 * j + t]);
+        }
+    }
+}
+
+__device__ __forceinline__ float max_abs16(const float (&r)[16], const float (&i)[16]) {
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m = fmaxf(m, fmaxf(fabsf(r[k]), fabsf(i[k])));
+    return m;
+}
+
+__device__ __forceinline__ void normalise(int mode, float (&cr)[16], float (&ci)[16], float (&nr)[16], float (&ni)[16]) {
+    if (mode == OFDMGAN_NORM_NONE) return;
+    float mc = max_abs16(cr, ci), mn = max_abs16(nr, ni);
+    if (mode == OFDMGAN_NORM_JOINT) mc = mn = fmaxf(mc, mn);
+    const float sc = mc > 0.f ? 1.0f / mc : 1.0f, sn = mn > 0.f ? 1.0f / mn : 1.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { cr[k] *= sc; ci[k] *= sc; nr[k] *= sn; ni[k] *= sn; }
+}
+
+// hard QPSK decisions on the complete OFDM symbols inside a frame; returns payload bits compared
+template <int SRC>
+__device__ __forceinline__ int qpsk_errors(const ofdmgan_chan_cfg& c, const float (&fr)[16], const float (&fi)[16],
+                                           uint32_t bits, int& errs) {
+    errs = 0;
+    if (SRC == SRC_GAUSS || SRC == SRC_Q16_CP2) return 0;
+    constexpr int N = SRC == SRC_Q16_CP0 ? 16 : 8;
+    constexpr int CP = SRC == SRC_Q8_CP2 ? 2 : 0;
+    constexpr int NSYM = 16 / (N + CP);
+    int bitpos = 0, nb = 0;
+#pragma unroll
+    for (int s = 0; s < NSYM; ++s) {
+        float Xr[N], Xi[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Xr[i] = fr[s * (N + CP) + CP + i]; Xi[i] = fi[s * (N + CP) + CP + i]; }
+        fft_inplace<N, -1>(Xr, Xi);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const bool pilot = c.pilot_spacing > 0 && (k % c.pilot_spacing) == 0;
+            if (pilot) continue;
+            const uint32_t t1 = bitpos < 32 ? (bits >> (31 - bitpos)) & 1u : 0u;
+            const uint32_t t0 = bitpos < 31 ? (bits >> (30 - bitpos)) & 1u : 0u;
+            bitpos += 2;
+            errs += ((Xr[k] < 0.f) != (t1 != 0u)) + ((Xi[k] < 0.f) != (t0 != 0u));
+            nb += 2;
+        }
+    }
+    return nb;
+}
+
+}  // namespace og

@@ -1,0 +1,117 @@
+// libofdmgan internals shared by the translation units: error plumbing, launch geometry, the per-stream
+// constant-memory weight slots, Philox4x32-10 and the warp transpose-reduce used by every gradient kernel.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ofdmgan.h"
+
+#define OG_CHECK(expr)                                   \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) return (int)_e;           \
+    } while (0)
+
+#define OG_THREADS 128          // frames per CTA tile: one frame per thread
+#define OG_NSLOT OFDMGAN_MAX_STREAMS
+
+namespace og {
+
+// ---- launch geometry: persistent grids sized as a multiple of the SM count (148 on B200) ---------------------
+struct DeviceInfo {
+    int device = -1;
+    int sms = 0;
+};
+const DeviceInfo& device_info(int* err);
+// CTAs for a frame-parallel kernel over B frames with `per_sm` resident CTAs per SM
+int grid_for(int64_t B, int threads, int per_sm);
+
+// ---- weight slots ----------------------------------------------------------------------------------------
+// Every kernel reads its weights through the uniform datapath from a __constant__ image (LDCU -> FFMA R,R,UR,R).
+// A call on stream S owns slot(S); the image is refreshed stream-ordered before each launch
+// (prep kernel -> staging -> cudaMemcpyToSymbolAsync D2D), so CUDA graphs replay with the current weights.
+int slot_for_stream(cudaStream_t s, int* slot);
+// device scratch owned by the library (per slot), `bytes` each; returns the slot's pointer
+int scratch_for_slot(int slot, size_t bytes, int which, void** ptr);
+// copy `n` floats that may live on the host or the device into device scratch (no-op if already on device)
+int to_device_f32(const float* src, int n, int slot, int which, cudaStream_t s, const float** dev);
+
+// ---- Philox4x32-10 (counter-based RNG; definition in oracle/channel.c header and DESIGN.md) -----------------
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];   // the 10 round keys are the same for every thread: precomputed on the host
+};
+inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = a;
+        k.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return k;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox4x32_10(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k.k0[r];
+        uint32_t n2 = hi0 ^ c3 ^ k.k1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// u1 = ((x>>9)+0.5)*2^-23 in (0,1): exact in fp32.   u2 = (x>>8)*2^-24 in [0,1): exact.
+__device__ __forceinline__ float u_open(uint32_t x) { return __uint_as_float(0x3F800000u | (x >> 9)) - (1.0f - 5.9604644775390625e-08f); }
+__device__ __forceinline__ float u_half(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+
+// Box-Muller on the word pairs (x0,x1), (x2,x3): 4 normals per Philox block.
+__device__ __forceinline__ void normals_from_block(const uint32_t (&x)[4], float (&n)[4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float r = sqrtf(-2.0f * __logf(u_open(x[2 * h])));
+        float s, c;
+        __sincosf(6.283185307179586f * u_half(x[2 * h + 1]), &s, &c);
+        n[2 * h] = r * c;
+        n[2 * h + 1] = r * s;
+    }
+}
+
+// ---- warp transpose-reduce ---------------------------------------------------------------------------------
+// in: every lane holds 32 per-lane partials v[0..31].  out: lane l returns sum over lanes of v[l].
+// 31 shuffles + 31 adds instead of 32 x 5: the split-K reduction every weight-gradient kernel ends with.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            float send = upper ? v[i] : v[i + s];
+            float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, 0.f) + slope * fminf(v, 0.f); }
+#endif  // __CUDACC__
+
+}  // namespace og

@@ -1,0 +1,254 @@
+// Per-thread (one OFDM frame per thread, everything in registers) generator forward passes.
+//   gen_fwd_f32   : MiniGenerator.forward, models/generator.py:180-208, from the folded G image (weights.cuh)
+//   gen_fwd_q     : Q1.7/Q8.8 integer generator, rtl/ofdmGAN/generator_mini.v:326-649, modes spec / rtl_literal,
+//                   evaluated bit-exactly on the FP32 pipe (see fxacc below)
+// Weights come from a __constant__ image: ptxas turns every W[i] into an LDCU'd uniform register, so one tap is
+// one FFMA R,R,UR,R.  All loops are compile-time unrolled; there is no indexing at run time.
+#pragma once
+#include "weights.cuh"
+
+namespace og {
+
+// tanh(x) = 1 - 2/(1+e^{2x}); MUFU.EX2 + MUFU.RCP, absolute error <= ~1.5e-7 over the whole range
+__device__ __forceinline__ float tanh_fast(float x) {
+    float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+__device__ __forceinline__ float lrelu_sel(float v, float slope) { return v > 0.f ? v : slope * v; }
+
+// ---------------------------------------------------------------------------------------------------- fp32
+// x[2][16] -> y[2][16].  If TAPE, also returns the activations the backward pass needs:
+//   a1[4][8] = lrelu(enc1), a2[8][4] = lrelu(bottleneck), z3pos bitmask (dec1 pre-activation > 0), sk[4][8] = skip sum
+template <bool TAPE>
+__device__ __forceinline__ void gen_fwd_f32(const float* __restrict__ W, float slope, const float (&x)[2][16],
+                                            float (&y)[2][16], float (&a1)[4][8], float (&a2)[8][4], float (&sk)[4][8],
+                                            uint32_t& z3pos) {
+    // enc1: Conv1d(2->4, k3, s2, p1) + LeakyReLU
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            float acc = W[GI_ENC_B + oc];
+#pragma unroll
+            for (int ic = 0; ic < 2; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i >= 0) acc = fmaf(W[GI_ENC_W + (oc * 2 + ic) * 3 + k], x[ic][i], acc);
+                }
+            a1[oc][p] = lrelu_sel(acc, slope);
+        }
+    // bottleneck: Conv1d(4->8, k3, s2, p1) + LeakyReLU
+#pragma unroll
+    for (int oc = 0; oc < 8; ++oc)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float acc = W[GI_BN_B + oc];
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i >= 0) acc = fmaf(W[GI_BN_W + (oc * 4 + ic) * 3 + k], a1[ic][i], acc);
+                }
+            a2[oc][p] = lrelu_sel(acc, slope);
+        }
+    // upsample x2 + dec1 Conv1d(8->4, k3, s1, p1) + LeakyReLU, folded; + additive skip
+    z3pos = 0;
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float e = W[GI_DEC_B + oc], o = e;
+#pragma unroll
+            for (int ic = 0; ic < 8; ++ic) {
+                const float* F = W + GI_DEC_F + (oc * 8 + ic) * 4;
+                if (p > 0) e = fmaf(F[0], a2[ic][p - 1], e);
+                e = fmaf(F[1], a2[ic][p], e);
+                o = fmaf(F[2], a2[ic][p], o);
+                if (p < 3) o = fmaf(F[3], a2[ic][p + 1], o);
+            }
+            if (TAPE) z3pos |= (e > 0.f ? 1u : 0u) << (oc * 8 + 2 * p) | (o > 0.f ? 1u : 0u) << (oc * 8 + 2 * p + 1);
+            sk[oc][2 * p] = lrelu_sel(e, slope) + a1[oc][2 * p];
+            sk[oc][2 * p + 1] = lrelu_sel(o, slope) + a1[oc][2 * p + 1];
+        }
+    // upsample x2 + out_conv Conv1d(4->2, k3, s1, p1), folded; tanh
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            float e = W[GI_OUT_B + oc], o = e;
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic) {
+                const float* F = W + GI_OUT_F + (oc * 4 + ic) * 4;
+                if (p > 0) e = fmaf(F[0], sk[ic][p - 1], e);
+                e = fmaf(F[1], sk[ic][p], e);
+                o = fmaf(F[2], sk[ic][p], o);
+                if (p < 7) o = fmaf(F[3], sk[ic][p + 1], o);
+            }
+            y[oc][2 * p] = tanh_fast(e);
+            y[oc][2 * p + 1] = tanh_fast(o);
+        }
+}
+
+__device__ __forceinline__ void gen_fwd_f32_infer(const float* __restrict__ W, float slope, const float (&x)[2][16],
+                                                  float (&y)[2][16]) {
+    float a1[4][8], a2[8][4], sk[4][8];
+    uint32_t z;
+    gen_fwd_f32<false>(W, slope, x, y, a1, a2, sk, z);
+}
+
+// ---------------------------------------------------------------------------------------------------- fixed point
+// Integer semantics on the FP32 pipe.  Activations are int16 values held exactly in floats; weights are k/128
+// (exact).  An accumulator carries MAGIC + n with MAGIC = 1.5*2^23, where one ulp is exactly 1, so
+//     acc = fma_rd(a, w, acc)  ==  acc + floor(a*k/128)          (round toward -inf, a*w formed exactly inside the FMA)
+// which is the RTL's per-tap `(a*w) >>> 7` followed by the 32-bit add (generator_mini.v:141-146): one FFMA.RM per tap.
+// Valid while |n| < 2^22; a layer's worst case is 24 taps * 2^15 < 2^20.
+constexpr float FX_MAGIC = 12582912.0f;
+__device__ __forceinline__ float fxacc(float a, float w, float acc) { return __fmaf_rd(a, w, acc); }
+__device__ __forceinline__ float fx_sat16(float v) { return fminf(fmaxf(v, -32768.0f), 32767.0f); }
+// LeakyReLU of the RTL: r < 0 -> (r>>>2) + (r>>>4)   (generator_mini.v:359-360)
+__device__ __forceinline__ float fx_lrelu(float r) {
+    float t = __fmaf_rd(r, 0.25f, FX_MAGIC);
+    t = __fmaf_rd(r, 0.0625f, t);
+    return r < 0.f ? t - FX_MAGIC : r;
+}
+__device__ __forceinline__ float fx_finish(float acc, float bias, bool act) {
+    float v = fx_sat16((acc - FX_MAGIC) + bias);
+    return act ? fx_lrelu(v) : v;
+}
+__device__ __forceinline__ float fx_clip(float v) { return v > 256.f ? 255.f : (v < -256.f ? -255.f : v); }
+
+// mode spec: RTL primitives on the textbook dataflow (all channels, aligned weights, 1x1 output conv, clip both)
+__device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, const float (&x)[2][16], float (&y)[2][16]) {
+    float a1[4][8], a2[8][4], sk[4][8];
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            float acc = FX_MAGIC;
+#pragma unroll
+            for (int ic = 0; ic < 2; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i >= 0) acc = fxacc(x[ic][i], Q[0 + (oc * 2 + ic) * 3 + k], acc);
+                }
+            a1[oc][p] = fx_finish(acc, Q[QI_BIAS + 0 + oc], true);
+        }
+#pragma unroll
+    for (int oc = 0; oc < 8; ++oc)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float acc = FX_MAGIC;
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i >= 0) acc = fxacc(a1[ic][i], Q[24 + (oc * 4 + ic) * 3 + k], acc);
+                }
+            a2[oc][p] = fx_finish(acc, Q[QI_BIAS + 4 + oc], true);
+        }
+    // per-tap floor does not commute with weight folding: evaluate the 3 taps on the upsampled signal
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float acc = FX_MAGIC;
+#pragma unroll
+            for (int ic = 0; ic < 8; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = q + k - 1;
+                    if (i >= 0 && i < 8) acc = fxacc(a2[ic][i >> 1], Q[120 + (oc * 8 + ic) * 3 + k], acc);
+                }
+            sk[oc][q] = fx_sat16(fx_finish(acc, Q[QI_BIAS + 12 + oc], true) + a1[oc][q]);
+        }
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            float acc = FX_MAGIC;
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic) acc = fxacc(sk[ic][p], Q[216 + oc * 4 + ic], acc);
+            float v = fx_clip(fx_finish(acc, Q[QI_BIAS + 16 + oc], false));
+            y[oc][2 * p] = v;
+            y[oc][2 * p + 1] = v;
+        }
+}
+
+// mode rtl_literal: what the committed RTL computes (oracle/fixed_point.c skewed_conv).
+// The weight triple used by loop iteration (oc,op,ic) is the one addressed by the previous iteration.
+template <int IN, int OC, int K, int WA, int OC_FIRST, int STALE>
+__device__ __forceinline__ constexpr int skew_addr(int oc, int op, int ic) {
+    return ic > 0 ? WA + oc * IN * K + (ic - 1) * K
+                  : (op > 0 || oc == OC - 1) ? WA + oc * IN * K + (IN - 1) * K
+                                             : (oc > OC_FIRST ? WA + (oc - 1) * IN * K + (IN - 1) * K : STALE);
+}
+
+__device__ __forceinline__ void gen_fwd_q_rtl(const float* __restrict__ Q, const float (&x)[2][16], float (&y)[2][16]) {
+    float a1[4][8], bn7[4], dec[4][8];
+    // enc1: all 4 channels, stale address 223 (steady state)
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            float acc = FX_MAGIC;
+#pragma unroll
+            for (int ic = 0; ic < 2; ++ic) {
+                const int a = skew_addr<2, 4, 3, 0, 0, 223>(oc, p, ic);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i >= 0) acc = fxacc(x[ic][i], Q[a + k], acc);
+                }
+            }
+            a1[oc][p] = fx_finish(acc, Q[QI_BIAS + 0 + oc], true);
+        }
+    // bottleneck: only out-channels 3..7 are computed and only channel 7 is ever consumed (UPSAMPLE1 copies ch 7 only)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float acc = FX_MAGIC;
+#pragma unroll
+        for (int ic = 0; ic < 4; ++ic) {
+            const int a = skew_addr<4, 8, 3, 24, 3, 21>(7, p, ic);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = 2 * p + k - 1;
+                if (i >= 0) acc = fxacc(a1[ic][i], Q[a + k], acc);
+            }
+        }
+        bn7[p] = fx_finish(acc, Q[QI_BIAS + 4 + 7], true);
+    }
+    // dec1 over up1 where only channel 7 is non-zero: a zero activation contributes floor(0)=0 per tap
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float acc = FX_MAGIC;
+            const int a = skew_addr<8, 4, 3, 120, 0, 117>(oc, q, 7);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = q + k - 1;
+                if (i >= 0 && i < 8) acc = fxacc(bn7[i >> 1], Q[a + k], acc);
+            }
+            dec[oc][q] = fx_finish(acc, Q[QI_BIAS + 12 + oc], true);
+        }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dec[3][q] = fx_sat16(dec[3][q] + a1[3][q]);           // skip add only on channel 3
+    // 1x1 output conv on the upsampled signal, skewed; clip only channel 1
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            float acc = FX_MAGIC;
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic) acc = fxacc(dec[ic][q >> 1], Q[skew_addr<4, 2, 1, 216, 0, 213>(oc, q, ic)], acc);
+            float v = fx_finish(acc, Q[QI_BIAS + 16 + oc], false);
+            y[oc][q] = oc == 1 ? fx_clip(v) : v;
+        }
+}
+
+}  // namespace og

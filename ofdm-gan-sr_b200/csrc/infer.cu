@@ -1,0 +1,522 @@
+// libofdmgan inference-side kernels (sm_100a):
+//   (1) channel simulator                    ofdmgan_chan_sim / ofdmgan_chan_draws / ofdmgan_philox_blocks
+//   (2) fp32 generator forward               ofdmgan_gen_fwd_f32
+//   (3) Q1.7/Q8.8 integer generator          ofdmgan_gen_fwd_q, ofdmgan_(de)quantize_q88
+//   fused (1)+(2|3)+metrics                  ofdmgan_sim_gen_metrics(_host), ofdmgan_frame_metrics
+// One frame per thread, weights through the uniform datapath from __constant__ images, persistent grids sized as a
+// multiple of the SM count, warp-private coalesced staging of frame tiles (io_tile.cuh).
+#include "chan_device.cuh"
+#include "gen_device.cuh"
+#include "io_tile.cuh"
+
+namespace og {
+
+constexpr int NM = OFDMGAN_N_METHODS, NC = OFDMGAN_METRIC_COLS;
+
+// ------------------------------------------------------------------------------------------------ (2) fp32 G
+__global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_f32(const float* __restrict__ x, float* __restrict__ y, int64_t B,
+                                                            int slot, float slope) {
+    __shared__ float4 sm[OG_THREADS * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* wsm = sm + warp * 32 * 8;
+    const float* W = c_g[slot];
+    const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * OG_THREADS + warp * 32;
+        if (base >= B) continue;
+        float xi[2][16], yo[2][16];
+        tile_load_f32(x, base, B, wsm, lane, xi);
+        gen_fwd_f32_infer(W, slope, xi, yo);
+        tile_store_f32(y, base, B, wsm, lane, yo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (3) integer G
+__device__ __forceinline__ uint64_t digest_word(uint32_t v16, uint64_t index) {
+    uint64_t h = (uint64_t)v16 + 0x9E3779B97F4A7C15ull * (index + 1);
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    return h;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_q(const int16_t* __restrict__ x, int16_t* __restrict__ y, int64_t B,
+                                                          int slot, unsigned long long* __restrict__ digest) {
+    __shared__ uint4 sm[OG_THREADS * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* wsm = sm + warp * 32 * 4;
+    const float* Q = c_q[slot];
+    const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
+    unsigned long long dsum = 0, dxor = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * OG_THREADS + warp * 32;
+        if (base >= B) continue;
+        float xi[2][16], yo[2][16];
+        tile_load_i16(x, base, B, wsm, lane, xi);
+        if (MODE == OFDMGAN_GEN_Q_SPEC) gen_fwd_q_spec(Q, xi, yo); else gen_fwd_q_rtl(Q, xi, yo);
+        if (digest && base + lane < B) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t w = __float_as_uint(yo[i >> 4][i & 15] + 12582912.0f) & 0xffffu;
+                const uint64_t h = digest_word(w, (uint64_t)(base + lane) * 32 + i);
+                dsum += h; dxor ^= h;
+            }
+        }
+        tile_store_i16(y, base, B, wsm, lane, yo);
+    }
+    if (digest) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, s);
+            dxor ^= __shfl_xor_sync(0xffffffffu, dxor, s);
+        }
+        if (lane == 0) { atomicAdd(digest, dsum); atomicXor(digest + 1, dxor); }
+    }
+}
+
+__global__ void k_quantize_q88(const float* __restrict__ x, int16_t* __restrict__ q, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        q[i] = (int16_t)(int)(x[i] * 256.0f);                 // C cast: truncation toward zero (proof/verification.py:297)
+}
+__global__ void k_dequantize_q88(const int16_t* __restrict__ q, float* __restrict__ x, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = (float)q[i] * (1.0f / 256.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ metrics
+// per-thread running sums for the SNR bin the thread is currently in; spilled to the CTA's shared table on a bin change
+struct Acc {
+    float v[2][7];      // [GAN, NoEQ][n, mse, mse^2, evm, evm^2, errs, bits] ; col 7 (ratio) shares the flush below
+    float ratio[2];
+    int bin;
+    int count;
+};
+
+__device__ __forceinline__ void frame_err(const float (&er)[16], const float (&ei)[16], const float (&cr)[16],
+                                          const float (&ci)[16], float& mse, float& evm, float& ratio) {
+    float se = 0.f, sr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float a = er[i] - cr[i], b = ei[i] - ci[i];
+        se = fmaf(a, a, fmaf(b, b, se));
+        sr = fmaf(cr[i], cr[i], fmaf(ci[i], ci[i], sr));
+    }
+    mse = se * 0.03125f;
+    ratio = __fdividef(se, sr);
+    // 20 log10(sqrt(mean|e|^2 / mean|ref|^2) + 1e-10)     benchmark_comparison.py:142-146
+    evm = 6.020599913279624f * __log2f(sqrtf(ratio) + 1e-10f);
+}
+
+__device__ __forceinline__ void acc_reset(Acc& a, int bin) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) a.v[m][c] = 0.f;
+        a.ratio[m] = 0.f;
+    }
+    a.bin = bin;
+    a.count = 0;
+}
+
+// add the thread's running sums into the CTA table (shared, double).  Warp-uniform bins take the shuffle path.
+__device__ __forceinline__ void acc_flush(Acc& a, double* table, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int bin0 = __shfl_sync(full, a.bin, 0);
+    const bool uniform = __all_sync(full, a.bin == bin0);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float val = c < 7 ? a.v[m][c] : a.ratio[m];
+            if (uniform) {
+                const float s = warp_sum(val);
+                if (lane == 0 && a.bin >= 0) atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)s);
+            } else if (a.bin >= 0 && val != 0.f) {
+                atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)val);
+            }
+        }
+    }
+    acc_reset(a, a.bin);
+}
+
+__device__ __forceinline__ void acc_add(Acc& a, int m, float mse, float evm, float ratio, int errs, int nb) {
+    a.v[m][0] += 1.f; a.v[m][1] += mse; a.v[m][2] = fmaf(mse, mse, a.v[m][2]);
+    a.v[m][3] += evm; a.v[m][4] = fmaf(evm, evm, a.v[m][4]);
+    a.v[m][5] += (float)errs; a.v[m][6] += (float)nb;
+    a.ratio[m] += ratio;
+}
+
+// ------------------------------------------------------------------------------------------------ (1) + fused
+// frames kept per thread before the running float sums are folded into the double table (bounds float rounding)
+constexpr int FLUSH_EVERY = 32;
+
+template <int SRC>
+__global__ void __launch_bounds__(OG_THREADS) k_sim(const __grid_constant__ SimArgs a) {
+    __shared__ float4 sm[OG_THREADS * 8];
+    __shared__ double table[OFDMGAN_MAX_SNR_BINS * NM * NC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* wsm = sm + warp * 32 * 8;
+    const bool want_metrics = a.partials != nullptr;
+    if (want_metrics) {
+        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) table[i] = 0.0;
+        __syncthreads();
+    }
+    Acc acc;
+    acc_reset(acc, -1);
+    const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t wbase = t * OG_THREADS + warp * 32;
+        if (wbase >= a.B) continue;
+        const int64_t b = wbase + lane;
+        const bool live = b < a.B;
+        const int64_t bb = live ? b : a.B - 1;                   // dead lanes recompute the last frame, results dropped
+        const uint64_t frame = a.frame0 + (uint64_t)bb;
+
+        // block 12: {snr uniform, payload bits}
+        uint32_t bits = 0;
+        float snr_db;
+        {
+            uint32_t x12[4] = {0u, 0u, 0u, 0u};
+            const bool need12 = (SRC != SRC_GAUSS && !a.bits) || (a.cfg.snr_mode == OFDMGAN_SNR_UNIFORM && !a.snr_db);
+            if (need12) philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
+            bits = a.bits ? a.bits[bb] : x12[1];
+            if (a.cfg.snr_mode == OFDMGAN_SNR_GRID) snr_db = a.cfg.snr_lo + a.cfg.snr_step * (float)snr_bin_of(a.cfg, frame);
+            else snr_db = a.snr_db ? a.snr_db[bb] : fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x12[0]), a.cfg.snr_lo);
+        }
+        float cr[16], ci[16], nr[16], ni[16];
+        tx_frame<SRC>(a, bb, frame, bits, cr, ci);
+        impair_channel(a, bb, frame, snr_db, cr, ci, nr, ni);
+        normalise(a.cfg.normalize, cr, ci, nr, ni);
+
+        if (a.clean) {
+            float f[2][16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { f[0][i] = cr[i]; f[1][i] = ci[i]; }
+            tile_store_f32(a.clean, wbase, a.B, wsm, lane, f);
+        }
+        if (a.noisy) {
+            float f[2][16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { f[0][i] = nr[i]; f[1][i] = ni[i]; }
+            tile_store_f32(a.noisy, wbase, a.B, wsm, lane, f);
+        }
+        if (a.snr_out && live) a.snr_out[b] = snr_db;
+        if (a.gen_kind < 0) continue;
+
+        // reconstruct
+        float xin[2][16], yo[2][16];
+        if (a.gen_kind == OFDMGAN_GEN_F32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xin[0][i] = nr[i]; xin[1][i] = ni[i]; }
+            gen_fwd_f32_infer(c_g[a.wslot], a.slope, xin, yo);
+        } else {
+            // Q8.8 by truncation toward zero (proof/verification.py:297-298); back to float by /256
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xin[0][i] = truncf(nr[i] * 256.0f); xin[1][i] = truncf(ni[i] * 256.0f); }
+            if (a.gen_kind == OFDMGAN_GEN_Q_SPEC) gen_fwd_q_spec(c_q[a.wslot], xin, yo); else gen_fwd_q_rtl(c_q[a.wslot], xin, yo);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { yo[0][i] *= 0.00390625f; yo[1][i] *= 0.00390625f; }
+        }
+        if (!want_metrics) continue;
+        const int bin = snr_bin_of(a.cfg, frame);
+        if (__any_sync(0xffffffffu, bin != acc.bin || acc.count >= FLUSH_EVERY)) {
+            acc_flush(acc, table, lane);
+            acc.bin = bin;
+        }
+        if (live) {
+            float mse, evm, ratio;
+            int errs, nb;
+            frame_err(yo[0], yo[1], cr, ci, mse, evm, ratio);
+            nb = qpsk_errors<SRC>(a.cfg, yo[0], yo[1], bits, errs);
+            acc_add(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs, nb);
+            frame_err(nr, ni, cr, ci, mse, evm, ratio);
+            nb = qpsk_errors<SRC>(a.cfg, nr, ni, bits, errs);
+            acc_add(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, errs, nb);
+        }
+        acc.count++;
+    }
+    if (want_metrics) {
+        acc_flush(acc, table, lane);
+        __syncthreads();
+        double* out = a.partials + (size_t)blockIdx.x * a.n_snr * NM * NC;
+        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) out[i] = table[i];
+    }
+}
+
+// fixed-order sum of the per-CTA partial tables into the caller's accumulator (deterministic for a given grid)
+__global__ void k_reduce_partials(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ metrics) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * n + i];
+    metrics[i] += s;
+}
+
+// metrics of frames already in HBM
+__global__ void __launch_bounds__(OG_THREADS) k_frame_metrics(const float* __restrict__ est, const float* __restrict__ ref,
+                                                              const int32_t* __restrict__ bin, int method, int n_snr,
+                                                              int64_t B, double* __restrict__ partials) {
+    __shared__ float4 sm[OG_THREADS * 8];
+    __shared__ double table[OFDMGAN_MAX_SNR_BINS * NC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* wsm = sm + warp * 32 * 8;
+    for (int i = threadIdx.x; i < n_snr * NC; i += blockDim.x) table[i] = 0.0;
+    __syncthreads();
+    const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t wbase = t * OG_THREADS + warp * 32;
+        if (wbase >= B) continue;
+        float e[2][16], r[2][16];
+        tile_load_f32(est, wbase, B, wsm, lane, e);
+        tile_load_f32(ref, wbase, B, wsm, lane, r);
+        const int64_t b = wbase + lane;
+        if (b < B) {
+            float mse, evm, ratio;
+            frame_err(e[0], e[1], r[0], r[1], mse, evm, ratio);
+            const int s = bin ? bin[b] : 0;
+            if (s >= 0 && s < n_snr) {
+                double* row = table + s * NC;
+                atomicAdd(row + 0, 1.0); atomicAdd(row + 1, (double)mse); atomicAdd(row + 2, (double)mse * mse);
+                atomicAdd(row + 3, (double)evm); atomicAdd(row + 4, (double)evm * evm); atomicAdd(row + 7, (double)ratio);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_snr * NC; i += blockDim.x) {
+        const int s = i / NC, c = i % NC;
+        partials[((size_t)blockIdx.x * n_snr + s) * NM * NC + method * NC + c] = table[i];
+    }
+}
+
+// raw draws (test hook)
+__global__ void k_chan_draws(const __grid_constant__ SimArgs a, float* sym, uint32_t* bits, float* pn, float* snr_db,
+                             float* noise) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const uint64_t frame = a.frame0 + (uint64_t)b;
+    float n[4];
+    if (sym) for (int j = 0; j < 8; ++j) { draw_normals(a, frame, j, n); for (int t = 0; t < 4; ++t) sym[b * 32 + 4 * j + t] = n[t]; }
+    if (pn) for (int j = 0; j < 4; ++j) { draw_normals(a, frame, 8 + j, n); for (int t = 0; t < 4; ++t) pn[b * 16 + 4 * j + t] = n[t]; }
+    if (noise) for (int j = 0; j < 8; ++j) { draw_normals(a, frame, 13 + j, n); for (int t = 0; t < 4; ++t) noise[b * 32 + 4 * j + t] = n[t]; }
+    if (bits || snr_db) {
+        uint32_t x[4];
+        philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x);
+        if (bits) bits[b] = x[1];
+        if (snr_db) snr_db[b] = fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x[0]), a.cfg.snr_lo);
+    }
+}
+
+__global__ void k_philox_blocks(PhiloxKeys keys, uint64_t ctr0, uint32_t c2, uint32_t c3, uint32_t* out, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t c = ctr0 + (uint64_t)i;
+    uint32_t x[4];
+    philox4x32_10(keys, (uint32_t)c, (uint32_t)(c >> 32), c2, c3, x);
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = x[j];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int src_of(const ofdmgan_chan_cfg& c, int* src) {
+    if (c.symbol_source == OFDMGAN_SYM_GAUSSIAN) {
+        if (c.n_fft != 16 || c.cp_len != 0) return OFDMGAN_E_UNSUPPORTED;   // the reference's synthetic path is N=16, no CP
+        *src = SRC_GAUSS;
+        return 0;
+    }
+    if (c.symbol_source != OFDMGAN_SYM_QPSK) return OFDMGAN_E_ARG;
+    if (c.n_fft == 16 && c.cp_len == 0) *src = SRC_Q16_CP0;
+    else if (c.n_fft == 16 && c.cp_len == 2) *src = SRC_Q16_CP2;
+    else if (c.n_fft == 8 && c.cp_len == 0) *src = SRC_Q8_CP0;
+    else if (c.n_fft == 8 && c.cp_len == 2) *src = SRC_Q8_CP2;
+    else return (c.n_fft == 8 || c.n_fft == 16) && c.cp_len >= 0 && c.cp_len <= c.n_fft ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
+    return 0;
+}
+
+static int check_cfg(const ofdmgan_chan_cfg* c, int* n_snr) {
+    if (!c) return OFDMGAN_E_ARG;
+    if (c->normalize < 0 || c->normalize > 2 || c->ifft_scale < 0 || c->ifft_scale > 1 || c->pilot_spacing < 0) return OFDMGAN_E_ARG;
+    if ((c->impair & OFDMGAN_IMPAIR_PA) && !(c->pa_saturation > 0.f && c->pa_smoothness > 0.f)) return OFDMGAN_E_ARG;
+    if (c->snr_mode == OFDMGAN_SNR_GRID) {
+        if (c->n_snr < 1 || c->n_snr > OFDMGAN_MAX_SNR_BINS || c->frames_per_snr < 1) return OFDMGAN_E_ARG;
+        *n_snr = c->n_snr;
+    } else if (c->snr_mode == OFDMGAN_SNR_UNIFORM) {
+        *n_snr = 1;
+    } else {
+        return OFDMGAN_E_ARG;
+    }
+    return 0;
+}
+
+static int launch_sim(int src, int grid, cudaStream_t s, const SimArgs& a) {
+    switch (src) {
+        case SRC_GAUSS: k_sim<SRC_GAUSS><<<grid, OG_THREADS, 0, s>>>(a); break;
+        case SRC_Q16_CP0: k_sim<SRC_Q16_CP0><<<grid, OG_THREADS, 0, s>>>(a); break;
+        case SRC_Q16_CP2: k_sim<SRC_Q16_CP2><<<grid, OG_THREADS, 0, s>>>(a); break;
+        case SRC_Q8_CP0: k_sim<SRC_Q8_CP0><<<grid, OG_THREADS, 0, s>>>(a); break;
+        case SRC_Q8_CP2: k_sim<SRC_Q8_CP2><<<grid, OG_THREADS, 0, s>>>(a); break;
+        default: return OFDMGAN_E_ARG;
+    }
+    return (int)cudaGetLastError();
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace og
+
+using namespace og;
+
+extern "C" {
+
+int ofdmgan_gen_fwd_f32(const float* x_dev, const float* gparams258, float* y_dev, int64_t B, float leaky_slope, void* stream) {
+    if (!x_dev || !y_dev || !gparams258 || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int slot, rc;
+    if ((rc = slot_for_stream(s, &slot))) return rc;
+    if ((rc = upload_g(gparams258, slot, s))) return rc;
+    k_gen_fwd_f32<<<grid_for(B, OG_THREADS, 4), OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, leaky_slope);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_gen_fwd_q(const int16_t* x_dev, const int8_t* wrom_host, const int16_t* brom_host, int16_t* y_dev, int64_t B,
+                      int mode, uint64_t* digest_dev, void* stream) {
+    if (!x_dev || !y_dev || !wrom_host || !brom_host || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
+    if (mode != OFDMGAN_GEN_Q_SPEC && mode != OFDMGAN_GEN_Q_RTL) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int slot, rc;
+    if ((rc = slot_for_stream(s, &slot))) return rc;
+    if ((rc = upload_q(wrom_host, brom_host, slot, s))) return rc;
+    const int grid = grid_for(B, OG_THREADS, 4);
+    if (mode == OFDMGAN_GEN_Q_SPEC)
+        k_gen_fwd_q<OFDMGAN_GEN_Q_SPEC><<<grid, OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, (unsigned long long*)digest_dev);
+    else
+        k_gen_fwd_q<OFDMGAN_GEN_Q_RTL><<<grid, OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, (unsigned long long*)digest_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_quantize_q88(const float* x_dev, int16_t* q_dev, int64_t n, void* stream) {
+    if (!x_dev || !q_dev || n < 0) return OFDMGAN_E_ARG;
+    if (n == 0) return 0;
+    k_quantize_q88<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x_dev, q_dev, n);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_dequantize_q88(const int16_t* q_dev, float* x_dev, int64_t n, void* stream) {
+    if (!x_dev || !q_dev || n < 0) return OFDMGAN_E_ARG;
+    if (n == 0) return 0;
+    k_dequantize_q88<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(q_dev, x_dev, n);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_chan_sim(const ofdmgan_chan_cfg* cfg_host, const ofdmgan_chan_rand* rand_host, uint64_t seed, uint64_t frame0,
+                     float* clean_dev, float* noisy_dev, float* snr_dev, int64_t B, void* stream) {
+    int n_snr, src, rc;
+    if ((rc = check_cfg(cfg_host, &n_snr))) return rc;
+    if ((rc = src_of(*cfg_host, &src))) return rc;
+    if (B < 0 || (clean_dev && !aligned16(clean_dev)) || (noisy_dev && !aligned16(noisy_dev))) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    SimArgs a{};
+    a.cfg = *cfg_host;
+    a.keys = philox_keys(seed);
+    a.frame0 = frame0;
+    a.B = B;
+    if (rand_host) { a.sym = rand_host->sym; a.bits = rand_host->bits; a.pn = rand_host->pn; a.snr_db = rand_host->snr_db; a.noise = rand_host->noise; }
+    a.clean = clean_dev; a.noisy = noisy_dev; a.snr_out = snr_dev;
+    a.gen_kind = -1;
+    a.n_snr = n_snr;
+    return launch_sim(src, grid_for(B, OG_THREADS, 4), (cudaStream_t)stream, a);
+}
+
+int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t frame0, float* sym_dev, uint32_t* bits_dev,
+                       float* pn_dev, float* snr_db_dev, float* noise_dev, int64_t B, void* stream) {
+    if (!cfg_host || B < 0) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    SimArgs a{};
+    a.cfg = *cfg_host;
+    a.keys = philox_keys(seed);
+    a.frame0 = frame0;
+    a.B = B;
+    k_chan_draws<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, sym_dev, bits_dev, pn_dev, snr_db_dev, noise_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_philox_blocks(uint64_t seed, uint64_t ctr0, uint32_t c2, uint32_t c3, uint32_t* out_dev, int64_t n, void* stream) {
+    if (!out_dev || n < 0) return OFDMGAN_E_ARG;
+    if (n == 0) return 0;
+    k_philox_blocks<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(philox_keys(seed), ctr0, c2, c3, out_dev, n);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_sim_gen_metrics(const ofdmgan_chan_cfg* cfg_host, int gen_kind, const float* gparams258, const int8_t* wrom_host,
+                            const int16_t* brom_host, float leaky_slope, uint64_t seed, uint64_t frame0, int64_t B,
+                            double* metrics_dev, void* stream) {
+    int n_snr, src, rc, slot;
+    if ((rc = check_cfg(cfg_host, &n_snr))) return rc;
+    if ((rc = src_of(*cfg_host, &src))) return rc;
+    if (!metrics_dev || B < 0 || gen_kind < OFDMGAN_GEN_F32 || gen_kind > OFDMGAN_GEN_Q_RTL) return OFDMGAN_E_ARG;
+    if (gen_kind == OFDMGAN_GEN_F32 ? !gparams258 : (!wrom_host || !brom_host)) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = slot_for_stream(s, &slot))) return rc;
+    if (gen_kind == OFDMGAN_GEN_F32) rc = upload_g(gparams258, slot, s); else rc = upload_q(wrom_host, brom_host, slot, s);
+    if (rc) return rc;
+    const int grid = grid_for(B, OG_THREADS, 4);
+    const int n = n_snr * NM * NC;
+    void* partials = nullptr;
+    if ((rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
+    SimArgs a{};
+    a.cfg = *cfg_host;
+    a.keys = philox_keys(seed);
+    a.frame0 = frame0;
+    a.B = B;
+    a.gen_kind = gen_kind;
+    a.wslot = slot;
+    a.slope = leaky_slope;
+    a.partials = (double*)partials;
+    a.n_snr = n_snr;
+    if ((rc = launch_sim(src, grid, s, a))) return rc;
+    k_reduce_partials<<<(n + 127) / 128, 128, 0, s>>>((const double*)partials, grid, n, metrics_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind, const float* gparams258_host,
+                                 const int8_t* wrom_host, const int16_t* brom_host, float leaky_slope, uint64_t seed,
+                                 uint64_t frame0, int64_t B, double* metrics_host, void* stream) {
+    int n_snr, rc, slot;
+    if ((rc = check_cfg(cfg_host, &n_snr))) return rc;
+    if (!metrics_host) return OFDMGAN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = slot_for_stream(s, &slot))) return rc;
+    const size_t bytes = (size_t)n_snr * NM * NC * sizeof(double);
+    void* mdev = nullptr;
+    if ((rc = scratch_for_slot(slot, bytes, 5, &mdev))) return rc;
+    OG_CHECK(cudaMemsetAsync(mdev, 0, bytes, s));
+    if ((rc = ofdmgan_sim_gen_metrics(cfg_host, gen_kind, gparams258_host, wrom_host, brom_host, leaky_slope, seed, frame0, B,
+                                      (double*)mdev, stream))) return rc;
+    double tmp[OFDMGAN_MAX_SNR_BINS * NM * NC];
+    OG_CHECK(cudaMemcpyAsync(tmp, mdev, bytes, cudaMemcpyDeviceToHost, s));
+    OG_CHECK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n_snr * NM * NC; ++i) metrics_host[i] += tmp[i];
+    return 0;
+}
+
+int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int32_t* bin_dev, int method, int n_snr, int64_t B,
+                          double* metrics_dev, void* stream) {
+    if (!est_dev || !ref_dev || !metrics_dev || B < 0 || method < 0 || method >= NM || n_snr < 1 || n_snr > OFDMGAN_MAX_SNR_BINS)
+        return OFDMGAN_E_ARG;
+    if (!aligned16(est_dev) || !aligned16(ref_dev)) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int slot, rc;
+    if ((rc = slot_for_stream(s, &slot))) return rc;
+    const int grid = grid_for(B, OG_THREADS, 4);
+    const int n = n_snr * NM * NC;
+    void* partials = nullptr;
+    if ((rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
+    OG_CHECK(cudaMemsetAsync(partials, 0, (size_t)grid * n * sizeof(double), s));
+    k_frame_metrics<<<grid, OG_THREADS, 0, s>>>(est_dev, ref_dev, bin_dev, method, n_snr, B, (double*)partials);
+    OG_CHECK(cudaGetLastError());
+    k_reduce_partials<<<(n + 127) / 128, 128, 0, s>>>((const double*)partials, grid, n, metrics_dev);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Constant-memory weight images and their stream-ordered refresh.  Included by every TU that runs a network
+// (each TU owns its own __constant__ bank, so each gets private copies of these symbols).
+//
+// G image (OG_G_IMG floats): raw enc1 / bottleneck weights + biases, and the two convolutions that follow a
+// nearest x2 upsample (dec1, out_conv; models/generator.py:196-205) FOLDED over the duplicated samples:
+//   z[2p]   = w0*a[p-1] + (w1+w2)*a[p]        z[2p+1] = (w0+w1)*a[p] + w2*a[p+1]
+// i.e. 4 folded taps {w0, w1+w2, w0+w1, w2} per (oc,ic) and 2 MACs per output instead of 3 (1344 instead of
+// 1728 MACs per frame).  The raw taps are kept too for the weight-gradient kernels.
+// D image (OG_D_IMG floats): the 521 raw critic parameters (models/discriminator.py:78-100).
+// Q image (OG_Q_IMG floats): the fixed-point generator ROM as exact floats: weights[0..225]/128, biases at 232.
+#pragma once
+#include "common.cuh"
+
+namespace og {
+
+// ---- G image layout
+constexpr int GI_ENC_W = 0;      // [4][2][3]
+constexpr int GI_ENC_B = 24;     // [4]
+constexpr int GI_BN_W = 28;      // [8][4][3]
+constexpr int GI_BN_B = 124;     // [8]
+constexpr int GI_DEC_F = 132;    // [4][8][4] folded
+constexpr int GI_DEC_B = 260;    // [4]
+constexpr int GI_OUT_F = 264;    // [2][4][4] folded
+constexpr int GI_OUT_B = 296;    // [2]
+constexpr int OG_G_IMG = 304;
+// raw parameter offsets (torch order, include/ofdmgan.h)
+constexpr int GP_ENC_W = 0, GP_ENC_B = 24, GP_BN_W = 28, GP_BN_B = 124, GP_DEC_W = 132, GP_DEC_B = 228, GP_OUT_W = 232,
+              GP_OUT_B = 256;
+constexpr int DP_C1_W = 0, DP_C1_B = 96, DP_C2_W = 104, DP_C2_B = 488, DP_FC_W = 504, DP_FC_B = 520;
+constexpr int OG_D_IMG = 528;
+constexpr int OG_Q_IMG = 256;
+constexpr int QI_BIAS = 232;
+
+__constant__ __align__(16) float c_g[OG_NSLOT][OG_G_IMG];
+__constant__ __align__(16) float c_d[OG_NSLOT][OG_D_IMG];
+__constant__ __align__(16) float c_q[OG_NSLOT][OG_Q_IMG];
+
+__global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
+    int i = threadIdx.x;
+    if (i < 132) { img[i] = p[i]; return; }                               // enc1 + bottleneck, verbatim
+    if (i < 132 + 128) {                                                  // dec1 folded
+        int j = i - 132, pair = j >> 2, t = j & 3;
+        const float* w = p + GP_DEC_W + pair * 3;
+        img[i] = t == 0 ? w[0] : t == 1 ? w[1] + w[2] : t == 2 ? w[0] + w[1] : w[2];
+        return;
+    }
+    if (i < 264) { img[i] = p[GP_DEC_B + (i - 260)]; return; }
+    if (i < 296) {
+        int j = i - 264, pair = j >> 2, t = j & 3;
+        const float* w = p + GP_OUT_W + pair * 3;
+        img[i] = t == 0 ? w[0] : t == 1 ? w[1] + w[2] : t == 2 ? w[0] + w[1] : w[2];
+        return;
+    }
+    if (i < 298) { img[i] = p[GP_OUT_B + (i - 296)]; return; }
+    if (i < OG_G_IMG) img[i] = 0.f;
+}
+
+__global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
+    int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i < OG_D_IMG) img[i] = i < OFDMGAN_D_NPARAMS ? p[i] : 0.f;
+}
+
+// params258 may be a host or a device pointer
+static int upload_g(const float* params258, int slot, cudaStream_t s) {
+    const float* dev = nullptr;
+    int rc = to_device_f32(params258, OFDMGAN_G_NPARAMS, slot, 0, s, &dev);
+    if (rc) return rc;
+    void* img = nullptr;
+    rc = scratch_for_slot(slot, OG_G_IMG * sizeof(float), 1, &img);
+    if (rc) return rc;
+    prep_g_image<<<1, OG_G_IMG, 0, s>>>(dev, (float*)img);
+    OG_CHECK(cudaGetLastError());
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_g, img, OG_G_IMG * sizeof(float), (size_t)slot * OG_G_IMG * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+static int upload_d(const float* params521, int slot, cudaStream_t s) {
+    const float* dev = nullptr;
+    int rc = to_device_f32(params521, OFDMGAN_D_NPARAMS, slot, 2, s, &dev);
+    if (rc) return rc;
+    void* img = nullptr;
+    rc = scratch_for_slot(slot, OG_D_IMG * sizeof(float), 3, &img);
+    if (rc) return rc;
+    prep_d_image<<<1, OG_D_IMG, 0, s>>>(dev, (float*)img);
+    OG_CHECK(cudaGetLastError());
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_d, img, OG_D_IMG * sizeof(float), (size_t)slot * OG_D_IMG * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ROMs are host pointers (weight_rom.v layout): converted on the host, exact (int8/128 and int16 are fp32-exact)
+static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot, cudaStream_t s) {
+    float img[OG_Q_IMG];
+    for (int i = 0; i < OG_Q_IMG; ++i) img[i] = 0.f;
+    for (int i = 0; i < 226; ++i) img[i] = (float)wrom_host[i] * (1.0f / 128.0f);
+    for (int i = 0; i < 18; ++i) img[QI_BIAS + i] = (float)brom_host[i];
+    // pageable source: the runtime stages it before returning, so the stack buffer may die afterwards
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_q, img, sizeof img, (size_t)slot * sizeof img, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+}  // namespace og
