@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py - the headline measurement of the ofdm-gan-sr hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Primary line (BASELINE.json metric "OFDM frames/s: fused channel sim + G inference"): one step = one pass of the fused
+kernel (on-chip Philox channel simulation with the non-linear chain, SNR grid 0..30 dB, -> fp32 MiniGenerator -> EVM/MSE
+accumulation) over FRAMES_PER_GPU frames on every rank, sharded by global frame index, plus the final metric allreduce.
+`also` carries the other BASELINE configs measured in the same run: the Q1.7/Q8.8 integer generator over 2^24 HBM-resident
+frames (config 2) and the CWGAN-GP training step at 65,536 frames per GPU (config 3).
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, OpenMP over all host cores) on a bounded
+sample of the same workload: the reference is Python/NumPy/Verilog, nothing of it compiles into oracle/_ref.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 1 << 24           # frames per rank per step of the primary workload (weak scaling)
+Q_FRAMES = 1 << 24                 # BASELINE config 2
+TRAIN_FRAMES_PER_GPU = 65536       # BASELINE config 3
+FLOP_SIM = 900                     # nominal channel-sim FLOP per frame (Philox integer work not credited)
+FLOP_GEN = 3456                    # 2 x 1728 MAC, models/generator.py:227-233
+FLOP_TRAIN = 311424                # 5 x 57,504 + 23,904 per sample, SURVEY.md 8(d)
+Q_BYTES = 128                      # int16 frame in + out
+WORKLOAD = dict(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7,
+                frames_per_snr=1 << 10)
+WORKLOAD_NAME = ("C4: Gaussian-symbol OFDM 2x16 frames, ifft*sqrt(N), Rapp PA (A=0.8,p=3) + IQ imbalance (1 dB, 5 deg) + "
+                 "phase noise (-80 dBc/Hz) + AWGN on an SNR grid 0..30 dB step 5, joint normalisation, fp32 MiniGenerator "
+                 "inference, per-SNR MSE/EVM accumulation; 2^24 frames per GPU per step, generated on-chip (Philox4x32-10)")
+
+
+def seed_params():
+    """Deterministic Xavier-like random-init weights of the two architectures (no checkpoints offline)."""
+    rng = np.random.default_rng(0)
+    gp = np.zeros(258, np.float32)
+    for off, (oc, ic) in ((0, (4, 2)), (28, (8, 4)), (132, (4, 8)), (232, (2, 4))):
+        a = np.sqrt(6.0 / (ic * 3 + oc * 3))
+        gp[off:off + oc * ic * 3] = rng.uniform(-a, a, oc * ic * 3)
+    dp = np.zeros(521, np.float32)
+    for off, (oc, ic, k) in ((0, (8, 4, 3)), (104, (16, 8, 3)), (504, (1, 16, 1))):
+        a = np.sqrt(6.0 / (ic * k + oc * k))
+        dp[off:off + oc * ic * k] = rng.uniform(-a, a, oc * ic * k)
+    return gp, dp
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_uuid):
+        self.rows, self.proc, self.uuid = [], None, gpu_uuid
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    """CPU restatement of the reference path on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle
+    gp, _ = seed_params()
+    cfg = oracle.make_cfg(**WORKLOAD)
+    cores = os.cpu_count()
+    t0 = time.perf_counter()
+    oracle.sim_gen_metrics(cfg, 0, 1 << 17, gparams=gp, seed=1)
+    rate = (1 << 17) / (time.perf_counter() - t0)
+    budget = 90.0 / (args.steps + args.warmup)                 # whole run ~1.5 min
+    sample = int(min(FRAMES_PER_GPU, max(1 << 16, 1 << int(np.log2(max(rate * budget, 1.0))))))
+    for _ in range(args.warmup):
+        oracle.sim_gen_metrics(cfg, 0, sample, gparams=gp, seed=1)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        oracle.sim_gen_metrics(cfg, 0, sample, gparams=gp, seed=1, frame0=s * sample)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "OFDM frames/s: fused channel sim + G inference", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 channel / f32 generator",
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "frames_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} frames per step of the same workload (oracle/channel.c + fp32_models.c, OpenMP)"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--skip-also", action="store_true", help="primary workload only (used under ncu)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ofdm_gan_sr_b200 as pkg
+    from ofdm_gan_sr_b200.train_step import CWGANGPStep
+    ops = pkg.ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: libofdmgan has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    gp_h, dp_h = seed_params()
+    gp_d = torch.as_tensor(gp_h).to(dev)
+    cfg = ops.make_cfg(**WORKLOAD)
+    F = args.frames_per_gpu
+    K, W = args.steps, args.warmup
+    hbm_peak, peak_src, sm_max = measured_peaks()
+
+    # ---- primary: fused sim + G + metrics, device-resident weights and accumulator
+    table = torch.zeros(7, pkg._lib.N_METHODS, pkg._lib.METRIC_COLS, dtype=torch.float64, device=dev)
+
+    def fused_step(s):
+        table.zero_()
+        ops.sim_gen_metrics(cfg, F, gparams=gp_d, seed=1, frame0=(s * world + rank) * F, out=table)
+        if world > 1:
+            dist.all_reduce(table)                               # the sweep's only exchange: < 2 KB
+
+    for s in range(W):
+        fused_step(s)
+    barrier()
+    uuid = str(getattr(torch.cuda.get_device_properties(dev), "uuid", "")) or str(local_rank)
+    clocks = ClockSampler(uuid if uuid.startswith("GPU-") or uuid.isdigit() else "GPU-" + uuid)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for s in range(K):
+        fused_step(W + s)
+        ev[s + 1].record()
+    barrier()
+    ms_total = max_over_ranks(ev[0].elapsed_time(ev[K]))
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = F * world / (ms_step * 1e-3)
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    n_frames_seen = float(table[:, :2, 0].sum().item())
+    assert n_frames_seen == 2.0 * F * world, "metric table does not account for every frame"
+
+    # ---- e2e: the host-buffer C-ABI call (weights from host memory in, metric table to host memory out), every step
+    def e2e_step(s):
+        out = ops.sim_gen_metrics_host(cfg, F, gparams=gp_h, seed=1, frame0=(s * world + rank) * F)
+        if world > 1:
+            t = torch.as_tensor(out).to(dev)
+            dist.all_reduce(t)
+            out = t.cpu().numpy()
+        return out
+
+    for s in range(2):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        e2e_step(2 + s)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = F * world * K / e2e_s
+    h2d = 258 * 4
+    d2h = 7 * pkg._lib.N_METHODS * pkg._lib.METRIC_COLS * 8
+
+    # ---- FP32 issue-rate peak measured in the same run (denominator of the fp32 roofline)
+    ffma = ops.ffma_peak(8192, device=dev)
+    flop_frame = FLOP_SIM + FLOP_GEN
+    achieved = F * flop_frame / (float(np.mean(per_step_ms)) * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma, "traffic": None,
+                "kernel": "og::k_sim<SRC_GAUSS>", "algorithmic_flop_per_frame": flop_frame, "frames_per_launch": F,
+                "peak_source": "FFMA issue-rate microbenchmark ofdmgan_ffma_peak, same run (148 SMs x 128 lanes x 2 flop x clock)",
+                "note": "inputs are generated on-chip and outputs reduced on-chip: HBM traffic per launch is the per-CTA metric "
+                        "partials only, so the binding roofline is the FP32/INT issue rate, not HBM (BASELINE.json north_star)",
+                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src}
+
+    also = {}
+    launches = K * 3                                             # prep_g_image + k_sim + k_reduce_partials per step
+    if not args.skip_also:
+        # ---- config 2: integer generator over 2^24 HBM-resident frames (1 GPU worth per rank)
+        g = torch.Generator(device=dev).manual_seed(1 + rank)
+        xq = ops.quantize_q88(torch.randn(Q_FRAMES, 2, 16, generator=g, device=dev).clamp_(-4, 4))
+        rng = np.random.default_rng(5)
+        Wrom = np.zeros(2048, np.int8)
+        Wrom[:224] = np.clip(np.rint(rng.standard_normal(224) * 40), -128, 127)
+        Brom = np.zeros(64, np.int16)
+        Brom[:18] = rng.integers(-64, 64, 18)
+        for mode, tag in ((ops.GEN_Q_SPEC, "spec"), (ops.GEN_Q_RTL, "rtl_literal")):
+            for _ in range(3):
+                yq = ops.gen_fwd_q(xq, Wrom, Brom, mode=mode)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                yq = ops.gen_fwd_q(xq, Wrom, Brom, mode=mode)      # 2 GiB of traffic per launch >> 126 MB L2
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / K
+            gbs = Q_FRAMES * Q_BYTES / (ms * 1e-3) / 1e9
+            also["fixed_point_" + tag] = {"frames_per_s": Q_FRAMES * world / (ms * 1e-3), "ms_per_launch": ms, "frames": Q_FRAMES,
+                                          "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak}
+        del xq, yq
+        # ---- config 3: CWGAN-GP step, 65,536 frames per GPU, data-parallel
+        Bt = TRAIN_FRAMES_PER_GPU
+        tcfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
+        clean, noisy, _ = ops.chan_sim(tcfg, Bt, seed=0, frame0=rank * Bt, device=dev)
+        trainer = CWGANGPStep(gp_h, dp_h, device=dev)
+        for _ in range(3):
+            trainer.step(clean, noisy)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            trainer.step(clean, noisy)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / K
+        st = trainer.stats()
+        assert np.isfinite(st["d_loss"]) and np.isfinite(st["g_loss"])
+        tflops = Bt * FLOP_TRAIN / (ms * 1e-3) / 1e12
+        # end to end: the batch comes from pinned host memory every step, the statistics go back to the host
+        hc, hn = clean.cpu().pin_memory(), noisy.cpu().pin_memory()
+        dc, dn = torch.empty_like(clean), torch.empty_like(noisy)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            dc.copy_(hc, non_blocking=True)
+            dn.copy_(hn, non_blocking=True)
+            trainer.step(dc, dn)
+            trainer.stats()
+        barrier()
+        e2e_train = Bt * world * K / max_over_ranks(time.perf_counter() - t0)
+        also["train"] = {"samples_per_s": Bt * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": Bt, "n_critic": 5,
+                         "fp32_tflops_per_gpu": tflops, "fp32_frac_of_ffma_peak": tflops / ffma,
+                         "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
+                         "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"]}
+        launches += 2 * K * 2 + K * trainer.launches_per_step()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        import oracle                                            # checker / CPU baseline leg only
+        ocfg = oracle.make_cfg(**WORKLOAD)
+        t0 = time.perf_counter()
+        oracle.sim_gen_metrics(ocfg, 0, 1 << 17, gparams=gp_h, seed=1)
+        rate = (1 << 17) / (time.perf_counter() - t0)
+        sample = int(min(1 << 25, max(1 << 17, 1 << int(np.log2(max(rate * 12.0, 1.0))))))
+        t0 = time.perf_counter()
+        om = oracle.sim_gen_metrics(ocfg, 0, sample, gparams=gp_h, seed=1)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sample / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{sample} frames of the same workload, oracle/channel.c + fp32_models.c with OpenMP on all host cores"}
+        # the same sample through the GPU path must tell the same story (parity spot check inside the bench)
+        gm = ops.sim_gen_metrics(cfg, sample, gparams=gp_d, seed=1).cpu().numpy()
+        assert np.array_equal(gm[:, :2, 0], om[:, :2, 0])
+        assert np.allclose(gm[:, :2, 3], om[:, :2, 3], rtol=1e-4), "GPU and CPU sweeps disagree"
+
+    if rank == 0:
+        line = {"metric": "OFDM frames/s: fused channel sim + G inference", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAME, "frames_per_gpu_per_step": F, "parallelism": f"frame-sharded x{world}",
+                           "l2": "no HBM inputs: frames are generated on-chip from Philox counters and reduced on-chip",
+                           "weights": "random-init (Xavier-uniform, seed 0)"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "ofdmgan_sim_gen_metrics_host (host weights in, host metric table out, synchronous)"},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "also": also,
+                "per_step_ms": per_step_ms}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

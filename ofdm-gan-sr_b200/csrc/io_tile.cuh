@@ -32,6 +32,46 @@ __device__ __forceinline__ void tile_load_f32(const float* __restrict__ g, int64
     __syncwarp();
 }
 
+// Two-phase variant for kernels that keep the warp's tile resident in shared memory and re-read a frame whenever it
+// is needed again (cheaper than holding 32 more registers live across a backward pass).
+__device__ __forceinline__ void tile_fill_f32(const float* __restrict__ g, int64_t frame_base, int64_t B, float4* wsm, int lane) {
+    const float4* src = reinterpret_cast<const float4*>(g) + frame_base * 8;
+    const int64_t limit = (B - frame_base) * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int idx = r * 32 + lane, f = idx >> 3, c = idx & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < limit) v = __ldg(src + idx);
+        wsm[f * 8 + (c ^ (f & 7))] = v;
+    }
+}
+__device__ __forceinline__ void tile_read_f32(const float4* wsm, int lane, float (&x)[2][16]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 v = wsm[lane * 8 + (c ^ (lane & 7))];
+        const int row = c >> 2, col = (c & 3) * 4;
+        x[row][col] = v.x; x[row][col + 1] = v.y; x[row][col + 2] = v.z; x[row][col + 3] = v.w;
+    }
+}
+// the thread's own frame back into its resident tile (e.g. the generator output the critic pass re-reads)
+__device__ __forceinline__ void tile_write_f32(float4* wsm, int lane, const float (&y)[2][16]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int row = c >> 2, col = (c & 3) * 4;
+        wsm[lane * 8 + (c ^ (lane & 7))] = make_float4(y[row][col], y[row][col + 1], y[row][col + 2], y[row][col + 3]);
+    }
+}
+// resident tile -> HBM, coalesced
+__device__ __forceinline__ void tile_drain_f32(float* __restrict__ g, int64_t frame_base, int64_t B, const float4* wsm, int lane) {
+    float4* dst = reinterpret_cast<float4*>(g) + frame_base * 8;
+    const int64_t limit = (B - frame_base) * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int idx = r * 32 + lane, f = idx >> 3, c = idx & 7;
+        if (idx < limit) dst[idx] = wsm[f * 8 + (c ^ (f & 7))];
+    }
+}
+
 __device__ __forceinline__ void tile_store_f32(float* __restrict__ g, int64_t frame_base, int64_t B, float4* wsm, int lane,
                                                const float (&y)[2][16]) {
 #pragma unroll

@@ -31,11 +31,11 @@ constexpr int OG_D_IMG = 528;
 constexpr int OG_Q_IMG = 256;
 constexpr int QI_BIAS = 232;
 
-__constant__ __align__(16) float c_g[OG_NSLOT][OG_G_IMG];
-__constant__ __align__(16) float c_d[OG_NSLOT][OG_D_IMG];
-__constant__ __align__(16) float c_q[OG_NSLOT][OG_Q_IMG];
+static __constant__ __align__(16) float c_g[OG_NSLOT][OG_G_IMG];
+static __constant__ __align__(16) float c_d[OG_NSLOT][OG_D_IMG];
+static __constant__ __align__(16) float c_q[OG_NSLOT][OG_Q_IMG];
 
-__global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
+static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
     int i = threadIdx.x;
     if (i < 132) { img[i] = p[i]; return; }                               // enc1 + bottleneck, verbatim
     if (i < 132 + 128) {                                                  // dec1 folded
@@ -55,7 +55,7 @@ __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ im
     if (i < OG_G_IMG) img[i] = 0.f;
 }
 
-__global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
+static __global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
     int i = threadIdx.x + blockIdx.x * blockDim.x;
     if (i < OG_D_IMG) img[i] = i < OFDMGAN_D_NPARAMS ? p[i] : 0.f;
 }

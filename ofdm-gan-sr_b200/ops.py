@@ -1,0 +1,330 @@
+"""Functional layer over the C ABI (include/ofdmgan.h): torch CUDA tensors in, torch CUDA tensors out, every call
+asynchronous on torch's current stream.  No CPU path - a CPU tensor raises OfdmGanError."""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (CRITIC_OUT, D_NPARAMS, G_NPARAMS, GEN_F32, GEN_OUT, GEN_Q_RTL, GEN_Q_SPEC, METRIC_COLS, N_METHODS,
+                   ChanCfg, ChanRand, OfdmGanError, check, dptr, frames, stream_ptr)
+
+SYM_GAUSSIAN, SYM_QPSK = 0, 1
+SCALE_SQRT_N, SCALE_N = 0, 1
+IMPAIR_PA, IMPAIR_IQ, IMPAIR_PN = 1, 2, 4
+SNR_UNIFORM, SNR_GRID = 0, 1
+NORM_NONE, NORM_JOINT, NORM_SEPARATE = 0, 1, 2
+
+
+def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j, ifft_scale=SCALE_SQRT_N,
+             nonlinear=False, pa=None, iq=None, pn=None, pa_saturation=1.0, pa_smoothness=3.0, iq_imbalance_db=1.0,
+             iq_phase_deg=5.0, phase_noise_dbchz=-80.0, sample_rate=1e6, snr_mode=SNR_UNIFORM, snr_lo=0.0, snr_hi=30.0,
+             snr_step=5.0, n_snr=1, frames_per_snr=1, normalize=NORM_JOINT):
+    """ChanCfg from the reference's user-facing parameters: SyntheticOFDMDataset.__init__ (utils/dataset.py:195-206),
+    NonLinearImpairments defaults (utils/ofdm_utils.py:394-521), run_benchmark's SNR grid
+    (benchmark_comparison.py:179-182)."""
+    pa = nonlinear if pa is None else pa
+    iq = nonlinear if iq is None else iq
+    pn = nonlinear if pn is None else pn
+    c = ChanCfg()
+    c.symbol_source, c.n_fft, c.cp_len, c.pilot_spacing = symbol_source, n_fft, cp_len, pilot_spacing
+    c.pilot_re, c.pilot_im = float(np.real(pilot)), float(np.imag(pilot))
+    c.ifft_scale = ifft_scale
+    c.impair = (IMPAIR_PA if pa else 0) | (IMPAIR_IQ if iq else 0) | (IMPAIR_PN if pn else 0)
+    c.pa_saturation, c.pa_smoothness = pa_saturation, pa_smoothness
+    c.iq_gain = 10.0 ** (iq_imbalance_db / 20.0)
+    phi = math.radians(iq_phase_deg)
+    c.iq_cos, c.iq_sin = math.cos(phi), math.sin(phi)
+    c.pn_sigma = math.sqrt(10.0 ** (phase_noise_dbchz / 10.0) * sample_rate)
+    c.snr_mode, c.snr_lo, c.snr_hi, c.snr_step = snr_mode, snr_lo, snr_hi, snr_step
+    c.n_snr, c.frames_per_snr, c.normalize = n_snr, frames_per_snr, normalize
+    return c
+
+
+def _params(t, n, name):
+    """flat fp32 parameter vector: CUDA tensor (device pointer) or CPU tensor / ndarray (host pointer; the library
+    accepts either).  Returns (keepalive, c_void_p)."""
+    if isinstance(t, torch.Tensor):
+        t = t.detach()
+        if t.numel() != n:
+            raise OfdmGanError(f"{name}: expected {n} values, got {t.numel()}")
+        t = t.to(torch.float32).contiguous().view(-1)
+        return t, ctypes.c_void_p(t.data_ptr())
+    a = np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
+    if a.size != n:
+        raise OfdmGanError(f"{name}: expected {n} values, got {a.size}")
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _roms(wrom, brom):
+    W = np.ascontiguousarray(wrom, dtype=np.int8).reshape(-1)
+    Bq = np.ascontiguousarray(brom, dtype=np.int16).reshape(-1)
+    if W.size != 2048 or Bq.size != 64:
+        raise OfdmGanError("ROMs must be int8[2048] and int16[64] (weight_rom.v layout)")
+    return W, Bq
+
+
+def flatten_params(module):
+    """parameters() order, flattened (the packing of include/ofdmgan.h)."""
+    return torch.cat([p.detach().reshape(-1) for p in module.parameters()]).to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- generator
+def gen_fwd_f32(x, gparams, slope=0.2):
+    x = frames(x)
+    y = torch.empty_like(x)
+    keep, gp = _params(gparams, G_NPARAMS, "gparams")
+    check(_lib.lib().ofdmgan_gen_fwd_f32(dptr(x), gp, dptr(y), x.shape[0], slope, stream_ptr(x.device)))
+    return y
+
+
+def gen_bwd_f32(x, gparams, dy, slope=0.2, need_dx=True):
+    x, dy = frames(x), frames(dy)
+    dx = torch.empty_like(x) if need_dx else None
+    dparams = torch.empty(G_NPARAMS, dtype=torch.float32, device=x.device)
+    keep, gp = _params(gparams, G_NPARAMS, "gparams")
+    check(_lib.lib().ofdmgan_gen_bwd_f32(dptr(x), gp, dptr(dy), dptr(dx), dptr(dparams), x.shape[0], slope,
+                                         stream_ptr(x.device)))
+    return dx, dparams
+
+
+def gen_fwd_q(x_q88, wrom, brom, mode=GEN_Q_SPEC, want_digest=False):
+    x = frames(x_q88, torch.int16)
+    y = torch.empty_like(x)
+    W, Bq = _roms(wrom, brom)
+    digest = torch.zeros(2, dtype=torch.int64, device=x.device) if want_digest else None
+    check(_lib.lib().ofdmgan_gen_fwd_q(dptr(x), W.ctypes.data_as(ctypes.c_void_p), Bq.ctypes.data_as(ctypes.c_void_p),
+                                       dptr(y), x.shape[0], mode, dptr(digest), stream_ptr(x.device)))
+    if want_digest:
+        d = digest.cpu().numpy().view(np.uint64)
+        return y, (int(d[0]), int(d[1]))
+    return y
+
+
+def quantize_q88(x):
+    if not x.is_cuda:
+        raise OfdmGanError("quantize_q88 needs a CUDA tensor")
+    x = x.to(torch.float32).contiguous()
+    q = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    check(_lib.lib().ofdmgan_quantize_q88(dptr(x), dptr(q), x.numel(), stream_ptr(x.device)))
+    return q
+
+
+def dequantize_q88(q):
+    if not q.is_cuda:
+        raise OfdmGanError("dequantize_q88 needs a CUDA tensor")
+    q = q.to(torch.int16).contiguous()
+    x = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    check(_lib.lib().ofdmgan_dequantize_q88(dptr(q), dptr(x), q.numel(), stream_ptr(q.device)))
+    return x
+
+
+# ---------------------------------------------------------------------------------------------- channel
+def _dev(device):
+    device = torch.device("cuda" if device is None else device)
+    if device.type != "cuda":
+        raise OfdmGanError("libofdmgan has no CPU path: a CUDA device is required")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None, snr_db=None, noise=None,
+             want_clean=True, want_noisy=True, want_snr=True):
+    """frames frame0..frame0+B-1 of SyntheticOFDMDataset / run_benchmark -> (clean, noisy, snr) CUDA tensors.
+    Any of the draw tensors may be injected (host-generated randomness in the reference's draw order)."""
+    device = _dev(device)
+    with torch.cuda.device(device):
+        clean = torch.empty(B, 2, 16, dtype=torch.float32, device=device) if want_clean else None
+        noisy = torch.empty(B, 2, 16, dtype=torch.float32, device=device) if want_noisy else None
+        snr = torch.empty(B, dtype=torch.float32, device=device) if want_snr else None
+        rand = None
+        keep = []
+        if any(a is not None for a in (sym, bits, pn, snr_db, noise)):
+            def f32(a, shape):
+                if a is None:
+                    return None
+                t = torch.as_tensor(a).to(device=device, dtype=torch.float32).contiguous().view(*shape)
+                keep.append(t)
+                return t.data_ptr()
+            rand = ChanRand()
+            rand.sym = f32(sym, (B, 32))
+            rand.pn = f32(pn, (B, 16))
+            rand.snr_db = f32(snr_db, (B,))
+            rand.noise = f32(noise, (B, 32))
+            if bits is not None:
+                tb = torch.as_tensor(np.ascontiguousarray(bits, dtype=np.uint32).view(np.int32)).to(device).contiguous()
+                keep.append(tb)
+                rand.bits = tb.data_ptr()
+        check(_lib.lib().ofdmgan_chan_sim(ctypes.byref(cfg), ctypes.byref(rand) if rand is not None else None, seed, frame0,
+                                          dptr(clean), dptr(noisy), dptr(snr), B, stream_ptr(device)))
+        if keep:
+            torch.cuda.current_stream(device).synchronize()     # the injected buffers must outlive the launch
+    return clean, noisy, snr
+
+
+def chan_draws(cfg, B, seed=0, frame0=0, device=None):
+    device = _dev(device)
+    with torch.cuda.device(device):
+        sym = torch.empty(B, 32, dtype=torch.float32, device=device)
+        pn = torch.empty(B, 16, dtype=torch.float32, device=device)
+        noise = torch.empty(B, 32, dtype=torch.float32, device=device)
+        snr = torch.empty(B, dtype=torch.float32, device=device)
+        bits = torch.empty(B, dtype=torch.int32, device=device)
+        check(_lib.lib().ofdmgan_chan_draws(ctypes.byref(cfg), seed, frame0, dptr(sym), dptr(bits), dptr(pn), dptr(snr),
+                                            dptr(noise), B, stream_ptr(device)))
+    return dict(sym=sym, bits=bits, pn=pn, snr_db=snr, noise=noise)
+
+
+def philox_blocks(seed, ctr0, c2, c3, n, device=None):
+    device = _dev(device)
+    with torch.cuda.device(device):
+        out = torch.empty(n, 4, dtype=torch.int32, device=device)
+        check(_lib.lib().ofdmgan_philox_blocks(seed, ctr0, c2, c3, dptr(out), n, stream_ptr(device)))
+    return out
+
+
+def n_snr_of(cfg):
+    return cfg.n_snr if cfg.snr_mode == SNR_GRID else 1
+
+
+def sim_gen_metrics(cfg, B, gen_kind=GEN_F32, gparams=None, wrom=None, brom=None, slope=0.2, seed=0, frame0=0, device=None,
+                    out=None):
+    """Fused simulate -> reconstruct -> metrics for frames frame0..frame0+B-1; ADDS into `out`
+    (double [n_snr][N_METHODS][METRIC_COLS] on the device) and returns it."""
+    device = _dev(device)
+    with torch.cuda.device(device):
+        if out is None:
+            out = torch.zeros(n_snr_of(cfg), N_METHODS, METRIC_COLS, dtype=torch.float64, device=device)
+        keep, gp, W, Bq = None, None, None, None
+        if gen_kind == GEN_F32:
+            keep, gp = _params(gparams, G_NPARAMS, "gparams")
+        else:
+            W, Bq = _roms(wrom, brom)
+        check(_lib.lib().ofdmgan_sim_gen_metrics(
+            ctypes.byref(cfg), gen_kind, gp, None if W is None else W.ctypes.data_as(ctypes.c_void_p),
+            None if Bq is None else Bq.ctypes.data_as(ctypes.c_void_p), slope, seed, frame0, B, dptr(out), stream_ptr(device)))
+    return out
+
+
+def sim_gen_metrics_host(cfg, B, gen_kind=GEN_F32, gparams=None, wrom=None, brom=None, slope=0.2, seed=0, frame0=0,
+                         device=None, out=None):
+    """Same through host buffers (weights in, metric table out, synchronous): the end-to-end call."""
+    device = _dev(device)
+    if out is None:
+        out = np.zeros((n_snr_of(cfg), N_METHODS, METRIC_COLS), dtype=np.float64)
+    gp = W = Bq = None
+    if gen_kind == GEN_F32:
+        gp = np.ascontiguousarray(gparams.detach().cpu().numpy() if isinstance(gparams, torch.Tensor) else gparams,
+                                  dtype=np.float32).reshape(-1)
+        if gp.size != G_NPARAMS:
+            raise OfdmGanError("gparams: expected 258 values")
+    else:
+        W, Bq = _roms(wrom, brom)
+    vp = ctypes.c_void_p
+    with torch.cuda.device(device):
+        check(_lib.lib().ofdmgan_sim_gen_metrics_host(
+            ctypes.byref(cfg), gen_kind, None if gp is None else gp.ctypes.data_as(vp),
+            None if W is None else W.ctypes.data_as(vp), None if Bq is None else Bq.ctypes.data_as(vp), slope, seed, frame0, B,
+            out.ctypes.data_as(vp), stream_ptr(device)))
+    return out
+
+
+def frame_metrics(est, ref, bins=None, method=0, n_snr=1, out=None):
+    est, ref = frames(est), frames(ref)
+    if out is None:
+        out = torch.zeros(n_snr, N_METHODS, METRIC_COLS, dtype=torch.float64, device=est.device)
+    if bins is not None:
+        bins = bins.to(device=est.device, dtype=torch.int32).contiguous()
+    check(_lib.lib().ofdmgan_frame_metrics(dptr(est), dptr(ref), dptr(bins), method, n_snr, est.shape[0], dptr(out),
+                                           stream_ptr(est.device)))
+    return out
+
+
+def metrics_summary(m):
+    """accumulator rows -> mean/std of MSE and EVM(dB) with np.mean / np.std (population) semantics
+    (benchmark_comparison.py:253-259) and BER."""
+    m = np.asarray(m.cpu() if isinstance(m, torch.Tensor) else m, dtype=np.float64)
+    n = np.maximum(m[..., 0], 1.0)
+    mse, evm = m[..., 1] / n, m[..., 3] / n
+    return dict(n=m[..., 0], mse=mse, mse_std=np.sqrt(np.maximum(m[..., 2] / n - mse ** 2, 0.0)), evm=evm,
+                evm_std=np.sqrt(np.maximum(m[..., 4] / n - evm ** 2, 0.0)), ber=m[..., 5] / np.maximum(m[..., 6], 1.0))
+
+
+# ---------------------------------------------------------------------------------------------- critic
+def disc_fwd_f32(cand, cond, dparams, slope=0.2):
+    cand, cond = frames(cand), frames(cond)
+    score = torch.empty(cand.shape[0], dtype=torch.float32, device=cand.device)
+    keep, dp = _params(dparams, D_NPARAMS, "dparams")
+    check(_lib.lib().ofdmgan_disc_fwd_f32(dptr(cand), dptr(cond), dp, dptr(score), cand.shape[0], slope, stream_ptr(cand.device)))
+    return score
+
+
+def disc_bwd_f32(cand, cond, dparams, g, slope=0.2, need_dcand=True, need_dcond=True, need_dparams=True):
+    cand, cond = frames(cand), frames(cond)
+    g = g.to(torch.float32).contiguous().view(-1)
+    dcand = torch.empty_like(cand) if need_dcand else None
+    dcond = torch.empty_like(cond) if need_dcond else None
+    grads = torch.empty(D_NPARAMS, dtype=torch.float32, device=cand.device) if need_dparams else None
+    keep, dp = _params(dparams, D_NPARAMS, "dparams")
+    check(_lib.lib().ofdmgan_disc_bwd_f32(dptr(cand), dptr(cond), dp, dptr(g), dptr(dcand), dptr(dcond), dptr(grads),
+                                          cand.shape[0], slope, stream_ptr(cand.device)))
+    return dcand, dcond, grads
+
+
+def gradient_penalty(real, fake, cond, dparams, alpha=None, seed=0, sample0=0, alpha_iter=0, slope=0.2, need_dparams=True):
+    real, fake, cond = frames(real), frames(fake), frames(cond)
+    if alpha is not None:
+        alpha = alpha.to(torch.float32).contiguous().view(-1)
+    gp = torch.empty(1, dtype=torch.float32, device=real.device)
+    grads = torch.empty(D_NPARAMS, dtype=torch.float32, device=real.device) if need_dparams else None
+    keep, dp = _params(dparams, D_NPARAMS, "dparams")
+    check(_lib.lib().ofdmgan_gradient_penalty(dptr(real), dptr(fake), dptr(cond), dptr(alpha), seed, sample0, alpha_iter, dp,
+                                              dptr(gp), dptr(grads), real.shape[0], slope, stream_ptr(real.device)))
+    return gp, grads
+
+
+def critic_step(clean, noisy, fake, dparams, alpha=None, seed=0, sample0=0, alpha_iter=0, gp_weight=10.0, slope=0.2,
+                b_global=None, out=None):
+    """-> out[528] = grad[521] (local sum / B_global), stats[5] (d_loss, wasserstein, gp, d_real, d_fake), 2 pad."""
+    clean, noisy, fake = frames(clean), frames(noisy), frames(fake)
+    if alpha is not None:
+        alpha = alpha.to(torch.float32).contiguous().view(-1)
+    if out is None:
+        out = torch.empty(CRITIC_OUT, dtype=torch.float32, device=clean.device)
+    B = clean.shape[0]
+    keep, dp = _params(dparams, D_NPARAMS, "dparams")
+    check(_lib.lib().ofdmgan_critic_step(dptr(clean), dptr(noisy), dptr(fake), dptr(alpha), seed, sample0, alpha_iter, dp,
+                                         gp_weight, slope, B, B if b_global is None else b_global, dptr(out),
+                                         stream_ptr(clean.device)))
+    return out
+
+
+def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, slope=0.2, b_global=None, out=None,
+             fake_out=None):
+    """-> out[264] = grad[258] (local sum / B_global), stats[3] (g_loss, adv, rec), 3 pad."""
+    clean, noisy = frames(clean), frames(noisy)
+    if out is None:
+        out = torch.empty(GEN_OUT, dtype=torch.float32, device=clean.device)
+    B = clean.shape[0]
+    keepd, dp = _params(dparams, D_NPARAMS, "dparams")
+    keepg, gp = _params(gparams, G_NPARAMS, "gparams")
+    check(_lib.lib().ofdmgan_gen_step(dptr(clean), dptr(noisy), dp, gp, adv_weight, rec_weight, slope, B,
+                                      B if b_global is None else b_global, dptr(out), dptr(fake_out), stream_ptr(clean.device)))
+    return out
+
+
+def adam(p, m, v, g, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """In-place fused Adam on flat fp32 CUDA vectors (torch.optim.Adam semantics, train.py:114-127)."""
+    n = p.numel()
+    check(_lib.lib().ofdmgan_adam(dptr(p), dptr(m), dptr(v), dptr(g), n, lr, beta1, beta2, eps, step, grad_scale,
+                                  stream_ptr(p.device)))
+
+
+def ffma_peak(iters=4096, device=None):
+    device = _dev(device)
+    out = ctypes.c_double(0)
+    with torch.cuda.device(device):
+        check(_lib.lib().ofdmgan_ffma_peak(iters, ctypes.byref(out), stream_ptr(device)))
+    return out.value

@@ -1,0 +1,110 @@
+"""The CWGAN-GP optimisation step of the reference trainer (train.py:201-344: n_critic x train_discriminator, then
+train_generator), as fused libofdmgan launches on flat parameter vectors, data-parallel over torch.distributed.
+
+Per step and per rank:  1 generator forward (the reference recomputes the same G(noisy) in each of the 5 critic
+iterations, train.py:225-226,333-334 - it is computed once here), n_critic x [critic_step -> allreduce(528 floats)
+-> Adam(521)], then gen_step -> allreduce(264 floats) -> Adam(258).  Loss statistics ride in the same buffers as the
+gradients, so a step needs no device->host synchronisation; `stats()` fetches them with one copy when asked.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import CRITIC_OUT, D_NPARAMS, G_NPARAMS, GEN_OUT, OfdmGanError
+
+
+class CWGANGPStep:
+    """State: flat generator / critic parameters + Adam moments on one CUDA device.
+
+    Hyper-parameters and their defaults follow CWGANGPTrainer._setup_config (train.py:146-185) and config/config.yaml:
+    Adam(lr 2e-4, betas (0.0, 0.9), eps 1e-8), n_critic 5, gp_weight 10, rec_weight 100, adv_weight 1.
+    """
+
+    def __init__(self, gparams, dparams, lr_g=2e-4, lr_d=2e-4, betas=(0.0, 0.9), eps=1e-8, n_critic=5, gp_weight=10.0,
+                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise OfdmGanError("CWGANGPStep needs a CUDA device (libofdmgan has no CPU path)")
+        f = lambda t, n: self._flat(t, n)
+        self.g, self.d = f(gparams, G_NPARAMS), f(dparams, D_NPARAMS)
+        z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.g_m, self.g_v, self.d_m, self.d_v = z(G_NPARAMS), z(G_NPARAMS), z(D_NPARAMS), z(D_NPARAMS)
+        self.lr_g, self.lr_d, self.betas, self.eps = lr_g, lr_d, tuple(betas), eps
+        self.n_critic, self.gp_weight, self.rec_weight, self.adv_weight = n_critic, gp_weight, rec_weight, adv_weight
+        self.slope, self.seed = leaky_slope, seed
+        self.group = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.rank = dist.get_rank(process_group) if self.distributed else 0
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        self.d_steps = self.g_steps = 0
+        self._dout = torch.zeros(max(n_critic, 1), CRITIC_OUT, dtype=torch.float32, device=self.device)
+        self._gout = torch.zeros(GEN_OUT, dtype=torch.float32, device=self.device)
+        self._fake = None
+
+    def _flat(self, t, n):
+        if isinstance(t, torch.nn.Module):
+            t = ops.flatten_params(t)
+        t = torch.as_tensor(t, dtype=torch.float32).detach().reshape(-1).to(self.device).clone()
+        if t.numel() != n:
+            raise OfdmGanError(f"expected {n} parameters, got {t.numel()}")
+        return t
+
+    # ---- parameters <-> nn.Module (state_dict order, train.py:413-424 checkpoints stay interchangeable)
+    def store_to(self, generator=None, discriminator=None):
+        for vec, mod in ((self.g, generator), (self.d, discriminator)):
+            if mod is None:
+                continue
+            off = 0
+            with torch.no_grad():
+                for p in mod.parameters():
+                    p.copy_(vec[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+
+    def load_from(self, generator=None, discriminator=None):
+        if generator is not None:
+            self.g.copy_(ops.flatten_params(generator).to(self.device))
+        if discriminator is not None:
+            self.d.copy_(ops.flatten_params(discriminator).to(self.device))
+
+    def _allreduce(self, buf):
+        if self.distributed:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, clean, noisy, alphas=None):
+        """One trainer iteration on this rank's shard of the batch (train.py:327-344).
+
+        clean, noisy: [B_local,2,16] CUDA tensors.  alphas (optional, [n_critic,B_local]): the torch.rand draws of
+        compute_gradient_penalty for parity runs; by default alpha comes from Philox(seed, global sample index,
+        critic-step counter), so the global batch does not depend on the number of ranks.
+        """
+        B = clean.shape[0]
+        Bg = B * self.world
+        self._fake = ops.gen_fwd_f32(noisy, self.g, self.slope)
+        for c in range(self.n_critic):
+            out = self._dout[c]
+            ops.critic_step(clean, noisy, self._fake, self.d, alpha=None if alphas is None else alphas[c], seed=self.seed,
+                            sample0=self.rank * B, alpha_iter=self.d_steps, gp_weight=self.gp_weight, slope=self.slope,
+                            b_global=Bg, out=out)
+            self._allreduce(out)
+            self.d_steps += 1
+            ops.adam(self.d, self.d_m, self.d_v, out, self.lr_d, self.betas[0], self.betas[1], self.eps, self.d_steps)
+        ops.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
+        self._allreduce(self._gout)
+        self.g_steps += 1
+        ops.adam(self.g, self.g_m, self.g_v, self._gout, self.lr_g, self.betas[0], self.betas[1], self.eps, self.g_steps)
+
+    def stats(self):
+        """The scalars train.py:255-261,301-305 log, from the last step: one device->host copy."""
+        d = self._dout[:, D_NPARAMS:D_NPARAMS + 5]
+        g = self._gout[G_NPARAMS:G_NPARAMS + 3]
+        packed = torch.cat([d.reshape(-1), g]).cpu()
+        last = packed[(self.n_critic - 1) * 5:self.n_critic * 5] if self.n_critic else torch.zeros(5)
+        gs = packed[self.n_critic * 5:]
+        return {"d_loss": float(last[0]), "wasserstein_distance": float(last[1]), "gradient_penalty": float(last[2]),
+                "d_real_mean": float(last[3]), "d_fake_mean": float(last[4]), "g_loss": float(gs[0]), "adv_loss": float(gs[1]),
+                "rec_loss": float(gs[2]), "critic_iterations": packed[:self.n_critic * 5].view(-1, 5).tolist()}
+
+    # kernels launched by one step() (for bench.py's gpu_launches): G fwd 2 (weight image + kernel), per critic iteration
+    # 4 (image, k_critic, finalize, adam), generator step 6 (2 images, k_gen_step, finalize, adam)... see DESIGN.md
+    def launches_per_step(self):
+        return 2 + self.n_critic * 4 + 5
