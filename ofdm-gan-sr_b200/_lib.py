@@ -6,7 +6,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libofdmgan.so")
+LIB_PATH = os.environ.get("OFDMGAN_LIB") or os.path.join(_HERE, "lib", "libofdmgan.so")
 _lib = None
 
 G_NPARAMS, D_NPARAMS = 258, 521

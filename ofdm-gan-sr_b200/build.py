@@ -11,11 +11,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "lib", "libofdmgan.so")
-UNITS = ["runtime.cu", "infer.cu", "train.cu"]
+# experiment hooks: OG_NVCC_FLAGS adds compiler flags (e.g. -DOG_SIM_MINB=4), OG_VARIANT names a side build that leaves
+# the default library untouched (lib/libofdmgan_<variant>.so, selected at run time with OFDMGAN_LIB=<path>)
+VARIANT = os.environ.get("OG_VARIANT", "")
+OBJ = os.path.join(CSRC, "_obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "lib", "libofdmgan" + ("_" + VARIANT if VARIANT else "") + ".so")
+UNITS = ["runtime.cu", "infer.cu", "sim_gauss.cu", "sim_qpsk.cu", "train.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + os.environ.get("OG_NVCC_FLAGS", "").split()
 
 
 def _headers():

@@ -24,12 +24,33 @@ struct SimArgs {
     float* clean;            // outputs (device, nullable)
     float* noisy;
     float* snr_out;
-    int gen_kind;            // -1: no generator, else OFDMGAN_GEN_*
     int wslot;               // weight slot of the generator image
     float slope;
     double* partials;        // [grid][n_snr][N_METHODS][COLS] per-CTA metric partials (nullable)
     int n_snr;
 };
+
+// what the API layer hands to a simulator translation unit (host struct)
+struct SimCall {
+    const ofdmgan_chan_cfg* cfg;
+    const ofdmgan_chan_rand* rand;     // nullable
+    uint64_t seed, frame0;
+    int64_t B;
+    float* clean;                      // device outputs, nullable
+    float* noisy;
+    float* snr;
+    int gen_kind;                      // -1: simulate only, else OFDMGAN_GEN_*
+    const float* gparams258;           // host or device (OFDMGAN_GEN_F32)
+    const int8_t* wrom;                // host ROMs (Q kinds)
+    const int16_t* brom;
+    float slope;
+    double* metrics;                   // device accumulator, nullable
+    int n_snr;
+    int src;                           // SRC_*
+    cudaStream_t stream;
+};
+int sim_launch_gauss(const SimCall& c);    // sim_gauss.cu
+int sim_launch_qpsk(const SimCall& c);     // sim_qpsk.cu
 
 // ---- radix-2 DIT inverse FFT, fully unrolled, unscaled: x[n] = sum_k X[k] e^{+j 2 pi k n / N} -------------
 template <int N>
@@ -170,8 +191,8 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float t = (nr[i] * nr[i] + ni[i] * ni[i]) * invA2;             // (|x|/A)^2
-            const float yp = p == 3.0f ? t * t * t : exp2f(p * __log2f(t));       // (|x|/A)^(2p)
-            const float gain = exp2f(ninv2p * __log2f(1.0f + yp));               // (1+.)^(-1/2p); phase preserved
+            const float yp = p == 3.0f ? t * t * t : fast_ex2(p * fast_lg2(t));     // (|x|/A)^(2p)
+            const float gain = fast_ex2(ninv2p * fast_lg2(1.0f + yp));            // (1+.)^(-1/2p); phase preserved
             nr[i] *= gain; ni[i] *= gain;
         }
     }
@@ -195,8 +216,7 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
                 const int i = 4 * j + t;
                 th = fmaf(c.pn_sigma, n[t], th);
                 const float red = fmaf(-6.283185307179586f, rintf(th * 0.15915494309189535f), th);
-                float s, co;
-                __sincosf(red, &s, &co);
+                const float s = fast_sin(red), co = fast_cos(red);
                 const float xr = nr[i], xi = ni[i];
                 nr[i] = xr * co - xi * s;
                 ni[i] = xr * s + xi * co;
@@ -208,7 +228,7 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
     for (int i = 0; i < 16; ++i) P = fmaf(nr[i], nr[i], fmaf(ni[i], ni[i], P));
     P *= 0.0625f;
     // sigma = sqrt(P / 10^(snr/10) / 2)
-    const float sd = sqrtf(0.5f * P * exp2f(-0.33219280948873623f * snr_db));
+    const float sd = fast_sqrt(0.5f * P * fast_ex2(-0.33219280948873623f * snr_db));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float n[4], m[4];

@@ -71,15 +71,23 @@ __device__ __forceinline__ void philox4x32_10(const PhiloxKeys& k, uint32_t c0, 
 __device__ __forceinline__ float u_open(uint32_t x) { return __uint_as_float(0x3F800000u | (x >> 9)) - (1.0f - 5.9604644775390625e-08f); }
 __device__ __forceinline__ float u_half(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 
+// ---- single-instruction MUFU forms (no range fix-up code, no slow-path calls) ---------------------------------
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Box-Muller on the word pairs (x0,x1), (x2,x3): 4 normals per Philox block.
+//   r = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2 u1), u1 in (0,1) so the radicand is > 0; angle 2 pi u2 in [0, 2 pi)
 __device__ __forceinline__ void normals_from_block(const uint32_t (&x)[4], float (&n)[4]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        float r = sqrtf(-2.0f * __logf(u_open(x[2 * h])));
-        float s, c;
-        __sincosf(6.283185307179586f * u_half(x[2 * h + 1]), &s, &c);
-        n[2 * h] = r * c;
-        n[2 * h + 1] = r * s;
+        const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u_open(x[2 * h])));
+        const float th = 6.283185307179586f * u_half(x[2 * h + 1]);
+        n[2 * h] = r * fast_cos(th);
+        n[2 * h + 1] = r * fast_sin(th);
     }
 }
 
@@ -111,7 +119,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, 0.f) + slope * fminf(v, 0.f); }
+// LeakyReLU for 0 <= slope <= 1 (the API rejects anything else): max(v, slope*v), FMUL + FMNMX
+__device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, slope * v); }
+inline bool slope_ok(float s) { return s >= 0.f && s <= 1.f; }
 #endif  // __CUDACC__
 
 }  // namespace og

@@ -5,13 +5,9 @@
 //   fused (1)+(2|3)+metrics                  ofdmgan_sim_gen_metrics(_host), ofdmgan_frame_metrics
 // One frame per thread, weights through the uniform datapath from __constant__ images, persistent grids sized as a
 // multiple of the SM count, warp-private coalesced staging of frame tiles (io_tile.cuh).
-#include "chan_device.cuh"
-#include "gen_device.cuh"
-#include "io_tile.cuh"
+#include "sim_kernel.cuh"
 
 namespace og {
-
-constexpr int NM = OFDMGAN_N_METHODS, NC = OFDMGAN_METRIC_COLS;
 
 // ------------------------------------------------------------------------------------------------ (2) fp32 G
 __global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_f32(const float* __restrict__ x, float* __restrict__ y, int64_t B,
@@ -80,175 +76,6 @@ __global__ void k_quantize_q88(const float* __restrict__ x, int16_t* __restrict_
 __global__ void k_dequantize_q88(const int16_t* __restrict__ q, float* __restrict__ x, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         x[i] = (float)q[i] * (1.0f / 256.0f);
-}
-
-// ------------------------------------------------------------------------------------------------ metrics
-// per-thread running sums for the SNR bin the thread is currently in; spilled to the CTA's shared table on a bin change
-struct Acc {
-    float v[2][7];      // [GAN, NoEQ][n, mse, mse^2, evm, evm^2, errs, bits] ; col 7 (ratio) shares the flush below
-    float ratio[2];
-    int bin;
-    int count;
-};
-
-__device__ __forceinline__ void frame_err(const float (&er)[16], const float (&ei)[16], const float (&cr)[16],
-                                          const float (&ci)[16], float& mse, float& evm, float& ratio) {
-    float se = 0.f, sr = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float a = er[i] - cr[i], b = ei[i] - ci[i];
-        se = fmaf(a, a, fmaf(b, b, se));
-        sr = fmaf(cr[i], cr[i], fmaf(ci[i], ci[i], sr));
-    }
-    mse = se * 0.03125f;
-    ratio = __fdividef(se, sr);
-    // 20 log10(sqrt(mean|e|^2 / mean|ref|^2) + 1e-10)     benchmark_comparison.py:142-146
-    evm = 6.020599913279624f * __log2f(sqrtf(ratio) + 1e-10f);
-}
-
-__device__ __forceinline__ void acc_reset(Acc& a, int bin) {
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-#pragma unroll
-        for (int c = 0; c < 7; ++c) a.v[m][c] = 0.f;
-        a.ratio[m] = 0.f;
-    }
-    a.bin = bin;
-    a.count = 0;
-}
-
-// add the thread's running sums into the CTA table (shared, double).  Warp-uniform bins take the shuffle path.
-__device__ __forceinline__ void acc_flush(Acc& a, double* table, int lane) {
-    const unsigned full = 0xffffffffu;
-    const int bin0 = __shfl_sync(full, a.bin, 0);
-    const bool uniform = __all_sync(full, a.bin == bin0);
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float val = c < 7 ? a.v[m][c] : a.ratio[m];
-            if (uniform) {
-                const float s = warp_sum(val);
-                if (lane == 0 && a.bin >= 0) atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)s);
-            } else if (a.bin >= 0 && val != 0.f) {
-                atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)val);
-            }
-        }
-    }
-    acc_reset(a, a.bin);
-}
-
-__device__ __forceinline__ void acc_add(Acc& a, int m, float mse, float evm, float ratio, int errs, int nb) {
-    a.v[m][0] += 1.f; a.v[m][1] += mse; a.v[m][2] = fmaf(mse, mse, a.v[m][2]);
-    a.v[m][3] += evm; a.v[m][4] = fmaf(evm, evm, a.v[m][4]);
-    a.v[m][5] += (float)errs; a.v[m][6] += (float)nb;
-    a.ratio[m] += ratio;
-}
-
-// ------------------------------------------------------------------------------------------------ (1) + fused
-// frames kept per thread before the running float sums are folded into the double table (bounds float rounding)
-constexpr int FLUSH_EVERY = 32;
-
-template <int SRC>
-__global__ void __launch_bounds__(OG_THREADS) k_sim(const __grid_constant__ SimArgs a) {
-    __shared__ float4 sm[OG_THREADS * 8];
-    __shared__ double table[OFDMGAN_MAX_SNR_BINS * NM * NC];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* wsm = sm + warp * 32 * 8;
-    const bool want_metrics = a.partials != nullptr;
-    if (want_metrics) {
-        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) table[i] = 0.0;
-        __syncthreads();
-    }
-    Acc acc;
-    acc_reset(acc, -1);
-    const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t wbase = t * OG_THREADS + warp * 32;
-        if (wbase >= a.B) continue;
-        const int64_t b = wbase + lane;
-        const bool live = b < a.B;
-        const int64_t bb = live ? b : a.B - 1;                   // dead lanes recompute the last frame, results dropped
-        const uint64_t frame = a.frame0 + (uint64_t)bb;
-
-        // block 12: {snr uniform, payload bits}
-        uint32_t bits = 0;
-        float snr_db;
-        {
-            uint32_t x12[4] = {0u, 0u, 0u, 0u};
-            const bool need12 = (SRC != SRC_GAUSS && !a.bits) || (a.cfg.snr_mode == OFDMGAN_SNR_UNIFORM && !a.snr_db);
-            if (need12) philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
-            bits = a.bits ? a.bits[bb] : x12[1];
-            if (a.cfg.snr_mode == OFDMGAN_SNR_GRID) snr_db = a.cfg.snr_lo + a.cfg.snr_step * (float)snr_bin_of(a.cfg, frame);
-            else snr_db = a.snr_db ? a.snr_db[bb] : fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x12[0]), a.cfg.snr_lo);
-        }
-        float cr[16], ci[16], nr[16], ni[16];
-        tx_frame<SRC>(a, bb, frame, bits, cr, ci);
-        impair_channel(a, bb, frame, snr_db, cr, ci, nr, ni);
-        normalise(a.cfg.normalize, cr, ci, nr, ni);
-
-        if (a.clean) {
-            float f[2][16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { f[0][i] = cr[i]; f[1][i] = ci[i]; }
-            tile_store_f32(a.clean, wbase, a.B, wsm, lane, f);
-        }
-        if (a.noisy) {
-            float f[2][16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { f[0][i] = nr[i]; f[1][i] = ni[i]; }
-            tile_store_f32(a.noisy, wbase, a.B, wsm, lane, f);
-        }
-        if (a.snr_out && live) a.snr_out[b] = snr_db;
-        if (a.gen_kind < 0) continue;
-
-        // reconstruct
-        float xin[2][16], yo[2][16];
-        if (a.gen_kind == OFDMGAN_GEN_F32) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { xin[0][i] = nr[i]; xin[1][i] = ni[i]; }
-            gen_fwd_f32_infer(c_g[a.wslot], a.slope, xin, yo);
-        } else {
-            // Q8.8 by truncation toward zero (proof/verification.py:297-298); back to float by /256
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { xin[0][i] = truncf(nr[i] * 256.0f); xin[1][i] = truncf(ni[i] * 256.0f); }
-            if (a.gen_kind == OFDMGAN_GEN_Q_SPEC) gen_fwd_q_spec(c_q[a.wslot], xin, yo); else gen_fwd_q_rtl(c_q[a.wslot], xin, yo);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { yo[0][i] *= 0.00390625f; yo[1][i] *= 0.00390625f; }
-        }
-        if (!want_metrics) continue;
-        const int bin = snr_bin_of(a.cfg, frame);
-        if (__any_sync(0xffffffffu, bin != acc.bin || acc.count >= FLUSH_EVERY)) {
-            acc_flush(acc, table, lane);
-            acc.bin = bin;
-        }
-        if (live) {
-            float mse, evm, ratio;
-            int errs, nb;
-            frame_err(yo[0], yo[1], cr, ci, mse, evm, ratio);
-            nb = qpsk_errors<SRC>(a.cfg, yo[0], yo[1], bits, errs);
-            acc_add(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs, nb);
-            frame_err(nr, ni, cr, ci, mse, evm, ratio);
-            nb = qpsk_errors<SRC>(a.cfg, nr, ni, bits, errs);
-            acc_add(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, errs, nb);
-        }
-        acc.count++;
-    }
-    if (want_metrics) {
-        acc_flush(acc, table, lane);
-        __syncthreads();
-        double* out = a.partials + (size_t)blockIdx.x * a.n_snr * NM * NC;
-        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) out[i] = table[i];
-    }
-}
-
-// fixed-order sum of the per-CTA partial tables into the caller's accumulator (deterministic for a given grid)
-__global__ void k_reduce_partials(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ metrics) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * n + i];
-    metrics[i] += s;
 }
 
 // metrics of frames already in HBM
@@ -345,18 +172,6 @@ static int check_cfg(const ofdmgan_chan_cfg* c, int* n_snr) {
     return 0;
 }
 
-static int launch_sim(int src, int grid, cudaStream_t s, const SimArgs& a) {
-    switch (src) {
-        case SRC_GAUSS: k_sim<SRC_GAUSS><<<grid, OG_THREADS, 0, s>>>(a); break;
-        case SRC_Q16_CP0: k_sim<SRC_Q16_CP0><<<grid, OG_THREADS, 0, s>>>(a); break;
-        case SRC_Q16_CP2: k_sim<SRC_Q16_CP2><<<grid, OG_THREADS, 0, s>>>(a); break;
-        case SRC_Q8_CP0: k_sim<SRC_Q8_CP0><<<grid, OG_THREADS, 0, s>>>(a); break;
-        case SRC_Q8_CP2: k_sim<SRC_Q8_CP2><<<grid, OG_THREADS, 0, s>>>(a); break;
-        default: return OFDMGAN_E_ARG;
-    }
-    return (int)cudaGetLastError();
-}
-
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace og
@@ -366,8 +181,9 @@ using namespace og;
 extern "C" {
 
 int ofdmgan_gen_fwd_f32(const float* x_dev, const float* gparams258, float* y_dev, int64_t B, float leaky_slope, void* stream) {
+    if (!slope_ok(leaky_slope)) return OFDMGAN_E_ARG;
+    if (B == 0 && gparams258) return 0;                       // empty batch: nothing to launch, pointers may be NULL
     if (!x_dev || !y_dev || !gparams258 || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
-    if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
     if ((rc = slot_for_stream(s, &slot))) return rc;
@@ -378,9 +194,9 @@ int ofdmgan_gen_fwd_f32(const float* x_dev, const float* gparams258, float* y_de
 
 int ofdmgan_gen_fwd_q(const int16_t* x_dev, const int8_t* wrom_host, const int16_t* brom_host, int16_t* y_dev, int64_t B,
                       int mode, uint64_t* digest_dev, void* stream) {
-    if (!x_dev || !y_dev || !wrom_host || !brom_host || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
     if (mode != OFDMGAN_GEN_Q_SPEC && mode != OFDMGAN_GEN_Q_RTL) return OFDMGAN_E_ARG;
-    if (B == 0) return 0;
+    if (B == 0 && wrom_host && brom_host) return 0;
+    if (!x_dev || !y_dev || !wrom_host || !brom_host || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
     if ((rc = slot_for_stream(s, &slot))) return rc;
@@ -407,6 +223,8 @@ int ofdmgan_dequantize_q88(const int16_t* q_dev, float* x_dev, int64_t n, void* 
     return (int)cudaGetLastError();
 }
 
+static int sim_dispatch(const SimCall& c) { return c.src == SRC_GAUSS ? sim_launch_gauss(c) : sim_launch_qpsk(c); }
+
 int ofdmgan_chan_sim(const ofdmgan_chan_cfg* cfg_host, const ofdmgan_chan_rand* rand_host, uint64_t seed, uint64_t frame0,
                      float* clean_dev, float* noisy_dev, float* snr_dev, int64_t B, void* stream) {
     int n_snr, src, rc;
@@ -414,16 +232,11 @@ int ofdmgan_chan_sim(const ofdmgan_chan_cfg* cfg_host, const ofdmgan_chan_rand* 
     if ((rc = src_of(*cfg_host, &src))) return rc;
     if (B < 0 || (clean_dev && !aligned16(clean_dev)) || (noisy_dev && !aligned16(noisy_dev))) return OFDMGAN_E_ARG;
     if (B == 0) return 0;
-    SimArgs a{};
-    a.cfg = *cfg_host;
-    a.keys = philox_keys(seed);
-    a.frame0 = frame0;
-    a.B = B;
-    if (rand_host) { a.sym = rand_host->sym; a.bits = rand_host->bits; a.pn = rand_host->pn; a.snr_db = rand_host->snr_db; a.noise = rand_host->noise; }
-    a.clean = clean_dev; a.noisy = noisy_dev; a.snr_out = snr_dev;
-    a.gen_kind = -1;
-    a.n_snr = n_snr;
-    return launch_sim(src, grid_for(B, OG_THREADS, 4), (cudaStream_t)stream, a);
+    SimCall c{};
+    c.cfg = cfg_host; c.rand = rand_host; c.seed = seed; c.frame0 = frame0; c.B = B;
+    c.clean = clean_dev; c.noisy = noisy_dev; c.snr = snr_dev;
+    c.gen_kind = -1; c.n_snr = n_snr; c.src = src; c.stream = (cudaStream_t)stream;
+    return sim_dispatch(c);
 }
 
 int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t frame0, float* sym_dev, uint32_t* bits_dev,
@@ -449,33 +262,17 @@ int ofdmgan_philox_blocks(uint64_t seed, uint64_t ctr0, uint32_t c2, uint32_t c3
 int ofdmgan_sim_gen_metrics(const ofdmgan_chan_cfg* cfg_host, int gen_kind, const float* gparams258, const int8_t* wrom_host,
                             const int16_t* brom_host, float leaky_slope, uint64_t seed, uint64_t frame0, int64_t B,
                             double* metrics_dev, void* stream) {
-    int n_snr, src, rc, slot;
+    int n_snr, src, rc;
     if ((rc = check_cfg(cfg_host, &n_snr))) return rc;
     if ((rc = src_of(*cfg_host, &src))) return rc;
-    if (!metrics_dev || B < 0 || gen_kind < OFDMGAN_GEN_F32 || gen_kind > OFDMGAN_GEN_Q_RTL) return OFDMGAN_E_ARG;
+    if (!metrics_dev || B < 0 || gen_kind < OFDMGAN_GEN_F32 || gen_kind > OFDMGAN_GEN_Q_RTL || !slope_ok(leaky_slope)) return OFDMGAN_E_ARG;
     if (gen_kind == OFDMGAN_GEN_F32 ? !gparams258 : (!wrom_host || !brom_host)) return OFDMGAN_E_ARG;
     if (B == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = slot_for_stream(s, &slot))) return rc;
-    if (gen_kind == OFDMGAN_GEN_F32) rc = upload_g(gparams258, slot, s); else rc = upload_q(wrom_host, brom_host, slot, s);
-    if (rc) return rc;
-    const int grid = grid_for(B, OG_THREADS, 4);
-    const int n = n_snr * NM * NC;
-    void* partials = nullptr;
-    if ((rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
-    SimArgs a{};
-    a.cfg = *cfg_host;
-    a.keys = philox_keys(seed);
-    a.frame0 = frame0;
-    a.B = B;
-    a.gen_kind = gen_kind;
-    a.wslot = slot;
-    a.slope = leaky_slope;
-    a.partials = (double*)partials;
-    a.n_snr = n_snr;
-    if ((rc = launch_sim(src, grid, s, a))) return rc;
-    k_reduce_partials<<<(n + 127) / 128, 128, 0, s>>>((const double*)partials, grid, n, metrics_dev);
-    return (int)cudaGetLastError();
+    SimCall c{};
+    c.cfg = cfg_host; c.seed = seed; c.frame0 = frame0; c.B = B;
+    c.gen_kind = gen_kind; c.gparams258 = gparams258; c.wrom = wrom_host; c.brom = brom_host; c.slope = leaky_slope;
+    c.metrics = metrics_dev; c.n_snr = n_snr; c.src = src; c.stream = (cudaStream_t)stream;
+    return sim_dispatch(c);
 }
 
 int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind, const float* gparams258_host,
@@ -501,10 +298,9 @@ int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind,
 
 int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int32_t* bin_dev, int method, int n_snr, int64_t B,
                           double* metrics_dev, void* stream) {
-    if (!est_dev || !ref_dev || !metrics_dev || B < 0 || method < 0 || method >= NM || n_snr < 1 || n_snr > OFDMGAN_MAX_SNR_BINS)
-        return OFDMGAN_E_ARG;
-    if (!aligned16(est_dev) || !aligned16(ref_dev)) return OFDMGAN_E_ARG;
+    if (!metrics_dev || B < 0 || method < 0 || method >= NM || n_snr < 1 || n_snr > OFDMGAN_MAX_SNR_BINS) return OFDMGAN_E_ARG;
     if (B == 0) return 0;
+    if (!est_dev || !ref_dev || !aligned16(est_dev) || !aligned16(ref_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
     if ((rc = slot_for_stream(s, &slot))) return rc;

@@ -1,0 +1,281 @@
+// Kernel (1) and the fused headline path (1)+(2|3)+metrics: one OFDM frame per thread, everything in registers.
+//   Philox draws -> symbols -> IFFT -> [CP] -> Rapp PA -> IQ imbalance -> phase noise -> AWGN -> normalise
+//   [-> generator (fp32 | Q spec | Q rtl_literal) -> per-SNR-bin MSE / EVM / bit-error accumulation]
+// Included by sim_gauss.cu and sim_qpsk.cu (each translation unit owns its constant-memory weight images); the
+// instantiation list is what differs.  Template parameters: SRC = symbol source layout (chan_device.cuh),
+// GEN = -1 (simulate only) or OFDMGAN_GEN_*.
+//
+// Work distribution: a persistent grid of (SM count x resident CTAs) blocks, each taking one CONTIGUOUS chunk of
+// 128-frame tiles, so the SNR bin of a thread's successive frames changes rarely and the per-thread running sums are
+// folded into the CTA's shared double table only on a bin change or every FLUSH_EVERY frames.
+#pragma once
+#include "chan_device.cuh"
+#include "gen_device.cuh"
+#include "io_tile.cuh"
+
+#ifndef OG_SIM_MINB
+#define OG_SIM_MINB 4           // resident CTAs per SM the fused kernels are compiled for (<= 128 registers, no spills;
+                                // measured best of 3/4/5/6 on B200, profiles/r1_notes.md)
+#endif
+
+namespace og {
+
+constexpr int NM = OFDMGAN_N_METHODS, NC = OFDMGAN_METRIC_COLS;
+constexpr int FLUSH_EVERY = 32;     // frames a thread accumulates in fp32 before folding into the double table
+
+// per-thread running sums for the SNR bin the thread is currently in, [GAN, NoEQ]
+struct Acc {
+    float mse[2], mse2[2], evm[2], evm2[2], ratio[2], errs[2];
+    float nbits;       // payload bits compared per method (same for both)
+    int count;         // live frames accumulated
+    int bin;
+};
+
+__device__ __forceinline__ void acc_reset(Acc& a, int bin) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { a.mse[m] = a.mse2[m] = a.evm[m] = a.evm2[m] = a.ratio[m] = a.errs[m] = 0.f; }
+    a.nbits = 0.f;
+    a.count = 0;
+    a.bin = bin;
+}
+
+__device__ __forceinline__ void frame_err(const float (&er)[16], const float (&ei)[16], const float (&cr)[16],
+                                          const float (&ci)[16], float& mse, float& evm, float& ratio) {
+    float se = 0.f, sr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float a = er[i] - cr[i], b = ei[i] - ci[i];
+        se = fmaf(a, a, fmaf(b, b, se));
+        sr = fmaf(cr[i], cr[i], fmaf(ci[i], ci[i], sr));
+    }
+    mse = se * 0.03125f;
+    ratio = se * fast_rcp(sr);
+    // 20 log10(sqrt(mean|e|^2 / mean|ref|^2) + 1e-10)     benchmark_comparison.py:142-146
+    evm = 6.020599913279624f * fast_lg2(fast_sqrt(ratio) + 1e-10f);
+}
+
+template <bool BITS>
+__device__ __forceinline__ void acc_add(Acc& a, int m, float mse, float evm, float ratio, int errs) {
+    a.mse[m] += mse; a.mse2[m] = fmaf(mse, mse, a.mse2[m]);
+    a.evm[m] += evm; a.evm2[m] = fmaf(evm, evm, a.evm2[m]);
+    a.ratio[m] += ratio;
+    if (BITS) a.errs[m] += (float)errs;
+}
+
+// fold the thread's running sums into the CTA table (shared, double).  Warp-uniform bins take the shuffle path.
+template <bool BITS>
+__device__ __forceinline__ void acc_flush(Acc& a, double* table, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int bin0 = __shfl_sync(full, a.bin, 0);
+    const bool uniform = __all_sync(full, a.bin == bin0);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const float col[NC] = {(float)a.count, a.mse[m], a.mse2[m], a.evm[m], a.evm2[m], a.errs[m], a.nbits, a.ratio[m]};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (!BITS && (c == 5 || c == 6)) continue;
+            if (uniform) {
+                const float s = warp_sum(col[c]);
+                if (lane == 0 && a.bin >= 0) atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)s);
+            } else if (a.bin >= 0 && col[c] != 0.f) {
+                atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)col[c]);
+            }
+        }
+    }
+    acc_reset(a, a.bin);
+}
+
+template <int SRC, int GEN>
+__global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(const __grid_constant__ SimArgs a) {
+    constexpr bool BITS = SRC != SRC_GAUSS;
+    __shared__ float4 sm[OG_THREADS * 8];
+    __shared__ double table[GEN < 0 ? 1 : OFDMGAN_MAX_SNR_BINS * NM * NC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* wsm = sm + warp * 32 * 8;
+    const bool want_metrics = GEN >= 0 && a.partials != nullptr;
+    if (want_metrics) {
+        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) table[i] = 0.0;
+        __syncthreads();
+    }
+    Acc acc;
+    acc_reset(acc, -1);
+
+    const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
+    const int64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per_cta;
+    const int64_t t1 = t0 + per_cta < ntiles ? t0 + per_cta : ntiles;
+
+    // SNR grid position of this thread's first frame; afterwards advanced by 128 frames per tile without divisions
+    const bool grid_mode = a.cfg.snr_mode == OFDMGAN_SNR_GRID;
+    const uint64_t fps = grid_mode ? (uint64_t)a.cfg.frames_per_snr : 1;
+    const bool incremental = grid_mode && fps >= (uint64_t)OG_THREADS;
+    int bin = 0;
+    uint64_t in_bin = 0;
+    if (grid_mode && t0 < t1) {
+        const uint64_t f0 = a.frame0 + (uint64_t)(t0 * OG_THREADS + threadIdx.x);
+        const uint64_t q = f0 / fps;
+        in_bin = f0 - q * fps;
+        bin = (int)(q % (uint64_t)a.cfg.n_snr);
+    }
+
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t wbase = t * OG_THREADS + warp * 32;
+        const int64_t b = wbase + lane;
+        const bool live = b < a.B;
+        const int64_t bb = live ? b : a.B - 1;                   // dead lanes recompute the last frame, results dropped
+        const uint64_t frame = a.frame0 + (uint64_t)bb;
+        int fbin = bin;
+        if (grid_mode && !incremental) fbin = snr_bin_of(a.cfg, frame);
+        else if (grid_mode && !live) fbin = acc.bin >= 0 ? acc.bin : bin;   // dead lanes must not force a flush
+        if (incremental) {                                         // advance to the next tile's frame
+            in_bin += OG_THREADS;
+            if (in_bin >= fps) { in_bin -= fps; bin = bin + 1 == a.cfg.n_snr ? 0 : bin + 1; }
+        }
+        if (wbase >= a.B) continue;                                // warp-uniform: whole warp beyond the batch
+
+        // block 12: {snr uniform, payload bits}
+        uint32_t bits = 0;
+        float snr_db;
+        {
+            uint32_t x12[4] = {0u, 0u, 0u, 0u};
+            const bool need12 = (BITS && !a.bits) || (!grid_mode && !a.snr_db);
+            if (need12) philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
+            if (BITS) bits = a.bits ? a.bits[bb] : x12[1];
+            if (grid_mode) snr_db = fmaf(a.cfg.snr_step, (float)(live || !incremental ? fbin : snr_bin_of(a.cfg, frame)), a.cfg.snr_lo);
+            else snr_db = a.snr_db ? a.snr_db[bb] : fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x12[0]), a.cfg.snr_lo);
+        }
+        float cr[16], ci[16], nr[16], ni[16];
+        tx_frame<SRC>(a, bb, frame, bits, cr, ci);
+        impair_channel(a, bb, frame, snr_db, cr, ci, nr, ni);
+        normalise(a.cfg.normalize, cr, ci, nr, ni);
+
+        if (a.clean) {
+            float f[2][16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { f[0][i] = cr[i]; f[1][i] = ci[i]; }
+            tile_store_f32(a.clean, wbase, a.B, wsm, lane, f);
+        }
+        if (a.noisy) {
+            float f[2][16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { f[0][i] = nr[i]; f[1][i] = ni[i]; }
+            tile_store_f32(a.noisy, wbase, a.B, wsm, lane, f);
+        }
+        if (a.snr_out && live) a.snr_out[b] = snr_db;
+        if (GEN < 0) continue;
+
+        if (want_metrics) {
+            if (__any_sync(0xffffffffu, fbin != acc.bin || acc.count >= FLUSH_EVERY)) {
+                acc_flush<BITS>(acc, table, lane);
+                acc.bin = fbin;
+            }
+            if (live) {                                            // NoEQ first: the received frame dies into G's input
+                float mse, evm, ratio;
+                int errs = 0;
+                frame_err(nr, ni, cr, ci, mse, evm, ratio);
+                if (BITS) acc.nbits += (float)qpsk_errors<SRC>(a.cfg, nr, ni, bits, errs);
+                acc_add<BITS>(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, errs);
+                acc.count++;
+            }
+        }
+        // reconstruct.  The clean frame waits in the thread's own (swizzled) slots of the warp tile meanwhile.
+        float xin[2][16], yo[2][16];
+        {
+            float f[2][16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { f[0][i] = cr[i]; f[1][i] = ci[i]; }
+            tile_write_f32(wsm, lane, f);
+        }
+        if (GEN == OFDMGAN_GEN_F32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xin[0][i] = nr[i]; xin[1][i] = ni[i]; }
+            gen_fwd_f32_infer(c_g[a.wslot], a.slope, xin, yo);
+        } else {
+            // Q8.8 by truncation toward zero (proof/verification.py:297-298); back to float by /256
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xin[0][i] = truncf(nr[i] * 256.0f); xin[1][i] = truncf(ni[i] * 256.0f); }
+            if (GEN == OFDMGAN_GEN_Q_SPEC) gen_fwd_q_spec(c_q[a.wslot], xin, yo); else gen_fwd_q_rtl(c_q[a.wslot], xin, yo);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { yo[0][i] *= 0.00390625f; yo[1][i] *= 0.00390625f; }
+        }
+        if (want_metrics && live) {
+            float f[2][16];
+            tile_read_f32(wsm, lane, f);
+            float mse, evm, ratio;
+            int errs = 0;
+            frame_err(yo[0], yo[1], f[0], f[1], mse, evm, ratio);
+            if (BITS) qpsk_errors<SRC>(a.cfg, yo[0], yo[1], bits, errs);
+            acc_add<BITS>(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs);
+        }
+        __syncwarp();
+    }
+    if (want_metrics) {
+        acc_flush<BITS>(acc, table, lane);
+        __syncthreads();
+        double* out = a.partials + (size_t)blockIdx.x * a.n_snr * NM * NC;
+        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) out[i] = table[i];
+    }
+}
+
+// fixed-order sum of the per-CTA partial tables into the caller's accumulator (deterministic for a given grid):
+// one thread per table entry, CTA rows read coalesced across threads
+static __global__ void k_reduce_partials(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ metrics) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < nblocks; b += 4) {
+        s0 += partials[(size_t)b * n + i];
+        s1 += partials[(size_t)(b + 1) * n + i];
+        s2 += partials[(size_t)(b + 2) * n + i];
+        s3 += partials[(size_t)(b + 3) * n + i];
+    }
+    for (; b < nblocks; ++b) s0 += partials[(size_t)b * n + i];
+    metrics[i] += (s0 + s1) + (s2 + s3);
+}
+
+template <int SRC, int GEN>
+static int sim_launch_one(const SimCall& c) {
+    cudaStream_t s = c.stream;
+    int slot = 0, rc;
+    if ((rc = slot_for_stream(s, &slot))) return rc;
+    if (GEN == OFDMGAN_GEN_F32) rc = upload_g(c.gparams258, slot, s);
+    else if (GEN > 0) rc = upload_q(c.wrom, c.brom, slot, s);
+    if (rc) return rc;
+    const int per_sm = GEN < 0 ? 2 : OG_SIM_MINB;
+    const int grid = grid_for(c.B, OG_THREADS, per_sm);
+    const int n = c.n_snr * NM * NC;
+    void* partials = nullptr;
+    if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
+    SimArgs a{};
+    a.cfg = *c.cfg;
+    a.keys = philox_keys(c.seed);
+    a.frame0 = c.frame0;
+    a.B = c.B;
+    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; }
+    a.clean = c.clean; a.noisy = c.noisy; a.snr_out = c.snr;
+    a.wslot = slot;
+    a.slope = c.slope;
+    a.partials = (double*)partials;
+    a.n_snr = c.n_snr;
+    k_sim<SRC, GEN><<<grid, OG_THREADS, 0, s>>>(a);
+    OG_CHECK(cudaGetLastError());
+    if (partials) {
+        k_reduce_partials<<<(n + 63) / 64, 64, 0, s>>>((const double*)partials, grid, n, c.metrics);
+        OG_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int SRC>
+static int sim_launch_src(const SimCall& c) {
+    switch (c.gen_kind) {
+        case -1: return sim_launch_one<SRC, -1>(c);
+        case OFDMGAN_GEN_F32: return sim_launch_one<SRC, OFDMGAN_GEN_F32>(c);
+        case OFDMGAN_GEN_Q_SPEC: return sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC>(c);
+        case OFDMGAN_GEN_Q_RTL: return sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL>(c);
+        default: return OFDMGAN_E_ARG;
+    }
+}
+
+}  // namespace og

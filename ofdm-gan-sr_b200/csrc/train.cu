@@ -470,8 +470,8 @@ extern "C" {
 
 int ofdmgan_disc_fwd_f32(const float* cand_dev, const float* cond_dev, const float* dparams521, float* score_dev, int64_t B,
                          float leaky_slope, void* stream) {
+    if (B == 0 && dparams521) return 0;
     if (!cand_dev || !cond_dev || !dparams521 || !score_dev || B < 0 || !aligned16(cand_dev) || !aligned16(cond_dev)) return OFDMGAN_E_ARG;
-    if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
     if ((rc = slot_for_stream(s, &slot))) return rc;
@@ -482,9 +482,10 @@ int ofdmgan_disc_fwd_f32(const float* cand_dev, const float* cond_dev, const flo
 
 int ofdmgan_disc_bwd_f32(const float* cand_dev, const float* cond_dev, const float* dparams521, const float* g_dev,
                          float* dcand_dev, float* dcond_dev, float* dparams521_dev, int64_t B, float leaky_slope, void* stream) {
-    if (!cand_dev || !cond_dev || !dparams521 || !g_dev || B < 0 || !aligned16(cand_dev) || !aligned16(cond_dev)) return OFDMGAN_E_ARG;
-    if ((dcand_dev && !aligned16(dcand_dev)) || (dcond_dev && !aligned16(dcond_dev))) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (B < 0 || !dparams521) return OFDMGAN_E_ARG;
+    if (B > 0 && (!cand_dev || !cond_dev || !g_dev || !aligned16(cand_dev) || !aligned16(cond_dev))) return OFDMGAN_E_ARG;
+    if ((dcand_dev && !aligned16(dcand_dev)) || (dcond_dev && !aligned16(dcond_dev))) return OFDMGAN_E_ARG;
     if (B == 0) {
         if (dparams521_dev) OG_CHECK(cudaMemsetAsync(dparams521_dev, 0, OFDMGAN_D_NPARAMS * sizeof(float), s));
         return 0;
@@ -548,9 +549,10 @@ int ofdmgan_gradient_penalty(const float* real_dev, const float* fake_dev, const
 int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* alpha_dev, uint64_t seed,
                         uint64_t sample0, uint32_t alpha_iter, const float* dparams521, float gp_weight, float leaky_slope,
                         int64_t B_local, int64_t B_global, float* out_dev, void* stream) {
-    if (!clean_dev || !noisy_dev || !fake_dev || !dparams521 || !out_dev || B_local < 0 || B_global < 1 || B_global < B_local) return OFDMGAN_E_ARG;
-    if (!aligned16(clean_dev) || !aligned16(noisy_dev) || !aligned16(fake_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!dparams521 || !out_dev || B_local < 0 || B_global < 1 || B_global < B_local) return OFDMGAN_E_ARG;
+    if (B_local > 0 && (!clean_dev || !noisy_dev || !fake_dev || !aligned16(clean_dev) || !aligned16(noisy_dev) || !aligned16(fake_dev)))
+        return OFDMGAN_E_ARG;
     if (B_local == 0) {
         OG_CHECK(cudaMemsetAsync(out_dev, 0, OFDMGAN_CRITIC_OUT * sizeof(float), s));
         return 0;
@@ -567,9 +569,10 @@ int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const fl
 int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float* dparams521, const float* gparams258, float adv_weight,
                      float rec_weight, float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, float* fake_out_dev,
                      void* stream) {
-    if (!clean_dev || !noisy_dev || !dparams521 || !gparams258 || !out_dev || B_local < 0 || B_global < 1 || B_global < B_local) return OFDMGAN_E_ARG;
-    if (!aligned16(clean_dev) || !aligned16(noisy_dev) || (fake_out_dev && !aligned16(fake_out_dev))) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!dparams521 || !gparams258 || !out_dev || B_local < 0 || B_global < 1 || B_global < B_local) return OFDMGAN_E_ARG;
+    if (B_local > 0 && (!clean_dev || !noisy_dev || !aligned16(clean_dev) || !aligned16(noisy_dev))) return OFDMGAN_E_ARG;
+    if (fake_out_dev && !aligned16(fake_out_dev)) return OFDMGAN_E_ARG;
     if (B_local == 0) {
         OG_CHECK(cudaMemsetAsync(out_dev, 0, OFDMGAN_GEN_OUT * sizeof(float), s));
         return 0;
@@ -594,9 +597,10 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
 
 int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float* dy_dev, float* dx_dev, float* dparams258_dev,
                         int64_t B, float leaky_slope, void* stream) {
-    if (!x_dev || !gparams258 || !dy_dev || !dparams258_dev || B < 0) return OFDMGAN_E_ARG;
-    if (!aligned16(x_dev) || !aligned16(dy_dev) || (dx_dev && !aligned16(dx_dev))) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!gparams258 || !dparams258_dev || B < 0) return OFDMGAN_E_ARG;
+    if (B > 0 && (!x_dev || !dy_dev || !aligned16(x_dev) || !aligned16(dy_dev))) return OFDMGAN_E_ARG;
+    if (dx_dev && !aligned16(dx_dev)) return OFDMGAN_E_ARG;
     if (B == 0) {
         OG_CHECK(cudaMemsetAsync(dparams258_dev, 0, OFDMGAN_G_NPARAMS * sizeof(float), s));
         return 0;

