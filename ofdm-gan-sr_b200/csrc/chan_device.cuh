@@ -53,19 +53,19 @@ int sim_launch_gauss(const SimCall& c);    // sim_gauss.cu
 int sim_launch_qpsk(const SimCall& c);     // sim_qpsk.cu
 
 // ---- radix-2 DIT inverse FFT, fully unrolled, unscaled: x[n] = sum_k X[k] e^{+j 2 pi k n / N} -------------
+// twiddles e^{+j 2 pi k / 16}, k = 0..7, as constant-folded selects (a constexpr table indexed after unrolling is
+// materialised in local memory by nvcc 12.9 and costs an LDL per use)
 template <int N>
-struct Tw;   // twiddles e^{+j 2 pi k / N}
+struct Tw;
 template <>
 struct Tw<16> {
-    static __device__ __forceinline__ float c(int k) {
-        constexpr float t[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
-                                0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
-        return t[k];
+    static __device__ __forceinline__ constexpr float c(int k) {
+        return k == 0 ? 1.f : k == 1 ? 0.92387953251128674f : k == 2 ? 0.70710678118654752f : k == 3 ? 0.38268343236508977f
+             : k == 4 ? 0.f : k == 5 ? -0.38268343236508977f : k == 6 ? -0.70710678118654752f : -0.92387953251128674f;
     }
-    static __device__ __forceinline__ float s(int k) {
-        constexpr float t[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
-                                1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
-        return t[k];
+    static __device__ __forceinline__ constexpr float s(int k) {
+        return k == 0 ? 0.f : k == 1 ? 0.38268343236508977f : k == 2 ? 0.70710678118654752f : k == 3 ? 0.92387953251128674f
+             : k == 4 ? 1.f : k == 5 ? 0.92387953251128674f : k == 6 ? 0.70710678118654752f : 0.38268343236508977f;
     }
 };
 
@@ -84,21 +84,19 @@ __device__ __forceinline__ void fft_inplace(float (&re)[N], float (&im)[N]) {
     for (int i = 0; i < N; ++i) { tr[i] = re[bitrev(i, LOG)]; ti[i] = im[bitrev(i, LOG)]; }
 #pragma unroll
     for (int st = 1; st <= LOG; ++st) {
-        const int m = 1 << st, h = m >> 1;
+        const int h = 1 << (st - 1);
 #pragma unroll
-        for (int base = 0; base < N; base += m)
-#pragma unroll
-            for (int j = 0; j < h; ++j) {
-                const int tw = j * (16 / m);                     // index into the 16-point table
-                const float wr = Tw<16>::c(tw), wi = (float)SIGN * Tw<16>::s(tw);
-                const int a = base + j, b = a + h;
-                float xr, xi;
-                if (tw == 0) { xr = tr[b]; xi = ti[b]; }
-                else if (tw == 4) { xr = -(float)SIGN * ti[b]; xi = (float)SIGN * tr[b]; }
-                else { xr = tr[b] * wr - ti[b] * wi; xi = tr[b] * wi + ti[b] * wr; }
-                tr[b] = tr[a] - xr; ti[b] = ti[a] - xi;
-                tr[a] = tr[a] + xr; ti[a] = ti[a] + xi;
-            }
+        for (int q = 0; q < N / 2; ++q) {                        // fixed trip count: every index below folds to a constant
+            const int j = q & (h - 1), a = ((q >> (st - 1)) << st) + j, b = a + h;
+            const int tw = j * (8 >> (st - 1));                  // index into the 16-point table
+            const float wr = Tw<16>::c(tw), wi = (float)SIGN * Tw<16>::s(tw);
+            float xr, xi;
+            if (tw == 0) { xr = tr[b]; xi = ti[b]; }
+            else if (tw == 4) { xr = -(float)SIGN * ti[b]; xi = (float)SIGN * tr[b]; }
+            else { xr = tr[b] * wr - ti[b] * wi; xi = tr[b] * wi + ti[b] * wr; }
+            tr[b] = tr[a] - xr; ti[b] = ti[a] - xi;
+            tr[a] = tr[a] + xr; ti[a] = ti[a] + xi;
+        }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) { re[i] = tr[i]; im[i] = ti[i]; }

@@ -13,9 +13,16 @@
 #include "gen_device.cuh"
 #include "io_tile.cuh"
 
-#ifndef OG_SIM_MINB
-#define OG_SIM_MINB 4           // resident CTAs per SM the fused kernels are compiled for (<= 128 registers, no spills;
-                                // measured best of 3/4/5/6 on B200, profiles/r1_notes.md)
+// Launch shape.  16 warps per SM at <= 128 registers (measured best of 12/16/20/24 warps on B200, profiles/r1_notes.md)
+// as ONE 512-thread CTA per SM with a few CTA barriers per tile: the loop body is ~70 KB of straight-line code, far
+// beyond the instruction caches, so warps that drift apart each stream their own copy of it (stall_no_inst was 33 % of
+// all stall samples with 4 independent 128-thread CTAs).  Barriers keep the 4 warps of every scheduler on the same
+// cache lines.
+#ifndef OG_SIM_THREADS
+#define OG_SIM_THREADS 512
+#endif
+#ifndef OG_SIM_BARRIERS
+#define OG_SIM_BARRIERS 1
 #endif
 
 namespace og {
@@ -85,11 +92,18 @@ __device__ __forceinline__ void acc_flush(Acc& a, double* table, int lane) {
     acc_reset(a, a.bin);
 }
 
+constexpr int ST = OG_SIM_THREADS;                                   // frames per CTA tile
+constexpr size_t SIM_SMEM = (size_t)ST * 8 * sizeof(float4) + OFDMGAN_MAX_SNR_BINS * NM * NC * sizeof(double);
+
+__device__ __forceinline__ void cta_lockstep(int level) {
+    if (OG_SIM_BARRIERS >= level) __syncthreads();
+}
+
 template <int SRC, int GEN>
-__global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(ST, 512 / ST) k_sim(const __grid_constant__ SimArgs a) {
     constexpr bool BITS = SRC != SRC_GAUSS;
-    __shared__ float4 sm[OG_THREADS * 8];
-    __shared__ double table[GEN < 0 ? 1 : OFDMGAN_MAX_SNR_BINS * NM * NC];
+    extern __shared__ float4 sm[];                                   // [ST*8] warp tiles, then the CTA's metric table
+    double* table = reinterpret_cast<double*>(sm + ST * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* wsm = sm + warp * 32 * 8;
     const bool want_metrics = GEN >= 0 && a.partials != nullptr;
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(c
     Acc acc;
     acc_reset(acc, -1);
 
-    const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
+    const int64_t ntiles = (a.B + ST - 1) / ST;
     const int64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * per_cta;
     const int64_t t1 = t0 + per_cta < ntiles ? t0 + per_cta : ntiles;
@@ -108,18 +122,18 @@ __global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(c
     // SNR grid position of this thread's first frame; afterwards advanced by 128 frames per tile without divisions
     const bool grid_mode = a.cfg.snr_mode == OFDMGAN_SNR_GRID;
     const uint64_t fps = grid_mode ? (uint64_t)a.cfg.frames_per_snr : 1;
-    const bool incremental = grid_mode && fps >= (uint64_t)OG_THREADS;
+    const bool incremental = grid_mode && fps >= (uint64_t)ST;
     int bin = 0;
     uint64_t in_bin = 0;
     if (grid_mode && t0 < t1) {
-        const uint64_t f0 = a.frame0 + (uint64_t)(t0 * OG_THREADS + threadIdx.x);
+        const uint64_t f0 = a.frame0 + (uint64_t)(t0 * ST + threadIdx.x);
         const uint64_t q = f0 / fps;
         in_bin = f0 - q * fps;
         bin = (int)(q % (uint64_t)a.cfg.n_snr);
     }
 
     for (int64_t t = t0; t < t1; ++t) {
-        const int64_t wbase = t * OG_THREADS + warp * 32;
+        const int64_t wbase = t * ST + warp * 32;
         const int64_t b = wbase + lane;
         const bool live = b < a.B;
         const int64_t bb = live ? b : a.B - 1;                   // dead lanes recompute the last frame, results dropped
@@ -128,10 +142,10 @@ __global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(c
         if (grid_mode && !incremental) fbin = snr_bin_of(a.cfg, frame);
         else if (grid_mode && !live) fbin = acc.bin >= 0 ? acc.bin : bin;   // dead lanes must not force a flush
         if (incremental) {                                         // advance to the next tile's frame
-            in_bin += OG_THREADS;
+            in_bin += ST;
             if (in_bin >= fps) { in_bin -= fps; bin = bin + 1 == a.cfg.n_snr ? 0 : bin + 1; }
         }
-        if (wbase >= a.B) continue;                                // warp-uniform: whole warp beyond the batch
+        // (a warp wholly beyond the batch keeps going with live == false everywhere: the CTA barriers below need it)
 
         // block 12: {snr uniform, payload bits}
         uint32_t bits = 0;
@@ -146,8 +160,10 @@ __global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(c
         }
         float cr[16], ci[16], nr[16], ni[16];
         tx_frame<SRC>(a, bb, frame, bits, cr, ci);
+        cta_lockstep(2);
         impair_channel(a, bb, frame, snr_db, cr, ci, nr, ni);
         normalise(a.cfg.normalize, cr, ci, nr, ni);
+        cta_lockstep(1);
 
         if (a.clean) {
             float f[2][16];
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(c
             tile_store_f32(a.noisy, wbase, a.B, wsm, lane, f);
         }
         if (a.snr_out && live) a.snr_out[b] = snr_db;
-        if (GEN < 0) continue;
+        if (GEN < 0) continue;                                     // (compile-time: the simulate-only kernel ends its tile here)
 
         if (want_metrics) {
             if (__any_sync(0xffffffffu, fbin != acc.bin || acc.count >= FLUSH_EVERY)) {
@@ -208,6 +224,7 @@ __global__ void __launch_bounds__(OG_THREADS, GEN < 0 ? 2 : OG_SIM_MINB) k_sim(c
             acc_add<BITS>(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs);
         }
         __syncwarp();
+        cta_lockstep(3);
     }
     if (want_metrics) {
         acc_flush<BITS>(acc, table, lane);
@@ -242,8 +259,9 @@ static int sim_launch_one(const SimCall& c) {
     if (GEN == OFDMGAN_GEN_F32) rc = upload_g(c.gparams258, slot, s);
     else if (GEN > 0) rc = upload_q(c.wrom, c.brom, slot, s);
     if (rc) return rc;
-    const int per_sm = GEN < 0 ? 2 : OG_SIM_MINB;
-    const int grid = grid_for(c.B, OG_THREADS, per_sm);
+    const int grid = grid_for(c.B, ST, 512 / ST);
+    // opt in to > 48 KB of dynamic shared memory (per device; a host-side table write, no launch)
+    OG_CHECK(cudaFuncSetAttribute(k_sim<SRC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM));
     const int n = c.n_snr * NM * NC;
     void* partials = nullptr;
     if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
@@ -258,7 +276,7 @@ static int sim_launch_one(const SimCall& c) {
     a.slope = c.slope;
     a.partials = (double*)partials;
     a.n_snr = c.n_snr;
-    k_sim<SRC, GEN><<<grid, OG_THREADS, 0, s>>>(a);
+    k_sim<SRC, GEN><<<grid, ST, SIM_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
     if (partials) {
         k_reduce_partials<<<(n + 63) / 64, 64, 0, s>>>((const double*)partials, grid, n, c.metrics);

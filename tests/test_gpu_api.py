@@ -70,7 +70,8 @@ def _pair(pkg, seed=0):
 
 
 def _grads(mod):
-    return torch.cat([p.grad.reshape(-1) for p in mod.parameters()]).cpu().numpy()
+    # a parameter autograd never reached (the penalty has no bias gradient) counts as zero
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in mod.parameters()]).cpu().numpy()
 
 
 def test_module_surface(pkg):
@@ -82,7 +83,7 @@ def test_module_surface(pkg):
     assert list(D.state_dict()) == ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "dense.weight", "dense.bias"]
     assert pkg.models.UNetGenerator is pkg.models.MiniGenerator and pkg.models.Discriminator is pkg.models.MiniDiscriminator
     assert [l["name"] for l in G.get_layer_info()][:2] == ["enc1", "bottleneck"]
-    assert all(float(p.abs().sum()) == 0 for n, p in G.named_parameters() if n.endswith("bias"))     # zero-bias init
+    assert all(float(p.detach().abs().sum()) == 0 for n, p in G.named_parameters() if n.endswith("bias"))     # zero-bias init
     with pytest.raises(pkg.OfdmGanError):
         G(torch.zeros(2, 2, 16))                             # CPU tensors: no fallback
     with pytest.raises(pkg.OfdmGanError):
