@@ -13,8 +13,9 @@
  *    on that stream unless it says "host" in its name; *_host entry points take host buffers, do their own
  *    H2D / D2H copies and synchronise the stream before returning.
  *  - returns 0 on success, a positive cudaError_t, or a negative OFDMGAN_E_* argument error.  Never throws,
- *    never calls exit().  Re-entrant across streams (up to OFDMGAN_MAX_STREAMS concurrently active streams
- *    per device, each gets its own constant-memory weight slot).
+ *    never calls exit().  Safe to call from several host threads and on several streams: the network weights live in
+ *    one constant-memory image per device, so calls are serialised inside the library (a call on a new stream is
+ *    ordered after the previous call's stream); streams do not overlap inside libofdmgan.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point returns a cudaError_t.
  */
 #ifndef OFDMGAN_H
@@ -33,11 +34,10 @@ extern "C" {
 #define OFDMGAN_D_NPARAMS 521             /* models/discriminator.py:61 */
 #define OFDMGAN_WROM_DEPTH 2048           /* rtl/ofdmGAN/weight_rom.v:14 */
 #define OFDMGAN_BROM_DEPTH 64             /* rtl/ofdmGAN/weight_rom.v:186 */
-#define OFDMGAN_MAX_STREAMS 8
 #define OFDMGAN_MAX_SNR_BINS 16
 
 #define OFDMGAN_E_ARG (-1)                /* null pointer / bad enum / bad size */
-#define OFDMGAN_E_STREAMS (-2)            /* more than OFDMGAN_MAX_STREAMS distinct streams in use */
+#define OFDMGAN_E_STREAMS (-2)            /* reserved (stream bookkeeping failure) */
 #define OFDMGAN_E_UNSUPPORTED (-3)        /* valid in the reference but not built here (named in DESIGN.md) */
 
 /* Parameter packing = torch parameters()/state_dict order, flattened (models/generator.py:129-164,

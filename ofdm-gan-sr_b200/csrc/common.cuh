@@ -14,7 +14,7 @@
     } while (0)
 
 #define OG_THREADS 128          // frames per CTA tile: one frame per thread
-#define OG_NSLOT OFDMGAN_MAX_STREAMS
+#define OG_NSLOT 1              // one scratch set per device (calls are serialised by CallGuard)
 
 namespace og {
 
@@ -27,11 +27,21 @@ const DeviceInfo& device_info(int* err);
 // CTAs for a frame-parallel kernel over B frames with `per_sm` resident CTAs per SM
 int grid_for(int64_t B, int threads, int per_sm);
 
-// ---- weight slots ----------------------------------------------------------------------------------------
-// Every kernel reads its weights through the uniform datapath from a __constant__ image (LDCU -> FFMA R,R,UR,R).
-// A call on stream S owns slot(S); the image is refreshed stream-ordered before each launch
-// (prep kernel -> staging -> cudaMemcpyToSymbolAsync D2D), so CUDA graphs replay with the current weights.
-int slot_for_stream(cudaStream_t s, int* slot);
+// ---- call serialisation ------------------------------------------------------------------------------------
+// Every kernel reads its weights as immediate constant-bank operands from one fixed __constant__ image per network
+// (weights.cuh); the image is refreshed stream-ordered before each launch (prep kernel -> staging ->
+// cudaMemcpyToSymbolAsync D2D), so CUDA graphs replay with the current weights.  The images and the library's scratch
+// buffers are therefore shared state: a CallGuard is held for the duration of every entry point that touches them.
+// It (a) serialises host threads and (b) when the stream differs from the previous call's stream, makes the new stream
+// wait for everything enqueued on the previous one (event record + stream wait), so concurrent streams stay correct -
+// they simply do not overlap inside libofdmgan.
+struct CallGuard {
+    int rc;
+    explicit CallGuard(cudaStream_t s);
+    ~CallGuard();
+    CallGuard(const CallGuard&) = delete;
+    CallGuard& operator=(const CallGuard&) = delete;
+};
 // device scratch owned by the library (per slot), `bytes` each; returns the slot's pointer
 int scratch_for_slot(int slot, size_t bytes, int which, void** ptr);
 // copy `n` floats that may live on the host or the device into device scratch (no-op if already on device)
@@ -107,6 +117,16 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
     }
     return v[0];
 }
+
+// per-lane register accumulators of transpose-reduced gradient groups: NG registers per lane = 32*NG slots per warp
+template <int NG>
+struct GradAcc {
+    float g[NG];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < NG; ++i) g[i] = 0.f;
+    }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -17,15 +17,6 @@
 
 namespace og {
 
-template <int NG>
-struct GradAcc {
-    float g[NG];
-    __device__ __forceinline__ void zero() {
-#pragma unroll
-        for (int i = 0; i < NG; ++i) g[i] = 0.f;
-    }
-};
-
 constexpr int D_NG = 17;
 constexpr int DS_C1W = 0, DS_C1B = 96, DS_FCB = 104, DS_SREAL = 105, DS_SFAKE = 106, DS_SGP = 107, DS_C2W = 128,
               DS_C2B = 512, DS_FCW = 528, DS_SLOTS = 544;

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_f32(const float* __restr
     __shared__ float4 sm[OG_THREADS * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* wsm = sm + warp * 32 * 8;
-    const float* W = c_g[slot];
+    const float* W = c_g;
     const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t base = t * OG_THREADS + warp * 32;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_q(const int16_t* __restr
     __shared__ uint4 sm[OG_THREADS * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* wsm = sm + warp * 32 * 4;
-    const float* Q = c_q[slot];
+    const float* Q = c_q;
     const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
     unsigned long long dsum = 0, dxor = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -186,7 +186,9 @@ int ofdmgan_gen_fwd_f32(const float* x_dev, const float* gparams258, float* y_de
     if (!x_dev || !y_dev || !gparams258 || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
-    if ((rc = slot_for_stream(s, &slot))) return rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    slot = 0;
     if ((rc = upload_g(gparams258, slot, s))) return rc;
     k_gen_fwd_f32<<<grid_for(B, OG_THREADS, 4), OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, leaky_slope);
     return (int)cudaGetLastError();
@@ -199,7 +201,9 @@ int ofdmgan_gen_fwd_q(const int16_t* x_dev, const int8_t* wrom_host, const int16
     if (!x_dev || !y_dev || !wrom_host || !brom_host || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
-    if ((rc = slot_for_stream(s, &slot))) return rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    slot = 0;
     if ((rc = upload_q(wrom_host, brom_host, slot, s))) return rc;
     const int grid = grid_for(B, OG_THREADS, 4);
     if (mode == OFDMGAN_GEN_Q_SPEC)
@@ -282,7 +286,9 @@ int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind,
     if ((rc = check_cfg(cfg_host, &n_snr))) return rc;
     if (!metrics_host) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = slot_for_stream(s, &slot))) return rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    slot = 0;
     const size_t bytes = (size_t)n_snr * NM * NC * sizeof(double);
     void* mdev = nullptr;
     if ((rc = scratch_for_slot(slot, bytes, 5, &mdev))) return rc;
@@ -303,7 +309,9 @@ int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int3
     if (!est_dev || !ref_dev || !aligned16(est_dev) || !aligned16(ref_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int slot, rc;
-    if ((rc = slot_for_stream(s, &slot))) return rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    slot = 0;
     const int grid = grid_for(B, OG_THREADS, 4);
     const int n = n_snr * NM * NC;
     void* partials = nullptr;

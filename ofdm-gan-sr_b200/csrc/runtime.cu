@@ -8,8 +8,6 @@ namespace og {
 
 static std::mutex g_mu;
 static DeviceInfo g_dev[64];
-static cudaStream_t g_slot_stream[64][OG_NSLOT];
-static bool g_slot_used[64][OG_NSLOT];
 static void* g_scratch[64][OG_NSLOT][8];
 static size_t g_scratch_bytes[64][OG_NSLOT][8];
 
@@ -46,25 +44,38 @@ int grid_for(int64_t B, int threads, int per_sm) {
     return (int)(tiles < cap ? tiles : cap);
 }
 
-int slot_for_stream(cudaStream_t s, int* slot) {
+static std::recursive_mutex g_call_mu;
+static cudaStream_t g_last_stream[64];
+static bool g_have_last[64];
+static cudaEvent_t g_order_ev[64];
+
+CallGuard::CallGuard(cudaStream_t s) : rc(0) {
+    g_call_mu.lock();
     int d = -1;
-    OG_CHECK(cudaGetDevice(&d));
-    if (d < 0 || d >= 64) return OFDMGAN_E_ARG;
-    std::lock_guard<std::mutex> lk(g_mu);
-    for (int i = 0; i < OG_NSLOT; ++i)
-        if (g_slot_used[d][i] && g_slot_stream[d][i] == s) {
-            *slot = i;
-            return 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess || d < 0 || d >= 64) {
+        rc = e != cudaSuccess ? (int)e : OFDMGAN_E_ARG;
+        return;
+    }
+    if (g_have_last[d] && g_last_stream[d] != s) {
+        // order this stream after everything the previous stream was given (skipped while either side is being
+        // captured into a CUDA graph: a captured stream may not wait on / be waited on by work outside the capture)
+        cudaStreamCaptureStatus c0 = cudaStreamCaptureStatusNone, c1 = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(g_last_stream[d], &c0);
+        cudaStreamIsCapturing(s, &c1);
+        (void)cudaGetLastError();
+        if (c0 == cudaStreamCaptureStatusNone && c1 == cudaStreamCaptureStatusNone) {
+            if (!g_order_ev[d]) e = cudaEventCreateWithFlags(&g_order_ev[d], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(g_order_ev[d], g_last_stream[d]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, g_order_ev[d], 0);
+            if (e != cudaSuccess) (void)cudaGetLastError();     // e.g. the previous stream was destroyed: nothing left to order against
         }
-    for (int i = 0; i < OG_NSLOT; ++i)
-        if (!g_slot_used[d][i]) {
-            g_slot_used[d][i] = true;
-            g_slot_stream[d][i] = s;
-            *slot = i;
-            return 0;
-        }
-    return OFDMGAN_E_STREAMS;
+    }
+    g_last_stream[d] = s;
+    g_have_last[d] = true;
 }
+
+CallGuard::~CallGuard() { g_call_mu.unlock(); }
 
 int scratch_for_slot(int slot, size_t bytes, int which, void** ptr) {
     int d = -1;

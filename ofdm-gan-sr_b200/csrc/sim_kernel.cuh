@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(ST, 512 / ST) k_sim(const __grid_constant__ Si
         if (GEN == OFDMGAN_GEN_F32) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) { xin[0][i] = nr[i]; xin[1][i] = ni[i]; }
-            gen_fwd_f32_infer(c_g[a.wslot], a.slope, xin, yo);
+            gen_fwd_f32_infer(c_g, a.slope, xin, yo);
         } else {
             // Q8.8 by truncation toward zero (proof/verification.py:297-298); back to float by /256
 #pragma unroll
             for (int i = 0; i < 16; ++i) { xin[0][i] = truncf(nr[i] * 256.0f); xin[1][i] = truncf(ni[i] * 256.0f); }
-            if (GEN == OFDMGAN_GEN_Q_SPEC) gen_fwd_q_spec(c_q[a.wslot], xin, yo); else gen_fwd_q_rtl(c_q[a.wslot], xin, yo);
+            if (GEN == OFDMGAN_GEN_Q_SPEC) gen_fwd_q_spec(c_q, xin, yo); else gen_fwd_q_rtl(c_q, xin, yo);
 #pragma unroll
             for (int i = 0; i < 16; ++i) { yo[0][i] *= 0.00390625f; yo[1][i] *= 0.00390625f; }
         }
@@ -255,7 +255,9 @@ template <int SRC, int GEN>
 static int sim_launch_one(const SimCall& c) {
     cudaStream_t s = c.stream;
     int slot = 0, rc;
-    if ((rc = slot_for_stream(s, &slot))) return rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    slot = 0;
     if (GEN == OFDMGAN_GEN_F32) rc = upload_g(c.gparams258, slot, s);
     else if (GEN > 0) rc = upload_q(c.wrom, c.brom, slot, s);
     if (rc) return rc;

@@ -1,6 +1,11 @@
 // Constant-memory weight images and their stream-ordered refresh.  Included by every TU that runs a network
 // (each TU owns its own __constant__ bank, so each gets private copies of these symbols).
 //
+// There is ONE image per network at a FIXED constant-bank address, so after unrolling every weight is an immediate
+// constant operand of its FFMA (FFMA R, R, c[0x3][imm], R): no load instruction and no register per weight - this is
+// what lets the training kernels fit 128 registers.  Calls on different streams are ordered against each other by
+// CallGuard (common.cuh), which is what keeps a single image safe.
+//
 // G image (OG_G_IMG floats): raw enc1 / bottleneck weights + biases, and the two convolutions that follow a
 // nearest x2 upsample (dec1, out_conv; models/generator.py:196-205) FOLDED over the duplicated samples:
 //   z[2p]   = w0*a[p-1] + (w1+w2)*a[p]        z[2p+1] = (w0+w1)*a[p] + w2*a[p+1]
@@ -31,9 +36,9 @@ constexpr int OG_D_IMG = 528;
 constexpr int OG_Q_IMG = 256;
 constexpr int QI_BIAS = 232;
 
-static __constant__ __align__(16) float c_g[OG_NSLOT][OG_G_IMG];
-static __constant__ __align__(16) float c_d[OG_NSLOT][OG_D_IMG];
-static __constant__ __align__(16) float c_q[OG_NSLOT][OG_Q_IMG];
+static __constant__ __align__(16) float c_g[OG_G_IMG];
+static __constant__ __align__(16) float c_d[OG_D_IMG];
+static __constant__ __align__(16) float c_q[OG_Q_IMG];
 
 static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
     int i = threadIdx.x;
@@ -70,7 +75,7 @@ static int upload_g(const float* params258, int slot, cudaStream_t s) {
     if (rc) return rc;
     prep_g_image<<<1, OG_G_IMG, 0, s>>>(dev, (float*)img);
     OG_CHECK(cudaGetLastError());
-    OG_CHECK(cudaMemcpyToSymbolAsync(c_g, img, OG_G_IMG * sizeof(float), (size_t)slot * OG_G_IMG * sizeof(float),
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_g, img, OG_G_IMG * sizeof(float), 0,
                                      cudaMemcpyDeviceToDevice, s));
     return 0;
 }
@@ -84,7 +89,7 @@ static int upload_d(const float* params521, int slot, cudaStream_t s) {
     if (rc) return rc;
     prep_d_image<<<1, OG_D_IMG, 0, s>>>(dev, (float*)img);
     OG_CHECK(cudaGetLastError());
-    OG_CHECK(cudaMemcpyToSymbolAsync(c_d, img, OG_D_IMG * sizeof(float), (size_t)slot * OG_D_IMG * sizeof(float),
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_d, img, OG_D_IMG * sizeof(float), 0,
                                      cudaMemcpyDeviceToDevice, s));
     return 0;
 }
@@ -96,7 +101,7 @@ static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot,
     for (int i = 0; i < 226; ++i) img[i] = (float)wrom_host[i] * (1.0f / 128.0f);
     for (int i = 0; i < 18; ++i) img[QI_BIAS + i] = (float)brom_host[i];
     // pageable source: the runtime stages it before returning, so the stack buffer may die afterwards
-    OG_CHECK(cudaMemcpyToSymbolAsync(c_q, img, sizeof img, (size_t)slot * sizeof img, cudaMemcpyHostToDevice, s));
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_q, img, sizeof img, 0, cudaMemcpyHostToDevice, s));
     return 0;
 }
 
