@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(OG_THREADS, CRITIC_PER_SM) k_critic2(const __g
             tile_fill_f32(kind == 1 ? a.real : a.fake, base, a.B, t_a, lane);
             __syncwarp();
             const float g = live ? (kind == 1 ? -1.0f : 1.0f) : 0.0f;
-            const float sc = cs_score_pass(W, a.slope, g, t_a, t_c, acc, lane);
+            const float sc = cs_score_pass<false>(W, a.slope, g, t_a, t_c, acc, lane);
             if (live) {
                 if (kind == 1) s_real += sc; else s_fake += sc;
             }

@@ -213,8 +213,10 @@ __device__ __forceinline__ void cs_grads_conv1_row(const float (&dz1)[8][8], con
 }
 
 // ---- one Wasserstein term: L += g * D(cand, cond).  Returns the score; accumulates dL/dtheta.
-__device__ __forceinline__ float cs_score_pass(const float* W, float slope, float g, const float4* t_cand, const float4* t_cond,
-                                               SAcc& acc, int lane) {
+// NEED_DU: additionally overwrites the thread's rows of t_cand / t_cond with dL/d cand and dL/d cond.
+template <bool NEED_DU>
+__device__ __forceinline__ float cs_score_pass(const float* W, float slope, float g, float4* t_cand, float4* t_cond, SAcc& acc,
+                                               int lane) {
     uint64_t m1, m2;
     float score;
     {
@@ -240,6 +242,25 @@ __device__ __forceinline__ float cs_score_pass(const float* W, float slope, floa
         for (int j = 0; j < 8; ++j) extra[j] = ic == 0 ? c1b[j] : 0.f;
         if (ic == 1) extra[0] = g;                              // dense.bias
         cs_grads_conv1_row(dz1, row, extra, ic, acc, lane);
+    }
+    if (NEED_DU) {                                              // du = conv1^T(dz1), one input row per iteration
+#pragma unroll 1
+        for (int ic = 0; ic < 4; ++ic) {
+            const float* w = W + DP_C1_W + ic * 3;
+            float row[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) row[i] = 0.f;
+#pragma unroll
+            for (int oc = 0; oc < 8; ++oc)
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int i = 2 * p + k - 1;
+                        if (i >= 0) row[i] = fmaf(w[oc * 12 + k], dz1[oc][p], row[i]);
+                    }
+            row_write(ic < 2 ? t_cand : t_cond, lane, ic & 1, row);
+        }
     }
     return score;
 }

@@ -1,7 +1,7 @@
 // libofdmgan generator-side training kernels: the fused generator step of CWGAN-GP (train.py:282-299), the API-level
 // MiniGenerator backward, and fused Adam.   ofdmgan_gen_step / ofdmgan_gen_bwd_f32 / ofdmgan_adam
 #include "train_common.cuh"
-#include "genbwd_device.cuh"
+#include "gen_stream.cuh"
 
 namespace og {
 
@@ -17,16 +17,26 @@ struct GenStepArgs {
     float* partials;          // [grid][GS_SLOTS]
 };
 
-__global__ void __launch_bounds__(OG_THREADS) k_gen_step(const __grid_constant__ GenStepArgs a) {
-    __shared__ float4 sm[3 * OG_THREADS * 8];
+// Per sample: (1) fake = G(noisy); (2) adversarial term through the critic -> d L / d fake, plus the L1 term;
+// (3) G forward again with its tape and backward (recomputing 1.2k FMAs is cheaper than carrying 130 activations across
+// the critic pass).  Register-lean rolled-loop passes (gen_stream.cuh, critic_stream.cuh); four resident 4 KB tiles per
+// warp: noisy | clean -> upstream gradient | fake -> parked rows | scratch.
+constexpr int GENSTEP_PER_SM = 3;
+constexpr size_t GENSTEP_SMEM = (size_t)4 * OG_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * OG_THREADS * sizeof(float);
+
+__global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const __grid_constant__ GenStepArgs a) {
+    extern __shared__ float4 sm[];
+    float* sacc = reinterpret_cast<float*>(sm + 4 * OG_THREADS * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* t_noisy = sm + warp * TILE4;
-    float4* t_clean = sm + (NWARP + warp) * TILE4;
-    float4* t_fake = sm + (2 * NWARP + warp) * TILE4;
+    float4* t_x = sm + warp * TILE4;
+    float4* t_c = sm + (NWARP + warp) * TILE4;
+    float4* t_y = sm + (2 * NWARP + warp) * TILE4;
+    float4* t_p = sm + (3 * NWARP + warp) * TILE4;
     const float* WG = c_g;
     const float* WD = c_d;
-    GradAcc<G_NG> acc;
-    acc.zero();
+    SAcc acc{sacc + threadIdx.x, OG_THREADS};
+#pragma unroll
+    for (int g = 0; g < GSX_NG; ++g) sacc[g * OG_THREADS + threadIdx.x] = 0.f;
     float s_d = 0.f, s_l1 = 0.f;
     const float rec_g = a.rec_w * 0.03125f;                      // rec_w / 32: l1_loss is a mean over B*32 elements
     const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
@@ -35,68 +45,86 @@ __global__ void __launch_bounds__(OG_THREADS) k_gen_step(const __grid_constant__
         if (base >= a.B) continue;
         const bool live = base + lane < a.B;
         __syncwarp();
-        tile_fill_f32(a.noisy, base, a.B, t_noisy, lane);
-        tile_fill_f32(a.clean, base, a.B, t_clean, lane);
+        tile_fill_f32(a.noisy, base, a.B, t_x, lane);
+        tile_fill_f32(a.clean, base, a.B, t_c, lane);
         __syncwarp();
-        // pass 1: fake = G(noisy), kept in the warp's third tile
+        // (1) fake = G(noisy) -> t_y
         {
-            float x[2][16], y[2][16];
-            tile_read_f32(t_noisy, lane, x);
-            gen_fwd_f32_infer(WG, a.slope, x, y);
-            tile_write_f32(t_fake, lane, y);
+            float a1[4][8], a2[8][4], sk[4][8];
+            uint32_t z;
+            gs_fwd<false>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z);
         }
-        __syncwarp();
-        if (a.fake_out) tile_drain_f32(a.fake_out, base, a.B, t_fake, lane);
-        // pass 2: adversarial term through the critic, input gradient w.r.t. the candidate rows only
-        float dy[2][16];
+        if (a.fake_out) {
+            __syncwarp();
+            tile_drain_f32(a.fake_out, base, a.B, t_y, lane);
+            __syncwarp();
+        }
+        // (2) critic on (fake, noisy): d(-adv_w * D)/d fake, + rec_w * sign(fake - clean)/32 -> upstream gradient rows in t_c
         {
-            float dz1[8][8], score;
+            float dz1[8][8];
             {
                 uint64_t m1, m2;
+                float score;
                 {
-                    float a1[8][8], pool[16], cand[2][16], cond[2][16];
-                    tile_read_f32(t_fake, lane, cand);
-                    tile_read_f32(t_noisy, lane, cond);
-                    disc_fwd(WD, a.slope, cand, cond, a1, m2, pool, score);
-                    m1 = sign_mask(a1);
+                    float a1[8][8];
+                    m1 = cs_conv1_fwd(WD, a.slope, t_y, t_x, lane, a1);
+                    m2 = cs_conv2_fwd<false>(WD, a.slope, 0.f, a1, acc, lane, score);
                 }
-                disc_bwd_to_z1(WD, a.slope, live ? -a.adv_w : 0.f, m1, m2, dz1);
+                if (live) s_d += score;
+                cs_bwd_to_z1(WD, a.slope, live ? -a.adv_w : 0.f, m1, m2, dz1);
             }
-            disc_bwd_to_input<0, 2>(WD, dz1, dy);
-            if (live) s_d += score;
-        }
-        // pass 3: + reconstruction term, then backward through G (forward recomputed with its tape: cheaper than
-        // keeping 130 activations live across the critic pass)
-        {
-            float x[2][16], y[2][16], a1[4][8], a2[8][4], sk[4][8], none[2][16];
-            uint32_t z3pos;
-            tile_read_f32(t_noisy, lane, x);
-            gen_fwd_f32<true>(WG, a.slope, x, y, a1, a2, sk, z3pos);
-            {
-                float c[2][16];
-                tile_read_f32(t_clean, lane, c);
+#pragma unroll 1
+            for (int ic = 0; ic < 2; ++ic) {
+                const float* w = WD + DP_C1_W + ic * 3;
+                float row[16], y[16], c[16];
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
+                for (int i = 0; i < 16; ++i) row[i] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e = y[r][i] - c[r][i];
-                        if (live) {
-                            s_l1 += fabsf(e);
-                            dy[r][i] += e > 0.f ? rec_g : (e < 0.f ? -rec_g : 0.f);     // l1_loss backward: sign(e)
-                        } else {
-                            dy[r][i] = 0.f;
+                for (int oc = 0; oc < 8; ++oc)
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int i = 2 * p + k - 1;
+                            if (i >= 0) row[i] = fmaf(w[oc * 12 + k], dz1[oc][p], row[i]);
                         }
+                row_read(t_y, lane, ic, y);
+                row_read(t_c, lane, ic, c);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float e = y[i] - c[i];
+                    if (live) {
+                        s_l1 += fabsf(e);
+                        row[i] += e > 0.f ? rec_g : (e < 0.f ? -rec_g : 0.f);       // l1_loss backward: sign(e)
+                    } else {
+                        row[i] = 0.f;
                     }
+                }
+                row_write(t_c, lane, ic, row);
             }
-            gen_bwd<false>(WG, a.slope, x, a1, a2, sk, z3pos, y, dy, acc, lane, none);
+        }
+        // (3) forward with tape, backward
+        {
+            float a1[4][8], a2[8][4], sk[4][8];
+            uint32_t z3pos;
+            gs_fwd<true>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z3pos);
+            gs_bwd<false>(WG, a.slope, t_x, t_y, t_c, t_p, lane, a1, a2, sk, z3pos, acc);
         }
     }
     {
         const float d = warp_sum(s_d), l = warp_sum(s_l1);
-        if (lane == GS_S0 - 288) acc.g[9] += d;
-        if (lane == GS_S0 + 1 - 288) acc.g[9] += l;
+        if (lane == GS_S0 - 288) acc.add(9, d);
+        if (lane == GS_S0 + 1 - 288) acc.add(9, l);
     }
-    cta_store_partials<G_NG>(acc, reinterpret_cast<float*>(sm), a.partials + (size_t)blockIdx.x * GS_SLOTS);
+    __syncthreads();
+    float* row = a.partials + (size_t)blockIdx.x * GS_SLOTS;
+    for (int s = threadIdx.x; s < GS_SLOTS; s += OG_THREADS) {
+        const int grp = s >> 5, j = s & 31;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) t += sacc[grp * OG_THREADS + w * 32 + j];
+        row[s] = t;
+    }
 }
 
 // generator parameter gradient (torch order) from the summed slot table
@@ -142,18 +170,21 @@ __global__ void __launch_bounds__(GS_SLOTS) k_finalize_gen(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ generator backward (API)
-// (dx is always formed: the dx-less instantiation trips a ptxas 12.9 register-allocation failure, and this entry point
-// is the API-level backward, not the training hot path - ofdmgan_gen_step is.)
-__global__ void __launch_bounds__(OG_THREADS) k_gen_bwd(const float* __restrict__ x, const float* __restrict__ dy,
-                                                        float* __restrict__ dx, float* __restrict__ partials, int64_t B, int slot,
-                                                        float slope) {
-    __shared__ float4 sm[2 * OG_THREADS * 8];
+// what autograd needs for MiniGenerator.forward: dparams = sum_b backward(dy_b) and (optionally) dx
+template <bool NEED_DX>
+__global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_bwd(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                        float* __restrict__ dx, float* __restrict__ partials, int64_t B,
+                                                                        float slope) {
+    extern __shared__ float4 sm[];
+    float* sacc = reinterpret_cast<float*>(sm + 4 * OG_THREADS * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* t_x = sm + warp * TILE4;
     float4* t_dy = sm + (NWARP + warp) * TILE4;
-    const float* W = c_g;
-    GradAcc<G_NG> acc;
-    acc.zero();
+    float4* t_y = sm + (2 * NWARP + warp) * TILE4;
+    float4* t_p = sm + (3 * NWARP + warp) * TILE4;
+    SAcc acc{sacc + threadIdx.x, OG_THREADS};
+#pragma unroll
+    for (int g = 0; g < GSX_NG; ++g) sacc[g * OG_THREADS + threadIdx.x] = 0.f;
     const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t base = t * OG_THREADS + warp * 32;
@@ -162,18 +193,24 @@ __global__ void __launch_bounds__(OG_THREADS) k_gen_bwd(const float* __restrict_
         tile_fill_f32(x, base, B, t_x, lane);
         tile_fill_f32(dy, base, B, t_dy, lane);            // rows beyond B are zero-filled: they contribute nothing
         __syncwarp();
-        float xi[2][16], y[2][16], a1[4][8], a2[8][4], sk[4][8], g[2][16], dxo[2][16];
+        float a1[4][8], a2[8][4], sk[4][8];
         uint32_t z3pos;
-        tile_read_f32(t_x, lane, xi);
-        gen_fwd_f32<true>(W, slope, xi, y, a1, a2, sk, z3pos);
-        tile_read_f32(t_dy, lane, g);
-        gen_bwd<true>(W, slope, xi, a1, a2, sk, z3pos, y, g, acc, lane, dxo);
-        if (dx) {
+        gs_fwd<true>(c_g, slope, t_x, t_y, t_p, lane, a1, a2, sk, z3pos);
+        gs_bwd<NEED_DX>(c_g, slope, t_x, t_y, t_dy, t_p, lane, a1, a2, sk, z3pos, acc);
+        if (NEED_DX) {
             __syncwarp();
-            tile_store_f32(dx, base, B, t_dy, lane, dxo);
+            tile_drain_f32(dx, base, B, t_dy, lane);
         }
     }
-    cta_store_partials<G_NG>(acc, reinterpret_cast<float*>(sm), partials + (size_t)blockIdx.x * GS_SLOTS);
+    __syncthreads();
+    float* row = partials + (size_t)blockIdx.x * GS_SLOTS;
+    for (int s = threadIdx.x; s < GS_SLOTS; s += OG_THREADS) {
+        const int grp = s >> 5, j = s & 31;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) t += sacc[grp * OG_THREADS + w * 32 + j];
+        row[s] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ Adam
@@ -217,14 +254,15 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
     slot = 0;
     if ((rc = upload_d(dparams521, slot, s))) return rc;
     if ((rc = upload_g(gparams258, slot, s))) return rc;
-    const int grid = grid_for(B_local, OG_THREADS, TRAIN_PER_SM);
+    const int grid = grid_for(B_local, OG_THREADS, GENSTEP_PER_SM);
     void* partials = nullptr;
     if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
+    OG_CHECK(cudaFuncSetAttribute(k_gen_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
     GenStepArgs a{};
     a.clean = clean_dev; a.noisy = noisy_dev; a.fake_out = fake_out_dev;
     a.B = B_local; a.slot = slot; a.slope = leaky_slope; a.adv_w = adv_weight; a.rec_w = rec_weight;
     a.partials = (float*)partials;
-    k_gen_step<<<grid, OG_THREADS, 0, s>>>(a);
+    k_gen_step<<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
     k_finalize_gen<<<1, GS_SLOTS, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
                                           out_dev, out_dev + OFDMGAN_G_NPARAMS);
@@ -246,10 +284,16 @@ int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float
     if ((rc = guard.rc)) return rc;
     slot = 0;
     if ((rc = upload_g(gparams258, slot, s))) return rc;
-    const int grid = grid_for(B, OG_THREADS, TRAIN_PER_SM);
+    const int grid = grid_for(B, OG_THREADS, GENSTEP_PER_SM);
     void* partials = nullptr;
     if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
-    k_gen_bwd<<<grid, OG_THREADS, 0, s>>>(x_dev, dy_dev, dx_dev, (float*)partials, B, slot, leaky_slope);
+    if (dx_dev) {
+        OG_CHECK(cudaFuncSetAttribute(k_gen_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
+        k_gen_bwd<true><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(x_dev, dy_dev, dx_dev, (float*)partials, B, leaky_slope);
+    } else {
+        OG_CHECK(cudaFuncSetAttribute(k_gen_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
+        k_gen_bwd<false><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(x_dev, dy_dev, nullptr, (float*)partials, B, leaky_slope);
+    }
     OG_CHECK(cudaGetLastError());
     k_finalize_gen<<<1, GS_SLOTS, 0, s>>>((const float*)partials, grid, 1.0, 0.0, 0.0, dparams258_dev, nullptr);
     return (int)cudaGetLastError();
