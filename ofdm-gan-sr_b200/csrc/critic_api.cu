@@ -75,15 +75,14 @@ __global__ void __launch_bounds__(OG_THREADS, CAPI_PER_SM) k_disc_bwd(const floa
     }
 }
 
-// fixed-order sum over CTA rows, slot -> parameter order
-__global__ void __launch_bounds__(CS_SLOTS) k_finalize_dparams(const float* __restrict__ partials, int nblocks, float* __restrict__ grads) {
-    __shared__ double s[CS_SLOTS];
-    const int t = threadIdx.x;
-    double sum = 0.0;
-    for (int b = 0; b < nblocks; ++b) sum += (double)partials[(size_t)b * CS_SLOTS + t];
-    s[t] = sum;
-    __syncthreads();
-    if (t < OFDMGAN_D_NPARAMS) grads[t] = (float)s[cs_slot_of(t)];
+// one block per accumulator group: fixed-order sum over CTA rows, slot -> parameter order
+__global__ void __launch_bounds__(1024) k_finalize_dparams(const float* __restrict__ partials, int nblocks, float* __restrict__ grads) {
+    __shared__ double red[32 * 32], total[32];
+    reduce_group_rows(partials, nblocks, CS_SLOTS, blockIdx.x, red, total);
+    if (threadIdx.x < 32) {
+        const int i = cs_param_of(blockIdx.x, threadIdx.x);
+        if (i >= 0) grads[i] = (float)total[threadIdx.x];
+    }
 }
 
 }  // namespace og
@@ -129,7 +128,7 @@ int ofdmgan_disc_bwd_f32(const float* cand_dev, const float* cond_dev, const flo
         k_disc_bwd<false><<<grid, OG_THREADS, 0, s>>>(cand_dev, cond_dev, g_dev, nullptr, nullptr, (float*)partials, B, leaky_slope);
     OG_CHECK(cudaGetLastError());
     if (dparams521_dev) {
-        k_finalize_dparams<<<1, CS_SLOTS, 0, s>>>((const float*)partials, grid, dparams521_dev);
+        k_finalize_dparams<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, dparams521_dev);
         OG_CHECK(cudaGetLastError());
     }
     return 0;

@@ -116,23 +116,21 @@ __global__ void __launch_bounds__(OG_THREADS, CRITIC_PER_SM) k_critic2(const __g
     }
 }
 
-__global__ void __launch_bounds__(CS_SLOTS) k_finalize_critic2(const float* __restrict__ partials, int nblocks, double inv_b,
-                                                               double gp_weight, float* __restrict__ grads, float* __restrict__ stats,
-                                                               int stat_mode) {
-    __shared__ double s[CS_SLOTS];
-    const int t = threadIdx.x;
-    double s0 = 0.0, s1 = 0.0;
-    int b = 0;
-    for (; b + 1 < nblocks; b += 2) {
-        s0 += (double)partials[(size_t)b * CS_SLOTS + t];
-        s1 += (double)partials[(size_t)(b + 1) * CS_SLOTS + t];
+// One block per accumulator group: fixed-order sum over the CTA rows, slot -> parameter order, 1/B scaling; the block of
+// group 1 also writes the loss statistics.   grads (nullable): 521 floats.  stats (nullable): stat_mode 0 -> the 5 scalars
+// of train.py:255-261 (+2 pad), stat_mode 1 -> 1 float = mean penalty.
+__global__ void __launch_bounds__(1024) k_finalize_critic2(const float* __restrict__ partials, int nblocks, double inv_b,
+                                                           double gp_weight, float* __restrict__ grads, float* __restrict__ stats,
+                                                           int stat_mode) {
+    __shared__ double red[32 * 32], total[32];
+    const int grp = blockIdx.x;
+    reduce_group_rows(partials, nblocks, CS_SLOTS, grp, red, total);
+    if (threadIdx.x < 32) {
+        const int i = cs_param_of(grp, threadIdx.x);
+        if (grads && i >= 0) grads[i] = (float)(total[threadIdx.x] * inv_b);
     }
-    if (b < nblocks) s0 += (double)partials[(size_t)b * CS_SLOTS + t];
-    s[t] = s0 + s1;
-    __syncthreads();
-    if (grads && t < OFDMGAN_D_NPARAMS) grads[t] = (float)(s[cs_slot_of(t)] * inv_b);
-    if (stats && t == 0) {
-        const double dr = s[CS_SREAL] * inv_b, df = s[CS_SFAKE] * inv_b, gp = s[CS_SGP] * inv_b;
+    if (grp == 1 && stats && threadIdx.x == 0) {
+        const double dr = total[CS_SREAL - 32] * inv_b, df = total[CS_SFAKE - 32] * inv_b, gp = total[CS_SGP - 32] * inv_b;
         if (stat_mode == 0) {
             stats[0] = (float)(df - dr + gp_weight * gp);
             stats[1] = (float)(dr - df);
@@ -189,7 +187,7 @@ int ofdmgan_gradient_penalty(const float* real_dev, const float* fake_dev, const
     void* partials;
     if ((rc = launch_critic(false, real_dev, fake_dev, cond_dev, alpha_dev, seed, sample0, alpha_iter, dparams521, 1.0f, leaky_slope, B,
                             dparams521_dev != nullptr, nullptr, s, &slot, &grid, &partials))) return rc;
-    k_finalize_critic2<<<1, CS_SLOTS, 0, s>>>((const float*)partials, grid, 1.0 / (double)B, 1.0, dparams521_dev, gp_dev, 1);
+    k_finalize_critic2<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B, 1.0, dparams521_dev, gp_dev, 1);
     return (int)cudaGetLastError();
 }
 
@@ -208,7 +206,7 @@ int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const fl
     void* partials;
     if ((rc = launch_critic(true, clean_dev, fake_dev, noisy_dev, alpha_dev, seed, sample0, alpha_iter, dparams521, gp_weight,
                             leaky_slope, B_local, true, nullptr, s, &slot, &grid, &partials))) return rc;
-    k_finalize_critic2<<<1, CS_SLOTS, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev,
+    k_finalize_critic2<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev,
                                               out_dev + OFDMGAN_D_NPARAMS, 0);
     return (int)cudaGetLastError();
 }

@@ -39,6 +39,12 @@ __host__ __device__ constexpr int cs_slot_of(int i) {
                          : CS_FCB;
 }
 
+// accumulator slot (group, j) -> parameter index (torch order), or -1 for a spare / statistics slot
+__host__ __device__ constexpr int cs_param_of(int grp, int j) {
+    return grp < 4 ? (j < 24 ? ((j / 3) * 4 + grp) * 3 + j % 3 : (grp == 0 ? DP_C1_B + (j - 24) : (grp == 1 && j == 24 ? DP_FC_B : -1)))
+                   : (j < 24 ? DP_C2_W + (grp - 4) * 24 + j : (j == 24 ? DP_C2_B + (grp - 4) : (j == 25 ? DP_FC_W + (grp - 4) : -1)));
+}
+
 // shared-memory gradient accumulator of one CTA: [CS_NG][threads]
 struct SAcc {
     float* base;       // + threadIdx.x already applied

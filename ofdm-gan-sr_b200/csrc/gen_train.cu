@@ -127,39 +127,36 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
     }
 }
 
-// generator parameter gradient (torch order) from the summed slot table
-__device__ __forceinline__ double gen_param_from_slots(const double* s, int i) {
-    if (i < GP_ENC_B) return s[GS_ENCW + i];
-    if (i < GP_BN_W) return s[GS_ENCB + (i - GP_ENC_B)];
-    if (i < GP_BN_B) return s[GS_BNW + (i - GP_BN_W)];
-    if (i < GP_DEC_W) return s[GS_BNB + (i - GP_BN_B)];
-    if (i < GP_DEC_B) {
-        const int j = i - GP_DEC_W, pair = j / 3, k = j % 3;
-        const double* F = s + GS_DECF + pair * 4;
-        return k == 0 ? F[0] + F[2] : (k == 1 ? F[1] + F[2] : F[1] + F[3]);
+// One block per accumulator group: fixed-order sum over the CTA rows, then slot -> parameter order.  The two
+// upsample+conv layers accumulate gradients of their FOLDED taps {F0=w0, F1=w1+w2, F2=w0+w1, F3=w2}; the raw taps follow
+// linearly: dw0 = dF0+dF2, dw1 = dF1+dF2, dw2 = dF1+dF3 (all four slots of a pair sit in the same group).
+// stats (nullable): g_loss, adv_loss, rec_loss (train.py:301-305) + 3 pad, written by the block of group 9.
+__global__ void __launch_bounds__(1024) k_finalize_gen(const float* __restrict__ partials, int nblocks, double inv_b, double adv_w,
+                                                       double rec_w, float* __restrict__ grads, float* __restrict__ stats) {
+    __shared__ double red[32 * 32], total[32];
+    const int grp = blockIdx.x, j = threadIdx.x;
+    reduce_group_rows(partials, nblocks, GS_SLOTS, grp, red, total);
+    if (grads && j < 32) {
+        int i = -1;
+        double v = total[j];
+        if (grp <= 4) {                                           // folded layers: thread (pair, t<3) emits raw tap k = t
+            const int pair = j >> 2, k = j & 3;
+            const double* F = total + pair * 4;
+            if (k < 3) {
+                v = k == 0 ? F[0] + F[2] : (k == 1 ? F[1] + F[2] : F[1] + F[3]);
+                i = grp == 0 ? GP_OUT_W + pair * 3 + k : GP_DEC_W + ((grp - 1) * 8 + pair) * 3 + k;
+            }
+        } else if (grp <= 7) {
+            i = GP_BN_W + (grp - 5) * 32 + j;
+        } else if (grp == 8) {
+            i = j < 24 ? GP_ENC_W + j : (j < 28 ? GP_ENC_B + (j - 24) : -1);
+        } else {
+            i = j < 8 ? GP_BN_B + j : (j < 12 ? GP_DEC_B + (j - 8) : (j < 14 ? GP_OUT_B + (j - 12) : -1));
+        }
+        if (i >= 0) grads[i] = (float)(v * inv_b);
     }
-    if (i < GP_OUT_W) return s[GS_DECB + (i - GP_DEC_B)];
-    if (i < GP_OUT_B) {
-        const int j = i - GP_OUT_W, pair = j / 3, k = j % 3;
-        const double* F = s + GS_OUTF + pair * 4;
-        return k == 0 ? F[0] + F[2] : (k == 1 ? F[1] + F[2] : F[1] + F[3]);
-    }
-    return s[GS_OUTB + (i - GP_OUT_B)];
-}
-
-// stats (nullable): g_loss, adv_loss, rec_loss (train.py:301-305) + 3 pad
-__global__ void __launch_bounds__(GS_SLOTS) k_finalize_gen(const float* __restrict__ partials, int nblocks, double inv_b,
-                                                           double adv_w, double rec_w, float* __restrict__ grads,
-                                                           float* __restrict__ stats) {
-    __shared__ double s[GS_SLOTS];
-    const int t = threadIdx.x;
-    double sum = 0.0;
-    for (int b = 0; b < nblocks; ++b) sum += (double)partials[(size_t)b * GS_SLOTS + t];
-    s[t] = sum;
-    __syncthreads();
-    if (grads && t < OFDMGAN_G_NPARAMS) grads[t] = (float)(gen_param_from_slots(s, t) * inv_b);
-    if (stats && t == 0) {
-        const double adv = -s[GS_S0] * inv_b, rec = s[GS_S0 + 1] * inv_b * 0.03125;
+    if (grp == 9 && stats && j == 0) {
+        const double adv = -total[GS_S0 - 288] * inv_b, rec = total[GS_S0 + 1 - 288] * inv_b * 0.03125;
         stats[0] = (float)(adv_w * adv + rec_w * rec);
         stats[1] = (float)adv;
         stats[2] = (float)rec;
@@ -264,7 +261,7 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
     a.partials = (float*)partials;
     k_gen_step<<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
-    k_finalize_gen<<<1, GS_SLOTS, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
+    k_finalize_gen<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
                                           out_dev, out_dev + OFDMGAN_G_NPARAMS);
     return (int)cudaGetLastError();
 }
@@ -295,7 +292,7 @@ int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float
         k_gen_bwd<false><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(x_dev, dy_dev, nullptr, (float*)partials, B, leaky_slope);
     }
     OG_CHECK(cudaGetLastError());
-    k_finalize_gen<<<1, GS_SLOTS, 0, s>>>((const float*)partials, grid, 1.0, 0.0, 0.0, dparams258_dev, nullptr);
+    k_finalize_gen<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0, 0.0, 0.0, dparams258_dev, nullptr);
     return (int)cudaGetLastError();
 }
 

@@ -28,6 +28,25 @@ __device__ __forceinline__ void cta_store_partials(const GradAcc<NG>& acc, float
 }
 
 
+// Sum one 32-slot group over all CTA partial rows, in a fixed order (deterministic): launched with 1024 threads per
+// block, one block per group.  Warp w adds rows w, w+32, ... (one coalesced 128-byte read per row), then warp 0 adds the
+// 32 warp totals in order.  Returns the group's 32 totals in `total` (shared) after a barrier.
+__device__ __forceinline__ void reduce_group_rows(const float* __restrict__ partials, int nblocks, int slots, int grp, double* red /*[32][32]*/,
+                                                  double* total /*[32]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int b = warp; b < nblocks; b += 32) s += (double)partials[(size_t)b * slots + grp * 32 + lane];
+    red[warp * 32 + lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double a = 0.0;
+#pragma unroll 4
+        for (int w = 0; w < 32; ++w) a += red[w * 32 + lane];
+        total[lane] = a;
+    }
+    __syncthreads();
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // resident CTAs per SM of the 255-register training kernels (2 x 128 threads)
