@@ -108,7 +108,7 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank):
+def run_reference(args, rank, saved_stdout):
     """CPU restatement of the reference path on the host cores, bounded sample per step."""
     if rank != 0:
         return
@@ -135,11 +135,25 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} frames per step of the same workload (oracle/channel.c + fp32_models.c, OpenMP)"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(saved_stdout, line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def _quiet_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout) are sent to stderr."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    saved_stdout = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -154,7 +168,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, saved_stdout)
         return
 
     import torch
@@ -342,7 +356,7 @@ def main():
                         "api": "ofdmgan_sim_gen_metrics_host (host weights in, host metric table out, synchronous)"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "also": also,
                 "per_step_ms": per_step_ms}
-        print(json.dumps(line), flush=True)
+        _emit(saved_stdout, line)
     if world > 1:
         dist.destroy_process_group()
 
