@@ -291,6 +291,23 @@ def main():
             also["fixed_point_" + tag] = {"frames_per_s": Q_FRAMES * world / (ms * 1e-3), "ms_per_launch": ms, "frames": Q_FRAMES,
                                           "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak}
         del xq, yq
+        # ---- config 1 at scale: fp32 MiniGenerator forward over HBM-resident frames (256 B of traffic per frame)
+        xf = torch.randn(Q_FRAMES, 2, 16, generator=g, device=dev)
+        for _ in range(3):
+            yf = ops.gen_fwd_f32(xf, gp_d)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            yf = ops.gen_fwd_f32(xf, gp_d)                          # 4 GiB of traffic per launch >> 126 MB L2
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / K
+        gbs = Q_FRAMES * 256 / (ms * 1e-3) / 1e9
+        also["generator_fp32_hbm"] = {"frames_per_s": Q_FRAMES * world / (ms * 1e-3), "ms_per_launch": ms, "frames": Q_FRAMES,
+                                      "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak,
+                                      "fp32_tflops": Q_FRAMES * FLOP_GEN / (ms * 1e-3) / 1e12}
+        del xf, yf
         # ---- config 3: CWGAN-GP step, 65,536 frames per GPU, data-parallel
         Bt = TRAIN_FRAMES_PER_GPU
         tcfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
@@ -325,7 +342,7 @@ def main():
                          "fp32_tflops_per_gpu": tflops, "fp32_frac_of_ffma_peak": tflops / ffma,
                          "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"]}
-        launches += 2 * K * 2 + K * trainer.launches_per_step()
+        launches += 2 * K * 1 + K * 2 + K * trainer.launches_per_step()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:

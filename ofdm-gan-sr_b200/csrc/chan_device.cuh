@@ -105,10 +105,10 @@ __device__ __forceinline__ void fft_inplace(float (&re)[N], float (&im)[N]) {
 // ---- draws ------------------------------------------------------------------------------------------------
 // Philox block layout per frame (purpose 0): 0-7 symbol normals, 8-11 phase increments, 12 {snr uniform, payload
 // bits}, 13-20 noise normals.  See oracle/channel.c header.
-__device__ __forceinline__ void draw_normals(const SimArgs& a, uint64_t frame, uint32_t blk, float (&n)[4]) {
+__device__ __forceinline__ void draw_normals(const SimArgs& a, uint64_t frame, uint32_t blk, float (&n)[4], float var = 1.0f) {
     uint32_t x[4];
     philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), blk, 0u, x);
-    normals_from_block(x, n);
+    normals_from_block(x, n, var);
 }
 
 __device__ __forceinline__ int snr_bin_of(const ofdmgan_chan_cfg& c, uint64_t frame) {
@@ -133,27 +133,26 @@ __device__ __forceinline__ void tx_frame(const SimArgs& a, int64_t b, uint64_t f
                                          float (&ci)[16]) {
     const ofdmgan_chan_cfg& c = a.cfg;
     if (SRC == SRC_GAUSS) {
-        float Xr[16], Xi[16];
+        // (1/sqrt2 per bin) * (ifft 1/N) * (sqrt(N) or N): the IFFT is linear, so the scale is applied to the symbols -
+        // for Philox symbols inside Box-Muller's square root (free), for injected symbols by one multiply each
+        const float sc = 0.70710678118654752f * (c.ifft_scale == OFDMGAN_SCALE_N ? 1.0f : 0.25f);
         if (a.sym) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { Xr[k] = a.sym[b * 32 + k]; Xi[k] = a.sym[b * 32 + 16 + k]; }
+            for (int k = 0; k < 16; ++k) { cr[k] = a.sym[b * 32 + k] * sc; ci[k] = a.sym[b * 32 + 16 + k] * sc; }
         } else {
+            const float var = sc * sc;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float n[4];
-                draw_normals(a, frame, j, n);
+                draw_normals(a, frame, j, n, var);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) Xr[4 * j + t] = n[t];
-                draw_normals(a, frame, 4 + j, n);
+                for (int t = 0; t < 4; ++t) cr[4 * j + t] = n[t];
+                draw_normals(a, frame, 4 + j, n, var);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) Xi[4 * j + t] = n[t];
+                for (int t = 0; t < 4; ++t) ci[4 * j + t] = n[t];
             }
         }
-        fft_inplace<16, +1>(Xr, Xi);
-        // (1/sqrt2 per bin) * (ifft 1/N) * (sqrt(N) or N)
-        const float sc = 0.70710678118654752f * (c.ifft_scale == OFDMGAN_SCALE_N ? 1.0f : 0.25f);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { cr[i] = Xr[i] * sc; ci[i] = Xi[i] * sc; }
+        fft_inplace<16, +1>(cr, ci);
         return;
     }
     constexpr int N = (SRC == SRC_Q16_CP0 || SRC == SRC_Q16_CP2) ? 16 : 8;

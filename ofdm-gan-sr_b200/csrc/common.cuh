@@ -91,11 +91,14 @@ __device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ft
 
 // Box-Muller on the word pairs (x0,x1), (x2,x3): 4 normals per Philox block.
 //   r = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2 u1), u1 in (0,1) so the radicand is > 0; angle 2 pi u2 in [0, 2 pi)
-__device__ __forceinline__ void normals_from_block(const uint32_t (&x)[4], float (&n)[4]) {
+//   `var` scales the variance (the caller folds any output scale s as var = s^2: the multiply disappears into the
+//   constant under the square root); the angle is (x >> 8) * (2 pi 2^-24), one multiply.
+__device__ __forceinline__ void normals_from_block(const uint32_t (&x)[4], float (&n)[4], float var = 1.0f) {
+    const float k = -1.3862943611198906f * var;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u_open(x[2 * h])));
-        const float th = 6.283185307179586f * u_half(x[2 * h + 1]);
+        const float r = fast_sqrt(k * fast_lg2(u_open(x[2 * h])));
+        const float th = (float)(x[2 * h + 1] >> 8) * 3.7450702829239286e-07f;
         n[2 * h] = r * fast_cos(th);
         n[2 * h + 1] = r * fast_sin(th);
     }

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(OG_THREADS) k_frame_metrics(const float* __res
         const int64_t b = wbase + lane;
         if (b < B) {
             float mse, evm, ratio;
-            frame_err(e[0], e[1], r[0], r[1], mse, evm, ratio);
+            frame_err(e[0], e[1], r[0], r[1], fast_rcp(frame_energy(r[0], r[1])), mse, evm, ratio);
             const int s = bin ? bin[b] : 0;
             if (s >= 0 && s < n_snr) {
                 double* row = table + s * NC;

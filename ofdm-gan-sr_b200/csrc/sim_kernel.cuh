@@ -46,17 +46,24 @@ __device__ __forceinline__ void acc_reset(Acc& a, int bin) {
     a.bin = bin;
 }
 
+// sum |ref|^2 of a frame (the EVM denominator; computed once per frame and shared by both methods)
+__device__ __forceinline__ float frame_energy(const float (&cr)[16], const float (&ci)[16]) {
+    float sr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sr = fmaf(cr[i], cr[i], fmaf(ci[i], ci[i], sr));
+    return sr;
+}
+
 __device__ __forceinline__ void frame_err(const float (&er)[16], const float (&ei)[16], const float (&cr)[16],
-                                          const float (&ci)[16], float& mse, float& evm, float& ratio) {
-    float se = 0.f, sr = 0.f;
+                                          const float (&ci)[16], float inv_energy, float& mse, float& evm, float& ratio) {
+    float se = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float a = er[i] - cr[i], b = ei[i] - ci[i];
         se = fmaf(a, a, fmaf(b, b, se));
-        sr = fmaf(cr[i], cr[i], fmaf(ci[i], ci[i], sr));
     }
     mse = se * 0.03125f;
-    ratio = se * fast_rcp(sr);
+    ratio = se * inv_energy;
     // 20 log10(sqrt(mean|e|^2 / mean|ref|^2) + 1e-10)     benchmark_comparison.py:142-146
     evm = 6.020599913279624f * fast_lg2(fast_sqrt(ratio) + 1e-10f);
 }
@@ -93,6 +100,7 @@ __device__ __forceinline__ void acc_flush(Acc& a, double* table, int lane) {
 }
 
 constexpr int ST = OG_SIM_THREADS;                                   // frames per CTA tile
+constexpr int SIM_PER_SM = ST >= 512 ? 1 : 512 / ST;                 // resident CTAs per SM
 constexpr size_t SIM_SMEM = (size_t)ST * 8 * sizeof(float4) + OFDMGAN_MAX_SNR_BINS * NM * NC * sizeof(double);
 
 __device__ __forceinline__ void cta_lockstep(int level) {
@@ -100,7 +108,7 @@ __device__ __forceinline__ void cta_lockstep(int level) {
 }
 
 template <int SRC, int GEN>
-__global__ void __launch_bounds__(ST, 512 / ST) k_sim(const __grid_constant__ SimArgs a) {
+__global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ SimArgs a) {
     constexpr bool BITS = SRC != SRC_GAUSS;
     extern __shared__ float4 sm[];                                   // [ST*8] warp tiles, then the CTA's metric table
     double* table = reinterpret_cast<double*>(sm + ST * 8);
@@ -179,16 +187,18 @@ __global__ void __launch_bounds__(ST, 512 / ST) k_sim(const __grid_constant__ Si
         }
         if (a.snr_out && live) a.snr_out[b] = snr_db;
         if (GEN < 0) continue;                                     // (compile-time: the simulate-only kernel ends its tile here)
+        float inv_energy = 0.f;
 
         if (want_metrics) {
             if (__any_sync(0xffffffffu, fbin != acc.bin || acc.count >= FLUSH_EVERY)) {
                 acc_flush<BITS>(acc, table, lane);
                 acc.bin = fbin;
             }
+            inv_energy = fast_rcp(frame_energy(cr, ci));
             if (live) {                                            // NoEQ first: the received frame dies into G's input
                 float mse, evm, ratio;
                 int errs = 0;
-                frame_err(nr, ni, cr, ci, mse, evm, ratio);
+                frame_err(nr, ni, cr, ci, inv_energy, mse, evm, ratio);
                 if (BITS) acc.nbits += (float)qpsk_errors<SRC>(a.cfg, nr, ni, bits, errs);
                 acc_add<BITS>(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, errs);
                 acc.count++;
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(ST, 512 / ST) k_sim(const __grid_constant__ Si
             tile_read_f32(wsm, lane, f);
             float mse, evm, ratio;
             int errs = 0;
-            frame_err(yo[0], yo[1], f[0], f[1], mse, evm, ratio);
+            frame_err(yo[0], yo[1], f[0], f[1], inv_energy, mse, evm, ratio);
             if (BITS) qpsk_errors<SRC>(a.cfg, yo[0], yo[1], bits, errs);
             acc_add<BITS>(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs);
         }
@@ -261,7 +271,7 @@ static int sim_launch_one(const SimCall& c) {
     if (GEN == OFDMGAN_GEN_F32) rc = upload_g(c.gparams258, slot, s);
     else if (GEN > 0) rc = upload_q(c.wrom, c.brom, slot, s);
     if (rc) return rc;
-    const int grid = grid_for(c.B, ST, 512 / ST);
+    const int grid = grid_for(c.B, ST, SIM_PER_SM);
     // opt in to > 48 KB of dynamic shared memory (per device; a host-side table write, no launch)
     OG_CHECK(cudaFuncSetAttribute(k_sim<SRC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM));
     const int n = c.n_snr * NM * NC;
