@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 1
+#define OFDMGAN_ABI_VERSION 2
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -53,7 +53,8 @@ enum { OFDMGAN_SCALE_SQRT_N = 0,          /* ifft * sqrt(N)                     
        OFDMGAN_SCALE_N = 1 };             /* ifft * N                                 utils/ofdm_utils.py:320 */
 enum { OFDMGAN_IMPAIR_PA = 1, OFDMGAN_IMPAIR_IQ = 2, OFDMGAN_IMPAIR_PN = 4 };   /* apply_all order :571-605 */
 enum { OFDMGAN_SNR_UNIFORM = 0,           /* np.random.uniform(lo, hi) per frame      utils/dataset.py:267 */
-       OFDMGAN_SNR_GRID = 1 };            /* snr = lo + step*((frame/frames_per_snr) % n_snr)  benchmark_comparison.py:179-182 */
+       OFDMGAN_SNR_GRID = 1,              /* snr = lo + step*((frame/frames_per_snr) % n_snr)  benchmark_comparison.py:179-182 */
+       OFDMGAN_SNR_NONE = 2 };            /* no AWGN stage (NonLinearImpairments.apply_* on their own) */
 enum { OFDMGAN_NORM_NONE = 0,
        OFDMGAN_NORM_JOINT = 1,            /* one max over noisy U clean               utils/dataset.py:284-287 */
        OFDMGAN_NORM_SEPARATE = 2 };       /* each by its own max                      benchmark_comparison.py:129-134,196-197 */
@@ -92,6 +93,8 @@ typedef struct ofdmgan_chan_rand {
     const float*    pn;        /* [B][16]  randn phase increments */
     const float*    snr_db;    /* [B]      the uniform(lo,hi) draw itself */
     const float*    noise;     /* [B][32]  randn Re[16], randn Im[16] */
+    const float*    tx;        /* [B][32]  time-domain frame Re[16], Im[16]: replaces symbol generation + IFFT altogether
+                                  (NonLinearImpairments.apply_* / ChannelModel.apply on caller-supplied signals) */
 } ofdmgan_chan_rand;
 
 /* per-SNR-bin, per-method accumulator row produced by ofdmgan_sim_gen_metrics (doubles):
@@ -139,6 +142,24 @@ int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t
 /* Philox4x32-10 block (test hook): out[n][4] = philox(key=seed, ctr=(c0[i] lo/hi, c2, c3)) */
 int ofdmgan_philox_blocks(uint64_t seed, uint64_t ctr0, uint32_t c2, uint32_t c3, uint32_t* out_dev, int64_t n,
                           void* stream);
+
+/* ---- modulator API (utils/ofdm_utils.py QAMModulator / OFDMModulator as batched entry points) ------------------------ */
+/* complex values are interleaved (re, im) float pairs = torch.complex64 / numpy complex64 memory layout. */
+/* replaces QAMModulator('QPSK').modulate, utils/ofdm_utils.py:163-193: bits_dev[2n] (0/1 bytes, MSB first) -> sym_dev[n] */
+int ofdmgan_qpsk_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, void* stream);
+/* replaces QAMModulator('QPSK').demodulate, :195-222: nearest constellation point, ties to the lowest index */
+int ofdmgan_qpsk_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_symbols, void* stream);
+/* replaces OFDMModulator.modulate, :281-329: n_symbols QAM symbols -> n_ofdm = ceil(n_symbols / n_data) OFDM symbols of
+ * n_fft + cp_len samples (data on the non-pilot bins in order, zero padded; pilots at arange(0, n_fft, pilot_spacing);
+ * ifft * n_fft; cyclic prefix).  n_fft in {8, 16}; 0 <= cp_len <= n_fft; pilot_spacing 0 = no pilots.  out_dev: n_ofdm*(n_fft+cp_len)
+ * samples - except that cp_len == 0 behaves as the reference does (its slice [-0:] is the whole symbol): every symbol is emitted
+ * twice, n_ofdm * 2 * n_fft samples. */
+int ofdmgan_ofdm_modulate(const float* sym_dev, int64_t n_symbols, int n_fft, int cp_len, int pilot_spacing, float pilot_re,
+                          float pilot_im, float* out_dev, void* stream);
+/* replaces OFDMModulator.demodulate, :331-371: n_ofdm symbols of n_fft+cp_len samples -> data_dev[n_ofdm*n_data] (fft / n_fft on
+ * the data bins) and chan_dev[n_ofdm*n_pilots] = pilot bins / pilot_value (may be NULL) */
+int ofdmgan_ofdm_demodulate(const float* sig_dev, int64_t n_ofdm, int n_fft, int cp_len, int pilot_spacing, float pilot_re,
+                            float pilot_im, float* data_dev, float* chan_dev, void* stream);
 
 /* ---- fused (1)+(2|3)+metrics: the headline path -------------------------------------------------------- */
 /* replaces the inner loops of run_benchmark (benchmark_comparison.py:179-250) and of

@@ -40,7 +40,7 @@ class ChanCfg(ctypes.Structure):
 
 class ChanRand(ctypes.Structure):
     """`ofdmgan_chan_rand`: device pointers to host-generated draws (any may be NULL)."""
-    _fields_ = [("sym", c_p), ("bits", c_p), ("pn", c_p), ("snr_db", c_p), ("noise", c_p)]
+    _fields_ = [("sym", c_p), ("bits", c_p), ("pn", c_p), ("snr_db", c_p), ("noise", c_p), ("tx", c_p)]
 
 
 _SIGNATURES = {
@@ -55,6 +55,10 @@ _SIGNATURES = {
     "ofdmgan_chan_sim": (ctypes.c_int, [c_p, c_p, c_u64, c_u64, c_p, c_p, c_p, c_i64, c_p]),
     "ofdmgan_chan_draws": (ctypes.c_int, [c_p, c_u64, c_u64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
     "ofdmgan_philox_blocks": (ctypes.c_int, [c_u64, c_u64, ctypes.c_uint32, ctypes.c_uint32, c_p, c_i64, c_p]),
+    "ofdmgan_qpsk_modulate": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
+    "ofdmgan_qpsk_demodulate": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
+    "ofdmgan_ofdm_modulate": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f, c_f, c_p, c_p]),
+    "ofdmgan_ofdm_demodulate": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f, c_f, c_p, c_p, c_p]),
     "ofdmgan_sim_gen_metrics": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_p, c_p, c_f, c_u64, c_u64, c_i64, c_p, c_p]),
     "ofdmgan_sim_gen_metrics_host": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_p, c_p, c_f, c_u64, c_u64, c_i64, c_p, c_p]),
     "ofdmgan_frame_metrics": (ctypes.c_int, [c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_i64, c_p, c_p]),
@@ -81,7 +85,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 1:
+        if L.ofdmgan_abi_version() != 2:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

@@ -21,6 +21,7 @@ struct SimArgs {
     const float* pn;
     const float* snr_db;
     const float* noise;
+    const float* tx;         // injected time-domain frames (device, nullable)
     float* clean;            // outputs (device, nullable)
     float* noisy;
     float* snr_out;
@@ -132,6 +133,11 @@ template <int SRC>
 __device__ __forceinline__ void tx_frame(const SimArgs& a, int64_t b, uint64_t frame, uint32_t bits, float (&cr)[16],
                                          float (&ci)[16]) {
     const ofdmgan_chan_cfg& c = a.cfg;
+    if (a.tx) {                                                  // caller-supplied signal: no symbol source, no IFFT
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { cr[k] = a.tx[b * 32 + k]; ci[k] = a.tx[b * 32 + 16 + k]; }
+        return;
+    }
     if (SRC == SRC_GAUSS) {
         // (1/sqrt2 per bin) * (ifft 1/N) * (sqrt(N) or N): the IFFT is linear, so the scale is applied to the symbols -
         // for Philox symbols inside Box-Muller's square root (free), for injected symbols by one multiply each
@@ -220,6 +226,7 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
             }
         }
     }
+    if (c.snr_mode == OFDMGAN_SNR_NONE) return;
     float P = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) P = fmaf(nr[i], nr[i], fmaf(ni[i], ni[i], P));

@@ -164,7 +164,7 @@ static int check_cfg(const ofdmgan_chan_cfg* c, int* n_snr) {
     if (c->snr_mode == OFDMGAN_SNR_GRID) {
         if (c->n_snr < 1 || c->n_snr > OFDMGAN_MAX_SNR_BINS || c->frames_per_snr < 1) return OFDMGAN_E_ARG;
         *n_snr = c->n_snr;
-    } else if (c->snr_mode == OFDMGAN_SNR_UNIFORM) {
+    } else if (c->snr_mode == OFDMGAN_SNR_UNIFORM || c->snr_mode == OFDMGAN_SNR_NONE) {
         *n_snr = 1;
     } else {
         return OFDMGAN_E_ARG;

@@ -1,0 +1,151 @@
+// libofdmgan modulator entry points: QAMModulator('QPSK') and OFDMModulator of utils/ofdm_utils.py as batched kernels
+// (one constellation symbol / one OFDM symbol per thread; the N-point transforms run in registers, chan_device.cuh).
+//   ofdmgan_qpsk_modulate / ofdmgan_qpsk_demodulate / ofdmgan_ofdm_modulate / ofdmgan_ofdm_demodulate
+// HBM-bound element-wise work: coalesced float2 / byte accesses, grids sized as a multiple of the SM count.
+#include "chan_device.cuh"
+
+namespace og {
+
+constexpr float INV_SQRT2 = 0.70710678118654752f;
+
+// utils/ofdm_utils.py:105-109: index = 2*b1 + b0 into [1+1j, 1-1j, -1+1j, -1-1j]/sqrt2 (MSB -> Re sign, LSB -> Im sign)
+__global__ void k_qpsk_mod(const uint8_t* __restrict__ bits, float2* __restrict__ sym, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uchar2 b = reinterpret_cast<const uchar2*>(bits)[i];
+        sym[i] = make_float2(b.x ? -INV_SQRT2 : INV_SQRT2, b.y ? -INV_SQRT2 : INV_SQRT2);
+    }
+}
+
+// :195-222: argmin_k |s - c_k|^2, np.argmin returns the lowest index on ties -> an exact 0 decides "bit 0"
+__global__ void k_qpsk_demod(const float2* __restrict__ sym, uint8_t* __restrict__ bits, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 s = sym[i];
+        reinterpret_cast<uchar2*>(bits)[i] = make_uchar2(s.x < 0.f ? 1 : 0, s.y < 0.f ? 1 : 0);
+    }
+}
+
+__device__ __forceinline__ bool is_pilot(int k, int spacing) { return spacing > 0 && (k % spacing) == 0; }
+
+// :281-329.  One OFDM symbol per thread.
+template <int N>
+__global__ void __launch_bounds__(128) k_ofdm_mod(const float2* __restrict__ sym, int64_t n_symbols, int64_t n_ofdm, int cp, int spacing,
+                                                  int n_data, float pr, float pi, float2* __restrict__ out) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n_ofdm; s += (int64_t)gridDim.x * blockDim.x) {
+        float Xr[N], Xi[N];
+        int64_t d = s * n_data;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (is_pilot(k, spacing)) { Xr[k] = pr; Xi[k] = pi; }
+            else {
+                const float2 v = d < n_symbols ? sym[d] : make_float2(0.f, 0.f);      // zero padding of the last symbol
+                Xr[k] = v.x; Xi[k] = v.y;
+                ++d;
+            }
+        }
+        fft_inplace<N, +1>(Xr, Xi);                              // unscaled inverse = np.fft.ifft * N
+        float2* o = out + s * (N + cp);
+        for (int i = 0; i < cp; ++i) {                           // cyclic prefix: the last cp samples first
+            float r = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < N; ++j) if (j == N - cp + i) { r = Xr[j]; q = Xi[j]; }
+            o[i] = make_float2(r, q);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[cp + j] = make_float2(Xr[j], Xi[j]);
+    }
+}
+
+// :331-371.  data = fft / N on the data bins; channel estimate = pilot bins / pilot_value
+template <int N>
+__global__ void __launch_bounds__(128) k_ofdm_demod(const float2* __restrict__ sig, int64_t n_ofdm, int cp, int spacing, int n_data,
+                                                    int n_pilot, float pr, float pi, float2* __restrict__ data, float2* __restrict__ chan) {
+    const float inv_p = 1.0f / (pr * pr + pi * pi);
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n_ofdm; s += (int64_t)gridDim.x * blockDim.x) {
+        float Xr[N], Xi[N];
+        const float2* in = sig + s * (N + cp) + cp;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { const float2 v = in[j]; Xr[j] = v.x; Xi[j] = v.y; }
+        fft_inplace<N, -1>(Xr, Xi);
+        int64_t d = s * n_data, p = s * n_pilot;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const float r = Xr[k] * (1.0f / N), q = Xi[k] * (1.0f / N);
+            if (is_pilot(k, spacing)) {
+                if (chan) chan[p] = make_float2((r * pr + q * pi) * inv_p, (q * pr - r * pi) * inv_p);
+                ++p;
+            } else {
+                data[d++] = make_float2(r, q);
+            }
+        }
+    }
+}
+
+static int pilots_of(int n_fft, int spacing) { return spacing > 0 ? (n_fft + spacing - 1) / spacing : 0; }
+
+}  // namespace og
+
+using namespace og;
+
+extern "C" {
+
+int ofdmgan_qpsk_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, void* stream) {
+    if (n_symbols < 0) return OFDMGAN_E_ARG;
+    if (n_symbols == 0) return 0;
+    if (!bits_dev || !sym_dev || (reinterpret_cast<uintptr_t>(bits_dev) & 1u) || (reinterpret_cast<uintptr_t>(sym_dev) & 7u)) return OFDMGAN_E_ARG;
+    k_qpsk_mod<<<grid_for(n_symbols, 256, 8), 256, 0, (cudaStream_t)stream>>>(bits_dev, reinterpret_cast<float2*>(sym_dev), n_symbols);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_qpsk_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_symbols, void* stream) {
+    if (n_symbols < 0) return OFDMGAN_E_ARG;
+    if (n_symbols == 0) return 0;
+    if (!bits_dev || !sym_dev || (reinterpret_cast<uintptr_t>(bits_dev) & 1u) || (reinterpret_cast<uintptr_t>(sym_dev) & 7u)) return OFDMGAN_E_ARG;
+    k_qpsk_demod<<<grid_for(n_symbols, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(sym_dev), bits_dev, n_symbols);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_ofdm_modulate(const float* sym_dev, int64_t n_symbols, int n_fft, int cp_len, int pilot_spacing, float pilot_re, float pilot_im,
+                          float* out_dev, void* stream) {
+    if (n_symbols < 0 || cp_len < 0 || pilot_spacing < 0) return OFDMGAN_E_ARG;
+    if (n_fft != 8 && n_fft != 16) return n_fft > 0 ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
+    if (cp_len > n_fft) return OFDMGAN_E_ARG;
+    const int n_data = n_fft - pilots_of(n_fft, pilot_spacing);
+    if (n_data < 1) return OFDMGAN_E_ARG;
+    const int64_t n_ofdm = (n_symbols + n_data - 1) / n_data;
+    if (n_ofdm == 0) return 0;
+    if (!sym_dev || !out_dev || (reinterpret_cast<uintptr_t>(sym_dev) & 7u) || (reinterpret_cast<uintptr_t>(out_dev) & 7u)) return OFDMGAN_E_ARG;
+    // reference behaviour kept on purpose: cp = time_symbols[:, -cp_length:] with cp_length == 0 is the WHOLE symbol
+    // (numpy's -0 == 0), so the reference emits every symbol twice (utils/ofdm_utils.py:323-324)
+    if (cp_len == 0) cp_len = n_fft;
+    const int grid = grid_for(n_ofdm, 128, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_fft == 16)
+        k_ofdm_mod<16><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sym_dev), n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re,
+                                            pilot_im, reinterpret_cast<float2*>(out_dev));
+    else
+        k_ofdm_mod<8><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sym_dev), n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re,
+                                           pilot_im, reinterpret_cast<float2*>(out_dev));
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_ofdm_demodulate(const float* sig_dev, int64_t n_ofdm, int n_fft, int cp_len, int pilot_spacing, float pilot_re, float pilot_im,
+                            float* data_dev, float* chan_dev, void* stream) {
+    if (n_ofdm < 0 || cp_len < 0 || pilot_spacing < 0) return OFDMGAN_E_ARG;
+    if (n_fft != 8 && n_fft != 16) return n_fft > 0 ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
+    if (cp_len > n_fft || (pilot_re == 0.f && pilot_im == 0.f && pilot_spacing > 0 && chan_dev)) return OFDMGAN_E_ARG;
+    const int n_pilot = pilots_of(n_fft, pilot_spacing), n_data = n_fft - n_pilot;
+    if (n_data < 1) return OFDMGAN_E_ARG;
+    if (n_ofdm == 0) return 0;
+    if (!sig_dev || !data_dev || (reinterpret_cast<uintptr_t>(sig_dev) & 7u) || (reinterpret_cast<uintptr_t>(data_dev) & 7u)) return OFDMGAN_E_ARG;
+    const int grid = grid_for(n_ofdm, 128, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_fft == 16)
+        k_ofdm_demod<16><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sig_dev), n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re,
+                                              pilot_im, reinterpret_cast<float2*>(data_dev), reinterpret_cast<float2*>(chan_dev));
+    else
+        k_ofdm_demod<8><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sig_dev), n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re,
+                                             pilot_im, reinterpret_cast<float2*>(data_dev), reinterpret_cast<float2*>(chan_dev));
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

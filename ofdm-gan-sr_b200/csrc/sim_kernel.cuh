@@ -160,10 +160,12 @@ __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ 
         float snr_db;
         {
             uint32_t x12[4] = {0u, 0u, 0u, 0u};
-            const bool need12 = (BITS && !a.bits) || (!grid_mode && !a.snr_db);
+            const bool no_awgn = a.cfg.snr_mode == OFDMGAN_SNR_NONE;
+            const bool need12 = (BITS && !a.bits && !a.tx) || (!grid_mode && !no_awgn && !a.snr_db);
             if (need12) philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
             if (BITS) bits = a.bits ? a.bits[bb] : x12[1];
             if (grid_mode) snr_db = fmaf(a.cfg.snr_step, (float)(live || !incremental ? fbin : snr_bin_of(a.cfg, frame)), a.cfg.snr_lo);
+            else if (no_awgn) snr_db = __int_as_float(0x7f800000);     // +inf: reported as "no noise"
             else snr_db = a.snr_db ? a.snr_db[bb] : fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x12[0]), a.cfg.snr_lo);
         }
         float cr[16], ci[16], nr[16], ni[16];
@@ -282,7 +284,7 @@ static int sim_launch_one(const SimCall& c) {
     a.keys = philox_keys(c.seed);
     a.frame0 = c.frame0;
     a.B = c.B;
-    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; }
+    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; a.tx = c.rand->tx; }
     a.clean = c.clean; a.noisy = c.noisy; a.snr_out = c.snr;
     a.wslot = slot;
     a.slope = c.slope;

@@ -13,7 +13,7 @@ from ._lib import (CRITIC_OUT, D_NPARAMS, G_NPARAMS, GEN_F32, GEN_OUT, GEN_Q_RTL
 SYM_GAUSSIAN, SYM_QPSK = 0, 1
 SCALE_SQRT_N, SCALE_N = 0, 1
 IMPAIR_PA, IMPAIR_IQ, IMPAIR_PN = 1, 2, 4
-SNR_UNIFORM, SNR_GRID = 0, 1
+SNR_UNIFORM, SNR_GRID, SNR_NONE = 0, 1, 2
 NORM_NONE, NORM_JOINT, NORM_SEPARATE = 0, 1, 2
 
 
@@ -130,7 +130,7 @@ def _dev(device):
     return device
 
 
-def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None, snr_db=None, noise=None,
+def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None, snr_db=None, noise=None, tx=None,
              want_clean=True, want_noisy=True, want_snr=True):
     """frames frame0..frame0+B-1 of SyntheticOFDMDataset / run_benchmark -> (clean, noisy, snr) CUDA tensors.
     Any of the draw tensors may be injected (host-generated randomness in the reference's draw order)."""
@@ -141,7 +141,7 @@ def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None
         snr = torch.empty(B, dtype=torch.float32, device=device) if want_snr else None
         rand = None
         keep = []
-        if any(a is not None for a in (sym, bits, pn, snr_db, noise)):
+        if any(a is not None for a in (sym, bits, pn, snr_db, noise, tx)):
             def f32(a, shape):
                 if a is None:
                     return None
@@ -153,6 +153,7 @@ def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None
             rand.pn = f32(pn, (B, 16))
             rand.snr_db = f32(snr_db, (B,))
             rand.noise = f32(noise, (B, 32))
+            rand.tx = f32(tx, (B, 32))
             if bits is not None:
                 tb = torch.as_tensor(np.ascontiguousarray(bits, dtype=np.uint32).view(np.int32)).to(device).contiguous()
                 keep.append(tb)
@@ -250,6 +251,60 @@ def metrics_summary(m):
     mse, evm = m[..., 1] / n, m[..., 3] / n
     return dict(n=m[..., 0], mse=mse, mse_std=np.sqrt(np.maximum(m[..., 2] / n - mse ** 2, 0.0)), evm=evm,
                 evm_std=np.sqrt(np.maximum(m[..., 4] / n - evm ** 2, 0.0)), ber=m[..., 5] / np.maximum(m[..., 6], 1.0))
+
+
+# ---------------------------------------------------------------------------------------------- modulators
+def _c64(t, device=None):
+    """complex64 contiguous CUDA tensor (view_as_real gives the interleaved float layout the C ABI takes)."""
+    t = torch.as_tensor(t)
+    if device is None and not t.is_cuda:
+        raise OfdmGanError("expected a CUDA tensor: libofdmgan has no CPU path")
+    return t.to(device=device if device is not None else t.device, dtype=torch.complex64).contiguous()
+
+
+def qpsk_modulate(bits):
+    """bits: uint8 CUDA tensor of 0/1, length 2n (MSB first) -> complex64[n] (QAMModulator('QPSK').modulate)."""
+    if not bits.is_cuda:
+        raise OfdmGanError("expected a CUDA tensor: libofdmgan has no CPU path")
+    bits = bits.to(torch.uint8).contiguous().view(-1)
+    n = bits.numel() // 2
+    sym = torch.empty(n, dtype=torch.complex64, device=bits.device)
+    check(_lib.lib().ofdmgan_qpsk_modulate(dptr(bits), ctypes.c_void_p(sym.data_ptr()), n, stream_ptr(bits.device)))
+    return sym
+
+
+def qpsk_demodulate(symbols):
+    sym = _c64(symbols).view(-1)
+    bits = torch.empty(2 * sym.numel(), dtype=torch.uint8, device=sym.device)
+    check(_lib.lib().ofdmgan_qpsk_demodulate(ctypes.c_void_p(sym.data_ptr()), dptr(bits), sym.numel(), stream_ptr(sym.device)))
+    return bits
+
+
+def _n_pilots(n_fft, spacing):
+    return (n_fft + spacing - 1) // spacing if spacing > 0 else 0
+
+
+def ofdm_modulate(symbols, n_fft, cp_len, pilot_spacing, pilot=1 + 0j):
+    sym = _c64(symbols).view(-1)
+    n_data = n_fft - _n_pilots(n_fft, pilot_spacing)
+    n_ofdm = -(-sym.numel() // max(n_data, 1))
+    cp_eff = cp_len if cp_len > 0 else n_fft                    # the reference's [-0:] slice duplicates the whole symbol
+    out = torch.empty(n_ofdm * (n_fft + cp_eff), dtype=torch.complex64, device=sym.device)
+    check(_lib.lib().ofdmgan_ofdm_modulate(ctypes.c_void_p(sym.data_ptr()), sym.numel(), n_fft, cp_len, pilot_spacing, float(np.real(pilot)),
+                                           float(np.imag(pilot)), ctypes.c_void_p(out.data_ptr()), stream_ptr(sym.device)))
+    return out
+
+
+def ofdm_demodulate(signal, n_fft, cp_len, pilot_spacing, pilot=1 + 0j):
+    sig = _c64(signal).view(-1)
+    n_ofdm = sig.numel() // (n_fft + cp_len)
+    n_pil = _n_pilots(n_fft, pilot_spacing)
+    data = torch.empty(n_ofdm * (n_fft - n_pil), dtype=torch.complex64, device=sig.device)
+    chan = torch.empty(n_ofdm, n_pil, dtype=torch.complex64, device=sig.device)
+    check(_lib.lib().ofdmgan_ofdm_demodulate(ctypes.c_void_p(sig.data_ptr()), n_ofdm, n_fft, cp_len, pilot_spacing, float(np.real(pilot)),
+                                             float(np.imag(pilot)), ctypes.c_void_p(data.data_ptr()),
+                                             ctypes.c_void_p(chan.data_ptr()) if n_pil else None, stream_ptr(sig.device)))
+    return data, chan
 
 
 # ---------------------------------------------------------------------------------------------- critic

@@ -1,0 +1,170 @@
+"""QAMModulator / OFDMModulator / NonLinearImpairments / ChannelModel with the reference's interface
+(utils/ofdm_utils.py:90-832), computed by libofdmgan.
+
+The reference works on one NumPy signal per call from the process-global np.random state.  Here every call is a batched
+GPU launch:
+  * a CUDA torch tensor in -> a CUDA torch tensor out (complex64; bits as uint8) - the fast path;
+  * a NumPy array in -> a NumPy array out (complex128 / int), for callers that were written against the reference.
+    The data makes a round trip through the device; there is still no CPU implementation behind it.
+Signals handled by the channel stages are batches of 16-sample frames ([16] or [B,16]), the frame length of the
+reference's training and benchmark paths; the memoryless stages (Rapp PA, IQ imbalance) accept any length.
+Randomness comes from Philox4x32-10(seed, frame index): pass `seed=` / `frame0=` for reproducible draws; the class-level
+counter otherwise advances so that successive calls see fresh noise, like successive np.random calls.
+"""
+import itertools
+from typing import Any, Dict, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._lib import OfdmGanError
+
+_frame_counter = itertools.count()
+
+
+def _to_dev(x, dtype):
+    """-> (CUDA tensor, was_numpy)"""
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            raise OfdmGanError("expected a CUDA tensor (or a NumPy array): libofdmgan has no CPU path")
+        return x.to(dtype), False
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda().to(dtype), True
+
+
+def _back(t, was_numpy, np_dtype):
+    return t.cpu().numpy().astype(np_dtype) if was_numpy else t
+
+
+class QAMModulator:
+    """utils/ofdm_utils.py:90-222.  'QPSK' (the scheme of config/config.yaml:14) is built; QAM16 / QAM64 raise."""
+
+    CONSTELLATIONS = {"QPSK": {"bits_per_symbol": 2}, "QAM16": {"bits_per_symbol": 4}, "QAM64": {"bits_per_symbol": 6}}
+
+    def __init__(self, modulation: str = "QAM16"):
+        self.modulation = modulation.upper()
+        if self.modulation not in self.CONSTELLATIONS:
+            raise ValueError(f"Unsupported modulation: {modulation}")
+        self.bits_per_symbol = self.CONSTELLATIONS[self.modulation]["bits_per_symbol"]
+        self.constellation = np.array([1 + 1j, 1 - 1j, -1 + 1j, -1 - 1j]) / np.sqrt(2) if self.modulation == "QPSK" else None
+
+    def _check(self):
+        if self.modulation != "QPSK":
+            raise OfdmGanError(f"{self.modulation} is not built (DESIGN.md 'next'); QPSK is")
+
+    def modulate(self, bits):
+        """bits (0/1, MSB first; a trailing odd bit is dropped) -> complex symbols."""
+        self._check()
+        b, was_np = _to_dev(bits, torch.uint8)
+        b = b.reshape(-1)
+        return _back(ops.qpsk_modulate(b[:(b.numel() // 2) * 2]), was_np, np.complex128)
+
+    def demodulate(self, symbols):
+        """hard decisions: nearest constellation point, ties to the lowest index -> bits (flattened, MSB first)."""
+        self._check()
+        s, was_np = _to_dev(symbols, torch.complex64)
+        return _back(ops.qpsk_demodulate(s), was_np, np.int64)
+
+
+class OFDMModulator:
+    """utils/ofdm_utils.py:229-371.  n_subcarriers in {8, 16} are built (config/config.yaml:11 uses 8)."""
+
+    def __init__(self, n_subcarriers: int = 64, cp_length: int = 16, pilot_spacing: int = 8, pilot_value: complex = 1 + 0j):
+        self.n_subcarriers, self.cp_length, self.pilot_spacing, self.pilot_value = n_subcarriers, cp_length, pilot_spacing, pilot_value
+        self.pilot_indices = np.arange(0, n_subcarriers, pilot_spacing)
+        self.data_indices = np.array([i for i in range(n_subcarriers) if i not in self.pilot_indices])
+        self.n_data_subcarriers = len(self.data_indices)
+        self.samples_per_symbol = n_subcarriers + cp_length
+
+    def modulate(self, qam_symbols):
+        s, was_np = _to_dev(qam_symbols, torch.complex64)
+        return _back(ops.ofdm_modulate(s, self.n_subcarriers, self.cp_length, self.pilot_spacing, self.pilot_value), was_np, np.complex128)
+
+    def demodulate(self, ofdm_signal):
+        s, was_np = _to_dev(ofdm_signal, torch.complex64)
+        data, chan = ops.ofdm_demodulate(s, self.n_subcarriers, self.cp_length, self.pilot_spacing, self.pilot_value)
+        return _back(data, was_np, np.complex128), _back(chan, was_np, np.complex128)
+
+
+def _frames_of(signal, allow_any_length):
+    """complex signal -> (float32 [B,32] tx layout Re[16] | Im[16], restore(frames32 -> same kind/shape as the input))"""
+    t, was_np = _to_dev(signal, torch.complex64)
+    shape = t.shape
+    flat = t.reshape(-1)
+    L = shape[-1] if t.dim() else 1
+    if L != 16 and not allow_any_length:
+        raise OfdmGanError("this stage couples the samples of a frame: signals must be [16] or [B,16] (the reference's frame length)")
+    n = flat.numel()
+    pad = (-n) % 16
+    if pad:
+        flat = torch.cat([flat, torch.zeros(pad, dtype=flat.dtype, device=flat.device)])
+    fr = flat.view(-1, 16)
+    tx = torch.cat([fr.real, fr.imag], dim=1).contiguous()
+
+    def restore(frames):                                         # frames: [B,2,16] float32
+        c = torch.complex(frames[:, 0, :], frames[:, 1, :]).reshape(-1)[:n].reshape(shape)
+        return _back(c, was_np, np.complex128)
+
+    return tx, restore
+
+
+def _run(tx, seed, frame0, **cfg_kw):
+    if frame0 is None:
+        frame0 = next(_frame_counter) * (1 << 32)
+    cfg = ops.make_cfg(normalize=ops.NORM_NONE, **cfg_kw)
+    clean, noisy, snr = ops.chan_sim(cfg, tx.shape[0], seed=seed, frame0=frame0, device=tx.device, tx=tx, want_clean=False, want_snr=False)
+    return noisy
+
+
+class NonLinearImpairments:
+    """utils/ofdm_utils.py:378-605: Rapp PA, IQ imbalance, Wiener phase noise and their chain (apply_all with the DC-offset and
+    CFO stages disabled, which is how every caller in the reference uses it: dataset.py:262-263, benchmark_comparison.py:104-106)."""
+
+    @staticmethod
+    def apply_pa_rapp(signal, saturation_level: float = 1.0, smoothness: float = 3.0):
+        tx, restore = _frames_of(signal, True)
+        return restore(_run(tx, 0, 0, pa=True, iq=False, pn=False, pa_saturation=saturation_level, pa_smoothness=smoothness,
+                            snr_mode=ops.SNR_NONE))
+
+    @staticmethod
+    def apply_iq_imbalance(signal, amplitude_imbalance_db: float = 1.0, phase_imbalance_deg: float = 5.0):
+        tx, restore = _frames_of(signal, True)
+        return restore(_run(tx, 0, 0, pa=False, iq=True, pn=False, iq_imbalance_db=amplitude_imbalance_db, iq_phase_deg=phase_imbalance_deg,
+                            snr_mode=ops.SNR_NONE))
+
+    @staticmethod
+    def apply_phase_noise(signal, phase_noise_power_dbchz: float = -80, sample_rate: float = 1e6, seed: int = 0, frame0=None):
+        tx, restore = _frames_of(signal, False)
+        return restore(_run(tx, seed, frame0, pa=False, iq=False, pn=True, phase_noise_dbchz=phase_noise_power_dbchz, sample_rate=sample_rate,
+                            snr_mode=ops.SNR_NONE))
+
+    @staticmethod
+    def apply_all(signal, pa_enabled: bool = True, pa_saturation: float = 1.0, iq_imbalance_enabled: bool = True, iq_amplitude_db: float = 1.0,
+                  iq_phase_deg: float = 5.0, phase_noise_enabled: bool = True, phase_noise_dbchz: float = -80, dc_offset_enabled: bool = False,
+                  cfo_enabled: bool = False, seed: int = 0, frame0=None):
+        if dc_offset_enabled or cfo_enabled:
+            raise OfdmGanError("DC offset / CFO stages are not built (disabled by every caller in the reference); DESIGN.md 'next'")
+        tx, restore = _frames_of(signal, not phase_noise_enabled)
+        return restore(_run(tx, seed, frame0, pa=pa_enabled, iq=iq_imbalance_enabled, pn=phase_noise_enabled, pa_saturation=pa_saturation,
+                            iq_imbalance_db=iq_amplitude_db, iq_phase_deg=iq_phase_deg, phase_noise_dbchz=phase_noise_dbchz,
+                            snr_mode=ops.SNR_NONE))
+
+
+class ChannelModel:
+    """utils/ofdm_utils.py:612-832.  'awgn' (per-frame measured signal power, :675-708) is built; the fading models raise."""
+
+    def __init__(self, channel_type: str = "awgn"):
+        self.channel_type = channel_type.lower()
+
+    def apply(self, signal, snr_db: float, seed: int = 0, frame0=None, **kwargs) -> Tuple[Any, Dict[str, Any]]:
+        if self.channel_type not in ("awgn", "rayleigh", "rician", "multipath"):
+            raise ValueError(f"Unknown channel type: {self.channel_type}")
+        if self.channel_type != "awgn":
+            raise OfdmGanError(f"channel '{self.channel_type}' is not built (DESIGN.md 'next'); 'awgn' is")
+        tx, restore = _frames_of(signal, False)
+        noisy = _run(tx, seed, frame0, pa=False, iq=False, pn=False, snr_mode=ops.SNR_GRID, snr_lo=float(snr_db), snr_step=0.0, n_snr=1)
+        power = (tx * tx).sum(dim=1) / 16.0                       # mean |x|^2 per frame
+        noise_power = power / (10.0 ** (float(snr_db) / 10.0))
+        info = {"type": "awgn", "snr_db": snr_db, "noise_power": noise_power if noise_power.numel() > 1 else float(noise_power),
+                "channel_response": np.array([1.0])}
+        return restore(noisy), info

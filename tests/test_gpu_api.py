@@ -128,7 +128,7 @@ def test_gradient_penalty_vs_autograd_double_backward(pkg):
     torch.manual_seed(123)                                   # same torch.rand draw
     gpt = torch_gp(TD, real, fake, cond)
     assert gp.dim() == 0
-    assert abs(float(gp) - float(gpt)) <= TOL * abs(float(gpt))
+    assert abs(float(gp.detach()) - float(gpt.detach())) <= TOL * abs(float(gpt.detach()))
     (10.0 * gp).backward()
     (10.0 * gpt).backward()
     assert_close(_grads(D), _grads(TD), TOL, "GP dparams")
