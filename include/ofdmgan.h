@@ -81,7 +81,8 @@ typedef struct ofdmgan_chan_cfg {
     int32_t n_snr;             /* grid mode: number of grid points (<= OFDMGAN_MAX_SNR_BINS); uniform mode: 1 */
     int64_t frames_per_snr;    /* grid mode: consecutive frames sharing one grid point (n_trials) */
     int32_t normalize;         /* OFDMGAN_NORM_* */
-    int32_t reserved;
+    int32_t equalizers;        /* != 0: the fused sweep also fills the OFDMGAN_METHOD_ZF / _MMSE rows (genie-aided equalisers of
+                                  benchmark_comparison.py:218-226, utils/classical_equalizers.py:33-230) */
 } ofdmgan_chan_cfg;
 
 /* Host-generated randomness for parity runs, in the reference's np.random draw order per frame
@@ -178,6 +179,12 @@ int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind,
  * est/ref: [B][2][16] f32 device; bin_dev: [B] int32 SNR bin per frame or NULL (all bin 0). */
 int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int32_t* bin_dev, int method, int n_snr,
                           int64_t B, double* metrics_dev, void* stream);
+
+/* replaces ZeroForcingEqualizer.equalize_iq / MMSEEqualizer.equalize_iq with the genie channel estimate (clean given),
+ * utils/classical_equalizers.py:88-126,203-230.  method: OFDMGAN_METHOD_ZF | OFDMGAN_METHOD_MMSE.  snr_db_dev: [B] per-frame SNR
+ * for MMSE (NULL: the reference's default 20 dB).  est_dev: [B][2][16] equalised frames. */
+int ofdmgan_equalize(const float* noisy_dev, const float* clean_dev, const float* snr_db_dev, int method, float* est_dev, int64_t B,
+                     void* stream);
 
 /* ---- kernel (4): critic ------------------------------------------------------------------------------- */
 /* replaces MiniDiscriminator.forward, models/discriminator.py:112-152.  score: [B] f32 device. */

@@ -13,7 +13,7 @@ reference's own Python call surface:
 There is no CPU fallback anywhere in this package: without the built library or without a CUDA device the compute
 entry points raise `OfdmGanError`.
 """
-from . import _lib, ops
+from . import _lib, ops, sweep
 from ._lib import OfdmGanError
 
 __all__ = ["ops", "OfdmGanError", "_lib"]

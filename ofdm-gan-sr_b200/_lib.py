@@ -34,7 +34,7 @@ class ChanCfg(ctypes.Structure):
         ("pa_smoothness", c_f), ("iq_gain", c_f), ("iq_cos", c_f), ("iq_sin", c_f), ("pn_sigma", c_f),
         ("snr_mode", ctypes.c_int32), ("snr_lo", c_f), ("snr_hi", c_f), ("snr_step", c_f),
         ("n_snr", ctypes.c_int32), ("frames_per_snr", c_i64), ("normalize", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("equalizers", ctypes.c_int32),
     ]
 
 
@@ -61,6 +61,7 @@ _SIGNATURES = {
     "ofdmgan_ofdm_demodulate": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f, c_f, c_p, c_p, c_p]),
     "ofdmgan_sim_gen_metrics": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_p, c_p, c_f, c_u64, c_u64, c_i64, c_p, c_p]),
     "ofdmgan_sim_gen_metrics_host": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_p, c_p, c_f, c_u64, c_u64, c_i64, c_p, c_p]),
+    "ofdmgan_equalize": (ctypes.c_int, [c_p, c_p, c_p, ctypes.c_int, c_p, c_i64, c_p]),
     "ofdmgan_frame_metrics": (ctypes.c_int, [c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_i64, c_p, c_p]),
     "ofdmgan_disc_fwd_f32": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_p]),
     "ofdmgan_disc_bwd_f32": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_f, c_p]),

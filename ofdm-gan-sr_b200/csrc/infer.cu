@@ -114,6 +114,32 @@ __global__ void __launch_bounds__(OG_THREADS) k_frame_metrics(const float* __res
     }
 }
 
+// genie-aided ZF / MMSE on frames already in HBM (utils/classical_equalizers.py equalize_iq)
+__global__ void __launch_bounds__(OG_THREADS) k_equalize(const float* __restrict__ noisy, const float* __restrict__ clean,
+                                                         const float* __restrict__ snr_db, int method, float* __restrict__ est, int64_t B) {
+    __shared__ float4 sm[OG_THREADS * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* wsm = sm + warp * 32 * 8;
+    const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t wbase = t * OG_THREADS + warp * 32;
+        if (wbase >= B) continue;
+        float y[2][16], x[2][16], e[2][16];
+        tile_load_f32(noisy, wbase, B, wsm, lane, y);
+        tile_load_f32(clean, wbase, B, wsm, lane, x);
+        const int64_t b = wbase + lane;
+        const float inv_snr = inv_snr_linear(snr_db && b < B ? snr_db[b] : 20.0f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float hr, hi;
+            eq_channel(y[0][i], y[1][i], x[0][i], x[1][i], hr, hi);
+            if (method == OFDMGAN_METHOD_ZF) eq_zf(y[0][i], y[1][i], hr, hi, e[0][i], e[1][i]);
+            else eq_mmse(y[0][i], y[1][i], hr, hi, inv_snr, e[0][i], e[1][i]);
+        }
+        tile_store_f32(est, wbase, B, wsm, lane, e);
+    }
+}
+
 // raw draws (test hook)
 __global__ void k_chan_draws(const __grid_constant__ SimArgs a, float* sym, uint32_t* bits, float* pn, float* snr_db,
                              float* noise) {
@@ -300,6 +326,15 @@ int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind,
     OG_CHECK(cudaStreamSynchronize(s));
     for (int i = 0; i < n_snr * NM * NC; ++i) metrics_host[i] += tmp[i];
     return 0;
+}
+
+int ofdmgan_equalize(const float* noisy_dev, const float* clean_dev, const float* snr_db_dev, int method, float* est_dev, int64_t B,
+                     void* stream) {
+    if (B < 0 || (method != OFDMGAN_METHOD_ZF && method != OFDMGAN_METHOD_MMSE)) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    if (!noisy_dev || !clean_dev || !est_dev || !aligned16(noisy_dev) || !aligned16(clean_dev) || !aligned16(est_dev)) return OFDMGAN_E_ARG;
+    k_equalize<<<grid_for(B, OG_THREADS, 4), OG_THREADS, 0, (cudaStream_t)stream>>>(noisy_dev, clean_dev, snr_db_dev, method, est_dev, B);
+    return (int)cudaGetLastError();
 }
 
 int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int32_t* bin_dev, int method, int n_snr, int64_t B,

@@ -12,6 +12,7 @@
 #include "chan_device.cuh"
 #include "gen_device.cuh"
 #include "io_tile.cuh"
+#include "equalizer_device.cuh"
 
 // Launch shape.  16 warps per SM at <= 128 registers (measured best of 12/16/20/24 warps on B200, profiles/r1_notes.md)
 // as ONE 512-thread CTA per SM with a few CTA barriers per tile: the loop body is ~70 KB of straight-line code, far
@@ -30,17 +31,19 @@ namespace og {
 constexpr int NM = OFDMGAN_N_METHODS, NC = OFDMGAN_METRIC_COLS;
 constexpr int FLUSH_EVERY = 32;     // frames a thread accumulates in fp32 before folding into the double table
 
-// per-thread running sums for the SNR bin the thread is currently in, [GAN, NoEQ]
+// per-thread running sums for the SNR bin the thread is currently in; methods [GAN, NoEQ] or [GAN, NoEQ, ZF, MMSE]
+template <int NMETH>
 struct Acc {
-    float mse[2], mse2[2], evm[2], evm2[2], ratio[2], errs[2];
-    float nbits;       // payload bits compared per method (same for both)
+    float mse[NMETH], mse2[NMETH], evm[NMETH], evm2[NMETH], ratio[NMETH], errs[NMETH];
+    float nbits;       // payload bits compared per method (same for all)
     int count;         // live frames accumulated
     int bin;
 };
 
-__device__ __forceinline__ void acc_reset(Acc& a, int bin) {
+template <int NMETH>
+__device__ __forceinline__ void acc_reset(Acc<NMETH>& a, int bin) {
 #pragma unroll
-    for (int m = 0; m < 2; ++m) { a.mse[m] = a.mse2[m] = a.evm[m] = a.evm2[m] = a.ratio[m] = a.errs[m] = 0.f; }
+    for (int m = 0; m < NMETH; ++m) { a.mse[m] = a.mse2[m] = a.evm[m] = a.evm2[m] = a.ratio[m] = a.errs[m] = 0.f; }
     a.nbits = 0.f;
     a.count = 0;
     a.bin = bin;
@@ -68,8 +71,15 @@ __device__ __forceinline__ void frame_err(const float (&er)[16], const float (&e
     evm = 6.020599913279624f * fast_lg2(fast_sqrt(ratio) + 1e-10f);
 }
 
-template <bool BITS>
-__device__ __forceinline__ void acc_add(Acc& a, int m, float mse, float evm, float ratio, int errs) {
+// mse / evm / ratio from a frame's summed squared error
+__device__ __forceinline__ void err_to_metrics(float se, float inv_energy, float& mse, float& evm, float& ratio) {
+    mse = se * 0.03125f;
+    ratio = se * inv_energy;
+    evm = 6.020599913279624f * fast_lg2(fast_sqrt(ratio) + 1e-10f);
+}
+
+template <bool BITS, int NMETH>
+__device__ __forceinline__ void acc_add(Acc<NMETH>& a, int m, float mse, float evm, float ratio, int errs) {
     a.mse[m] += mse; a.mse2[m] = fmaf(mse, mse, a.mse2[m]);
     a.evm[m] += evm; a.evm2[m] = fmaf(evm, evm, a.evm2[m]);
     a.ratio[m] += ratio;
@@ -77,13 +87,13 @@ __device__ __forceinline__ void acc_add(Acc& a, int m, float mse, float evm, flo
 }
 
 // fold the thread's running sums into the CTA table (shared, double).  Warp-uniform bins take the shuffle path.
-template <bool BITS>
-__device__ __forceinline__ void acc_flush(Acc& a, double* table, int lane) {
+template <bool BITS, int NMETH>
+__device__ __forceinline__ void acc_flush(Acc<NMETH>& a, double* table, int lane) {
     const unsigned full = 0xffffffffu;
     const int bin0 = __shfl_sync(full, a.bin, 0);
     const bool uniform = __all_sync(full, a.bin == bin0);
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < NMETH; ++m) {
         const float col[NC] = {(float)a.count, a.mse[m], a.mse2[m], a.evm[m], a.evm2[m], a.errs[m], a.nbits, a.ratio[m]};
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -107,9 +117,11 @@ __device__ __forceinline__ void cta_lockstep(int level) {
     if (OG_SIM_BARRIERS >= level) __syncthreads();
 }
 
-template <int SRC, int GEN>
+// EQ: also fill the ZF / MMSE rows (genie-aided equalisers, equalizer_device.cuh)
+template <int SRC, int GEN, bool EQ>
 __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ SimArgs a) {
     constexpr bool BITS = SRC != SRC_GAUSS;
+    constexpr int NMETH = EQ ? 4 : 2;
     extern __shared__ float4 sm[];                                   // [ST*8] warp tiles, then the CTA's metric table
     double* table = reinterpret_cast<double*>(sm + ST * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ 
         for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) table[i] = 0.0;
         __syncthreads();
     }
-    Acc acc;
+    Acc<NMETH> acc;
     acc_reset(acc, -1);
 
     const int64_t ntiles = (a.B + ST - 1) / ST;
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ 
 
         if (want_metrics) {
             if (__any_sync(0xffffffffu, fbin != acc.bin || acc.count >= FLUSH_EVERY)) {
-                acc_flush<BITS>(acc, table, lane);
+                acc_flush<BITS, NMETH>(acc, table, lane);
                 acc.bin = fbin;
             }
             inv_energy = fast_rcp(frame_energy(cr, ci));
@@ -202,8 +214,26 @@ __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ 
                 int errs = 0;
                 frame_err(nr, ni, cr, ci, inv_energy, mse, evm, ratio);
                 if (BITS) acc.nbits += (float)qpsk_errors<SRC>(a.cfg, nr, ni, bits, errs);
-                acc_add<BITS>(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, errs);
+                acc_add<BITS, NMETH>(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, errs);
                 acc.count++;
+                if (EQ) {                                          // genie-aided ZF and MMSE, sample by sample
+                    const float inv_snr = inv_snr_linear(snr_db);
+                    float zr[16], zi[16], se_m = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float hr, hi, mr, mi;
+                        eq_channel(nr[i], ni[i], cr[i], ci[i], hr, hi);
+                        eq_zf(nr[i], ni[i], hr, hi, zr[i], zi[i]);
+                        eq_mmse(nr[i], ni[i], hr, hi, inv_snr, mr, mi);
+                        const float dr = mr - cr[i], di = mi - ci[i];
+                        se_m = fmaf(dr, dr, fmaf(di, di, se_m));
+                    }
+                    frame_err(zr, zi, cr, ci, inv_energy, mse, evm, ratio);
+                    if (BITS) qpsk_errors<SRC>(a.cfg, zr, zi, bits, errs);
+                    acc_add<BITS, NMETH>(acc, OFDMGAN_METHOD_ZF, mse, evm, ratio, errs);
+                    err_to_metrics(se_m, inv_energy, mse, evm, ratio);
+                    acc_add<BITS, NMETH>(acc, OFDMGAN_METHOD_MMSE, mse, evm, ratio, 0);
+                }
             }
         }
         // reconstruct.  The clean frame waits in the thread's own (swizzled) slots of the warp tile meanwhile.
@@ -233,13 +263,13 @@ __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ 
             int errs = 0;
             frame_err(yo[0], yo[1], f[0], f[1], inv_energy, mse, evm, ratio);
             if (BITS) qpsk_errors<SRC>(a.cfg, yo[0], yo[1], bits, errs);
-            acc_add<BITS>(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs);
+            acc_add<BITS, NMETH>(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, errs);
         }
         __syncwarp();
         cta_lockstep(3);
     }
     if (want_metrics) {
-        acc_flush<BITS>(acc, table, lane);
+        acc_flush<BITS, NMETH>(acc, table, lane);
         __syncthreads();
         double* out = a.partials + (size_t)blockIdx.x * a.n_snr * NM * NC;
         for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) out[i] = table[i];
@@ -263,7 +293,7 @@ static __global__ void k_reduce_partials(const double* __restrict__ partials, in
     metrics[i] += (s0 + s1) + (s2 + s3);
 }
 
-template <int SRC, int GEN>
+template <int SRC, int GEN, bool EQ>
 static int sim_launch_one(const SimCall& c) {
     cudaStream_t s = c.stream;
     int slot = 0, rc;
@@ -275,7 +305,7 @@ static int sim_launch_one(const SimCall& c) {
     if (rc) return rc;
     const int grid = grid_for(c.B, ST, SIM_PER_SM);
     // opt in to > 48 KB of dynamic shared memory (per device; a host-side table write, no launch)
-    OG_CHECK(cudaFuncSetAttribute(k_sim<SRC, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM));
+    OG_CHECK(cudaFuncSetAttribute(k_sim<SRC, GEN, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM));
     const int n = c.n_snr * NM * NC;
     void* partials = nullptr;
     if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
@@ -290,7 +320,7 @@ static int sim_launch_one(const SimCall& c) {
     a.slope = c.slope;
     a.partials = (double*)partials;
     a.n_snr = c.n_snr;
-    k_sim<SRC, GEN><<<grid, ST, SIM_SMEM, s>>>(a);
+    k_sim<SRC, GEN, EQ><<<grid, ST, SIM_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
     if (partials) {
         k_reduce_partials<<<(n + 63) / 64, 64, 0, s>>>((const double*)partials, grid, n, c.metrics);
@@ -301,11 +331,13 @@ static int sim_launch_one(const SimCall& c) {
 
 template <int SRC>
 static int sim_launch_src(const SimCall& c) {
+    const bool eq = c.cfg->equalizers != 0;
     switch (c.gen_kind) {
-        case -1: return sim_launch_one<SRC, -1>(c);
-        case OFDMGAN_GEN_F32: return sim_launch_one<SRC, OFDMGAN_GEN_F32>(c);
-        case OFDMGAN_GEN_Q_SPEC: return sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC>(c);
-        case OFDMGAN_GEN_Q_RTL: return sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL>(c);
+        case -1: return sim_launch_one<SRC, -1, false>(c);
+        case OFDMGAN_GEN_F32: return eq ? sim_launch_one<SRC, OFDMGAN_GEN_F32, true>(c) : sim_launch_one<SRC, OFDMGAN_GEN_F32, false>(c);
+        // the equaliser rows are built with the fp32 generator only (the comparison benchmark_comparison.py makes)
+        case OFDMGAN_GEN_Q_SPEC: return eq ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC, false>(c);
+        case OFDMGAN_GEN_Q_RTL: return eq ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL, false>(c);
         default: return OFDMGAN_E_ARG;
     }
 }

@@ -20,7 +20,7 @@ NORM_NONE, NORM_JOINT, NORM_SEPARATE = 0, 1, 2
 def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j, ifft_scale=SCALE_SQRT_N,
              nonlinear=False, pa=None, iq=None, pn=None, pa_saturation=1.0, pa_smoothness=3.0, iq_imbalance_db=1.0,
              iq_phase_deg=5.0, phase_noise_dbchz=-80.0, sample_rate=1e6, snr_mode=SNR_UNIFORM, snr_lo=0.0, snr_hi=30.0,
-             snr_step=5.0, n_snr=1, frames_per_snr=1, normalize=NORM_JOINT):
+             snr_step=5.0, n_snr=1, frames_per_snr=1, normalize=NORM_JOINT, equalizers=False):
     """ChanCfg from the reference's user-facing parameters: SyntheticOFDMDataset.__init__ (utils/dataset.py:195-206),
     NonLinearImpairments defaults (utils/ofdm_utils.py:394-521), run_benchmark's SNR grid
     (benchmark_comparison.py:179-182)."""
@@ -39,6 +39,7 @@ def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pi
     c.pn_sigma = math.sqrt(10.0 ** (phase_noise_dbchz / 10.0) * sample_rate)
     c.snr_mode, c.snr_lo, c.snr_hi, c.snr_step = snr_mode, snr_lo, snr_hi, snr_step
     c.n_snr, c.frames_per_snr, c.normalize = n_snr, frames_per_snr, normalize
+    c.equalizers = 1 if equalizers else 0        # also fill the ZF / MMSE rows of the fused sweep
     return c
 
 
@@ -241,6 +242,19 @@ def frame_metrics(est, ref, bins=None, method=0, n_snr=1, out=None):
     check(_lib.lib().ofdmgan_frame_metrics(dptr(est), dptr(ref), dptr(bins), method, n_snr, est.shape[0], dptr(out),
                                            stream_ptr(est.device)))
     return out
+
+
+def equalize(noisy, clean, method, snr_db=None):
+    """Genie-aided ZF (METHOD_ZF) / MMSE (METHOD_MMSE) on [B,2,16] frames -> equalised frames
+    (ZeroForcingEqualizer / MMSEEqualizer.equalize_iq, utils/classical_equalizers.py:88-126,203-230)."""
+    noisy, clean = frames(noisy), frames(clean)
+    est = torch.empty_like(noisy)
+    snr = None
+    if snr_db is not None:
+        snr = torch.as_tensor(snr_db, dtype=torch.float32, device=noisy.device).reshape(-1)
+        snr = snr.expand(noisy.shape[0]).contiguous() if snr.numel() == 1 else snr.contiguous()
+    check(_lib.lib().ofdmgan_equalize(dptr(noisy), dptr(clean), dptr(snr), method, dptr(est), noisy.shape[0], stream_ptr(noisy.device)))
+    return est
 
 
 def metrics_summary(m):

@@ -13,9 +13,9 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from ._lib import GEN_F32, METHOD_GAN, METHOD_NOEQ, OfdmGanError
+from ._lib import GEN_F32, METHOD_GAN, METHOD_MMSE, METHOD_NOEQ, METHOD_ZF, OfdmGanError
 
-METHOD_ROWS = {"GAN": METHOD_GAN, "NoEQ": METHOD_NOEQ}
+METHOD_ROWS = {"GAN": METHOD_GAN, "ZF": METHOD_ZF, "MMSE": METHOD_MMSE, "NoEQ": METHOD_NOEQ}
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -55,7 +55,8 @@ def run_benchmark(generator, n_trials: int = 100, frame_length: int = 16, snr_va
                   channel_type: str = "awgn", nonlinear: bool = False, pa_saturation: float = 1.0, device=None, seed: int = 0,
                   group=None, backend=ops) -> Dict[str, Dict[float, Dict[str, float]]]:
     """Signature and return structure of benchmark_comparison.run_benchmark (method -> snr -> {'mse','mse_std','evm',
-    'evm_std'}) for the methods computed on the GPU (GAN, NoEQ); the trial loop (SNR outer, trial inner, separate
+    'evm_std'}) for the methods computed on the GPU (GAN, ZF, MMSE, NoEQ - the data-parallel ones; DFE / LMS / RLS are serial
+    adaptive filters and stay with the reference); the trial loop (SNR outer, trial inner, separate
     normalisation of noisy and clean, per-trial MSE / EVM in dB, mean and population std over trials) runs in one
     fused launch per rank.  `generator` is a MiniGenerator (its flat parameters are used) or a flat 258-vector."""
     if frame_length != 16 or channel_type != "awgn":
@@ -64,7 +65,7 @@ def run_benchmark(generator, n_trials: int = 100, frame_length: int = 16, snr_va
     gparams = ops.flatten_params(generator) if isinstance(generator, torch.nn.Module) else generator
     slope = getattr(generator, "leaky_slope", 0.2)
     common = dict(nonlinear=nonlinear, pa_saturation=pa_saturation if nonlinear else 1.0, normalize=ops.NORM_SEPARATE,
-                  snr_mode=ops.SNR_GRID, frames_per_snr=n_trials)
+                  snr_mode=ops.SNR_GRID, frames_per_snr=n_trials, equalizers=True)
     tables = []
     if _is_arithmetic(snr_values):
         step = snr_values[1] - snr_values[0] if len(snr_values) > 1 else 0.0

@@ -4,7 +4,7 @@ The reference builds one sample per `__getitem__` call in NumPy from the process
 per frame, the dominant cost of train.py --synthetic).  Here a sample is a pure function of (seed, frame index) through
 Philox4x32-10 counters, so any index range can be produced in one launch, on any rank, in any order.
 """
-from typing import Dict, Iterator, Tuple
+from typing import Dict, Iterator, List, Tuple
 
 import torch
 
@@ -83,3 +83,18 @@ def create_dataloader(dataset, batch_size: int = 32, shuffle: bool = True, num_w
     """Signature of utils/dataset.py:296-323.  Samples are i.i.d. functions of their index, so `shuffle` changes nothing
     statistically and `num_workers` is unused: batches are produced by one kernel launch each."""
     return GPUBatchLoader(dataset, batch_size=batch_size, drop_last=drop_last, rank=rank, world_size=world_size)
+
+
+def generate_test_samples(n_samples: int = 100, frame_length: int = 16, snr_values: List[float] = (5, 10, 15, 20, 25),
+                          channel_type: str = "awgn", seed: int = 0, device=None) -> Dict[float, List[Dict[str, torch.Tensor]]]:
+    """Signature and result structure of utils/dataset.py:326-383 (SNR -> list of {'noisy','clean','snr'}): Gaussian-symbol
+    frames through AWGN at fixed SNRs with joint normalisation, one launch per SNR value; the per-sample dicts are views
+    into the batched device tensors."""
+    if frame_length != 16 or channel_type != "awgn":
+        raise OfdmGanError("generate_test_samples: only frame_length 16 / 'awgn' are built")
+    out = {}
+    for i, snr in enumerate(snr_values):
+        cfg = ops.make_cfg(snr_mode=ops.SNR_GRID, snr_lo=float(snr), snr_step=0.0, n_snr=1, normalize=ops.NORM_JOINT)
+        clean, noisy, _ = ops.chan_sim(cfg, n_samples, seed=seed, frame0=i * n_samples, device=device, want_snr=False)
+        out[snr] = [{"noisy": noisy[j], "clean": clean[j], "snr": snr} for j in range(n_samples)]
+    return out

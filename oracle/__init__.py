@@ -38,14 +38,14 @@ class ChanCfg(ctypes.Structure):
         ("iq_sin", ctypes.c_float), ("pn_sigma", ctypes.c_float), ("snr_mode", ctypes.c_int32),
         ("snr_lo", ctypes.c_float), ("snr_hi", ctypes.c_float), ("snr_step", ctypes.c_float),
         ("n_snr", ctypes.c_int32), ("frames_per_snr", ctypes.c_int64), ("normalize", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("equalizers", ctypes.c_int32),
     ]
 
 
 def make_cfg(symbol_source=0, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j, ifft_scale=0, nonlinear=False,
              pa=None, iq=None, pn=None, pa_saturation=1.0, pa_smoothness=3.0, iq_imbalance_db=1.0, iq_phase_deg=5.0,
              phase_noise_dbchz=-80.0, sample_rate=1e6, snr_mode=0, snr_lo=0.0, snr_hi=30.0, snr_step=5.0, n_snr=1,
-             frames_per_snr=1, normalize=1):
+             frames_per_snr=1, normalize=1, equalizers=False):
     """Build a ChanCfg from the reference's user-facing parameters (SyntheticOFDMDataset.__init__,
     utils/dataset.py:195-206; NonLinearImpairments defaults, utils/ofdm_utils.py:394-521)."""
     pa = nonlinear if pa is None else pa
@@ -63,6 +63,7 @@ def make_cfg(symbol_source=0, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j,
     c.pn_sigma = float(np.sqrt(10.0 ** (phase_noise_dbchz / 10.0) * sample_rate))
     c.snr_mode, c.snr_lo, c.snr_hi, c.snr_step = snr_mode, snr_lo, snr_hi, snr_step
     c.n_snr, c.frames_per_snr, c.normalize = n_snr, frames_per_snr, normalize
+    c.equalizers = 1 if equalizers else 0
     return c
 
 
@@ -272,6 +273,16 @@ def sim_gen_metrics(cfg, gen_kind, B, gparams=None, wrom=None, brom=None, slope=
                                       ctypes.c_uint64(seed), ctypes.c_uint64(frame0), ctypes.c_int64(B), _p(m))
     assert rc == 0
     return m
+
+
+def equalize(noisy, clean, snr_db=None, method=2):
+    """ZF (method 2) / MMSE (method 3) with the genie channel estimate -> equalised frames [B,2,16] float32."""
+    noisy, clean = (_f32(a).reshape(-1, 2, 16) for a in (noisy, clean))
+    snr = None if snr_db is None else _f32(np.broadcast_to(np.asarray(snr_db, dtype=np.float32), (noisy.shape[0],)))
+    est = np.empty_like(noisy)
+    rc = lib().oracle_equalize(_p(noisy), _p(clean), _p(snr), int(method), _p(est), ctypes.c_int64(noisy.shape[0]))
+    assert rc == 0
+    return est
 
 
 def qpsk_bit_errors(cfg, frames, bits):

@@ -290,6 +290,8 @@ int oracle_frame_metrics(const float* est, const float* ref, const int32_t* bin,
 int oracle_gen_fwd_f32(const float* x, const float* gp, float* y, int64_t B, float slope);
 int oracle_gen_fwd_q(const int16_t* x, const int8_t* W, const int16_t* Bq, int16_t* y, int64_t B, int mode);
 
+void oracle_equalize_frame(const float* noisy, const float* clean, double snr_db, int method, float* est);
+
 /* mirror of ofdmgan_sim_gen_metrics: simulate -> reconstruct -> accumulate.  Also the CPU baseline that bench.py
  * times (OpenMP over frames, per-thread accumulators merged in thread order). */
 int oracle_sim_gen_metrics(const ofdmgan_chan_cfg* cfg, int gen_kind, const float* gparams, const int8_t* wrom,
@@ -325,6 +327,22 @@ int oracle_sim_gen_metrics(const ofdmgan_chan_cfg* cfg, int gen_kind, const floa
             errs = nb = 0;
             if (cfg->symbol_source == OFDMGAN_SYM_QPSK) nb = qpsk_bit_errors(cfg, noisy, bw, &errs);
             oracle_metrics_add(local + ((size_t)bin * OFDMGAN_N_METHODS + OFDMGAN_METHOD_NOEQ) * OFDMGAN_METRIC_COLS, mse, evm, ratio, errs, nb);
+            if (cfg->equalizers) {
+                double snr_db = oracle_snr_of_frame(cfg, frame, 0.0);
+                if (cfg->snr_mode != OFDMGAN_SNR_GRID) {
+                    uint32_t x12[4];
+                    oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), 12, 0, x12);
+                    snr_db = (double)(float)((double)cfg->snr_lo + ((double)cfg->snr_hi - (double)cfg->snr_lo) * u_half(x12[0]));
+                }
+                for (int method = OFDMGAN_METHOD_ZF; method <= OFDMGAN_METHOD_MMSE; ++method) {
+                    float est[32];
+                    oracle_equalize_frame(noisy, clean, snr_db, method, est);
+                    frame_mse_evm(est, clean, &mse, &evm, &ratio);
+                    errs = nb = 0;
+                    if (cfg->symbol_source == OFDMGAN_SYM_QPSK) nb = qpsk_bit_errors(cfg, est, bw, &errs);
+                    oracle_metrics_add(local + ((size_t)bin * OFDMGAN_N_METHODS + method) * OFDMGAN_METRIC_COLS, mse, evm, ratio, errs, nb);
+                }
+            }
         }
 #pragma omp critical
         for (size_t i = 0; i < rows; ++i) metrics[i] += local[i];
@@ -339,5 +357,53 @@ int oracle_qpsk_bit_errors(const ofdmgan_chan_cfg* cfg, const float* frames, con
     int64_t e = 0, n = 0;
     for (int64_t b = 0; b < B; ++b) { int eb; n += qpsk_bit_errors(cfg, frames + 32 * b, bits[b], &eb); e += eb; }
     *errs_out = e; *nbits_out = n;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ classical equalisers ----------------- */
+/* Genie-aided ZF and MMSE as benchmark_comparison.py:218-226 calls them (utils/classical_equalizers.py:33-230), in the
+ * complex64 arithmetic NumPy 2 gives the reference: CFLOAT_divide (Smith's algorithm, separately rounded float
+ * operations), eps = float32(1e-10) added to the real part.  Compiled without FP contraction (-std=c11), so the float
+ * sequence below is exactly NumPy's; ZF frames are bit-identical to the reference's (tests/golden/ref_eq.npz). */
+static void cdiv_np(float ar, float ai, float br, float bi, float* outr, float* outi) {
+    float abr = fabsf(br), abi = fabsf(bi);
+    if (abr >= abi) {
+        if (abr == 0.f && abi == 0.f) { *outr = ar / abr; *outi = ai / abr; return; }
+        float rat = bi / br;
+        float scl = 1.0f / (br + bi * rat);
+        *outr = (ar + ai * rat) * scl;
+        *outi = (ai - ar * rat) * scl;
+    } else {
+        float rat = br / bi;
+        float scl = 1.0f / (bi + br * rat);
+        *outr = (ar * rat + ai) * scl;
+        *outi = (ai * rat - ar) * scl;
+    }
+}
+
+/* method: OFDMGAN_METHOD_ZF or OFDMGAN_METHOD_MMSE; est[32] = equalised frame */
+void oracle_equalize_frame(const float* noisy, const float* clean, double snr_db, int method, float* est) {
+    const float eps = 1e-10f;
+    float inv_snr = (float)(1.0 / pow(10.0, snr_db / 10.0));
+    for (int i = 0; i < 16; ++i) {
+        float yr = noisy[i], yi = noisy[16 + i], hr, hi;
+        cdiv_np(yr, yi, clean[i] + eps, clean[16 + i], &hr, &hi);
+        if (method == OFDMGAN_METHOD_ZF) {
+            cdiv_np(yr, yi, hr + eps, hi, &est[i], &est[16 + i]);
+        } else {
+            float a = (float)sqrt((double)hr * (double)hr + (double)hi * (double)hi);
+            float den = a * a + inv_snr;
+            float scl = 1.0f / den;
+            float fr = hr * scl, fi = -hi * scl;
+            float p0 = fr * yr, p1 = fi * yi, p2 = fr * yi, p3 = fi * yr;
+            est[i] = p0 - p1;
+            est[16 + i] = p2 + p3;
+        }
+    }
+}
+
+int oracle_equalize(const float* noisy, const float* clean, const float* snr_db, int method, float* est, int64_t B) {
+    if (method != OFDMGAN_METHOD_ZF && method != OFDMGAN_METHOD_MMSE) return -1;
+    for (int64_t b = 0; b < B; ++b) oracle_equalize_frame(noisy + 32 * b, clean + 32 * b, snr_db ? (double)snr_db[b] : 20.0, method, est + 32 * b);
     return 0;
 }

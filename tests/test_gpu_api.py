@@ -157,7 +157,7 @@ def test_reference_training_iteration_through_the_modules(pkg):
         g_loss = -Dm(fake, noisy).mean() + 100.0 * F.l1_loss(fake, clean)
         g_loss.backward()
         oG.step()
-        return float(d_loss), float(g_loss)
+        return float(d_loss.detach()), float(g_loss.detach())
 
     l1 = iteration(G, D, lambda Dm, r, f, c: pkg.models.compute_gradient_penalty(Dm, r, f, c))
     l2 = iteration(TG, TD, torch_gp)
@@ -230,13 +230,17 @@ def test_synthetic_dataset_surface(pkg):
     assert torch.equal(torch.cat([r0["noisy"], r1["noisy"]]), whole["noisy"])
     with pytest.raises(pkg.OfdmGanError):
         DS(channel_type="rayleigh")
+    ts = pkg.utils.generate_test_samples(n_samples=50, snr_values=[5, 20])
+    assert list(ts) == [5, 20] and len(ts[5]) == 50 and ts[20][3]["snr"] == 20 and ts[5][0]["noisy"].shape == (2, 16)
+    err = lambda k: float(torch.stack([(d["noisy"] - d["clean"]).pow(2).mean() for d in ts[k]]).mean())
+    assert err(5) > 5 * err(20)                                # less noise at the higher SNR
 
 
 def test_run_benchmark_surface_and_consistency(pkg):
     from ofdm_gan_sr_b200.sweep import run_benchmark
     G, D, TG, TD = _pair(pkg, 6)
     res = run_benchmark(G, n_trials=2000, nonlinear=True, pa_saturation=0.8, seed=1)
-    assert set(res) == {"GAN", "NoEQ"} and list(res["GAN"]) == [0.0, 5.0, 10.0, 15.0, 20.0, 25.0, 30.0]
+    assert set(res) == {"GAN", "ZF", "MMSE", "NoEQ"} and list(res["GAN"]) == [0.0, 5.0, 10.0, 15.0, 20.0, 25.0, 30.0]
     assert set(res["GAN"][0.0]) == {"mse", "mse_std", "evm", "evm_std"}
     evm = [res["NoEQ"][s]["evm"] for s in res["NoEQ"]]
     assert all(a > b for a, b in zip(evm[:4], evm[1:5]))     # NoEQ EVM falls with SNR

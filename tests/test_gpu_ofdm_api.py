@@ -141,3 +141,66 @@ def test_random_stages_surface_and_statistics(api):
         u.ChannelModel("rayleigh").apply(r["x"], 10.0)
     with pytest.raises(ValueError):
         u.ChannelModel("bogus").apply(r["x"], 10.0)
+
+
+# ------------------------------------------------------------------------------------------------ classical equalisers
+def test_equalizers_match_reference(api):
+    """ZF bit-identical to the reference's complex64 arithmetic; MMSE to 1e-6 (np.abs' SIMD hypot is not reproduced)."""
+    pkg, u, _ = api
+    r = dict(np.load(os.path.join(GOLDEN, "ref_eq.npz")))
+    zf, met = u.ZeroForcingEqualizer().equalize_iq(r["noisy"], r["clean"])
+    assert isinstance(zf, np.ndarray) and np.array_equal(zf, r["zf"])
+    mm, _ = u.MMSEEqualizer().equalize_iq(torch.as_tensor(r["noisy"]).cuda(), torch.as_tensor(r["clean"]).cuda(),
+                                          snr_db=torch.as_tensor(r["snr"]))
+    assert mm.is_cuda
+    assert_close(mm.cpu().numpy(), r["mmse"], 1e-6, "MMSE frames")
+    one, m1 = u.MMSEEqualizer().equalize_iq(r["noisy"][5], r["clean"][5], snr_db=float(r["snr"][5]))
+    assert one.shape == (2, 16) and isinstance(m1["mse"], float)
+    assert_close(one, r["mmse"][5], 1e-6, "single frame")
+    # per-trial metrics through the metric kernel, against compute_mse / compute_evm of the reference
+    ops = pkg.ops
+    bins = torch.as_tensor((r["snr"] / 5).astype(np.int32)).cuda()
+    c = torch.as_tensor(r["clean"]).cuda()
+    m = ops.frame_metrics(torch.as_tensor(zf).cuda(), c, bins, method=2, n_snr=7)
+    m = ops.frame_metrics(mm, c, bins, method=3, n_snr=7, out=m).cpu().numpy()
+    ref = r["metrics"].reshape(7, 100, 4)
+    for method, col in ((2, 0), (3, 2)):
+        assert np.all(m[:, method, 0] == 100)
+        assert_close(m[:, method, 1], ref[:, :, col].sum(1), TOL, f"method {method} sum mse")
+        assert_close(m[:, method, 3], ref[:, :, col + 1].sum(1), TOL, f"method {method} sum evm")
+    with pytest.raises(pkg.OfdmGanError):
+        u.ZeroForcingEqualizer().equalize_iq(r["noisy"])
+
+
+def test_fused_equaliser_rows_vs_oracle_and_pieces(api):
+    import oracle
+    pkg, u, _ = api
+    ops = pkg.ops
+    gp = np.load(os.path.join(GOLDEN, "ref_fp32.npz"))["gparams"]
+    kw = dict(nonlinear=True, pa_saturation=0.8, normalize=2, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=512,
+              equalizers=True)
+    B = 7 * 512 * 6
+    m = ops.sim_gen_metrics(ops.make_cfg(**kw), B, gparams=gp, seed=4).cpu().numpy()
+    o = oracle.sim_gen_metrics(oracle.make_cfg(**kw), 0, B, gparams=gp, seed=4)
+    assert np.array_equal(m[:, :, 0], o[:, :, 0])
+    for c in (1, 3, 4):
+        assert_close(m[:, :2, c], o[:, :2, c], 2e-5, f"GAN/NoEQ col {c}")
+        assert_close(m[:, 3, c], o[:, 3, c], 2e-5, f"MMSE col {c}")
+    # ZF's residual is the rounding noise of its inputs, and the fp32 simulator's frames differ from the float64 oracle's in
+    # the last bit (and are scaled by a reciprocal multiply instead of a division): the rows agree statistically (mean EVM to
+    # ~0.2 dB at -142 dB), not digit for digit.  Digit-for-digit agreement on identical inputs is asserted below.
+    assert_close(m[:, 2, 3], o[:, 2, 3], 3e-3, "ZF sum evm")
+    # exactness on identical inputs: the same frames through the separate entry points
+    clean, noisy, snr = ops.chan_sim(ops.make_cfg(**kw), B, seed=4)
+    bins = torch.as_tensor(((np.arange(B) // 512) % 7).astype(np.int32)).cuda()
+    p = ops.frame_metrics(ops.equalize(noisy, clean, pkg._lib.METHOD_ZF), clean, bins, method=2, n_snr=7)
+    p = ops.frame_metrics(ops.equalize(noisy, clean, pkg._lib.METHOD_MMSE, snr_db=snr), clean, bins, method=3, n_snr=7, out=p).cpu().numpy()
+    for c in (1, 3, 4):
+        assert_close(m[:, 2:, c], p[:, 2:, c], 1e-6, f"fused vs pieces col {c}")
+    assert np.array_equal(ops.equalize(noisy, clean, pkg._lib.METHOD_ZF).cpu().numpy(),
+                          oracle.equalize(noisy.cpu().numpy(), clean.cpu().numpy(), None, 2))
+    # run_benchmark now reports the four data-parallel methods
+    res = pkg.sweep.run_benchmark(gp, n_trials=1000, nonlinear=True, pa_saturation=0.8, seed=2)
+    assert list(res) == ["GAN", "ZF", "MMSE", "NoEQ"] and res["ZF"][10.0]["evm"] < -130 < res["MMSE"][10.0]["evm"] < res["NoEQ"][10.0]["evm"]
+    with pytest.raises(pkg.OfdmGanError):
+        ops.sim_gen_metrics(ops.make_cfg(**kw), 64, gen_kind=1, wrom=np.zeros(2048, np.int8), brom=np.zeros(64, np.int16))
