@@ -308,6 +308,36 @@ def main():
                                       "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak,
                                       "fp32_tflops": Q_FRAMES * FLOP_GEN / (ms * 1e-3) / 1e12}
         del xf, yf
+        # ---- QPSK variant of the primary workload (QAMModulator + OFDMModulator source, N = 16, no pilots / CP): adds hard-decision BER
+        qcfg = ops.make_cfg(symbol_source=ops.SYM_QPSK, n_fft=16, cp_len=0, pilot_spacing=0, **WORKLOAD)
+        qtab = None
+        for _ in range(3):
+            qtab = ops.sim_gen_metrics(qcfg, F, gparams=gp_d, seed=2, frame0=rank * F)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(K):
+            qtab = ops.sim_gen_metrics(qcfg, F, gparams=gp_d, seed=2, frame0=(s * world + rank) * F)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / K
+        qs = ops.metrics_summary(qtab)
+        also["fused_qpsk"] = {"frames_per_s": F * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": F,
+                              "noeq_ber_per_snr": [float(v) for v in qs["ber"][:, 1]], "gan_ber_per_snr": [float(v) for v in qs["ber"][:, 0]]}
+        # ---- config 5: benchmark_comparison.run_benchmark with n_trials x 10^4 (10^6 trials x 7 SNRs x 2 scenarios), GAN / ZF / MMSE /
+        # NoEQ rows, sharded by frame index over the ranks, one final all-reduce
+        from ofdm_gan_sr_b200.sweep import run_benchmark
+        run_benchmark(gp_d, n_trials=1000, nonlinear=True, pa_saturation=0.8, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        res_lin = run_benchmark(gp_d, n_trials=1_000_000, nonlinear=False, device=dev, seed=3)
+        res_nl = run_benchmark(gp_d, n_trials=1_000_000, nonlinear=True, pa_saturation=0.8, device=dev, seed=4)
+        barrier()
+        c5_s = max_over_ranks(time.perf_counter() - t0)
+        also["benchmark_c5"] = {"trials": 14_000_000, "seconds": c5_s, "trials_per_s": 14_000_000 / c5_s, "methods": list(res_nl),
+                                "evm_db_at_10dB_nonlinear": {m: res_nl[m][10.0]["evm"] for m in res_nl},
+                                "evm_db_at_10dB_linear": {m: res_lin[m][10.0]["evm"] for m in res_lin},
+                                "note": "untrained random-init generator: the GAN row is not a quality claim"}
         # ---- config 3: CWGAN-GP step, 65,536 frames per GPU, data-parallel
         Bt = TRAIN_FRAMES_PER_GPU
         tcfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
@@ -342,7 +372,7 @@ def main():
                          "fp32_tflops_per_gpu": tflops, "fp32_frac_of_ffma_peak": tflops / ffma,
                          "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"]}
-        launches += 2 * K * 1 + K * 2 + K * trainer.launches_per_step()
+        launches += 2 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
