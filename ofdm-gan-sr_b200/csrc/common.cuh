@@ -81,6 +81,20 @@ __device__ __forceinline__ void philox4x32_10(const PhiloxKeys& k, uint32_t c0, 
 __device__ __forceinline__ float u_open(uint32_t x) { return __uint_as_float(0x3F800000u | (x >> 9)) - (1.0f - 5.9604644775390625e-08f); }
 __device__ __forceinline__ float u_half(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 
+// ---- packed fp32x2 (sm_100 FFMA2): two FMAs per issue slot -----------------------------------------------------
+// A 64-bit value holds two floats (lo, hi) in an aligned register pair.  ptxas folds a pair built from the same scalar
+// twice into the broadcast operand form (FFMA2 Rd, Ra.F32, URb.F32x2, Rc), and a pair loaded from constant memory into a
+// uniform-register pair, so no packing instructions are executed.  Same FLOP/s peak as scalar FFMA (the FMA pipe is
+// busy two cycles), but half the issue slots - which is what these issue-bound kernels are short of
+// (tools/microbench/ffma2.cu: 72 vs 74 TFLOP/s alone, 17.8 vs 25.9 TFLOP/s when mixed 1:2 with ALU work).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 fma2_rd(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// a pair of adjacent floats of a constant image (8-byte aligned index)
+__device__ __forceinline__ f32x2 ldc2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }
+
 // ---- single-instruction MUFU forms (no range fix-up code, no slow-path calls) ---------------------------------
 __device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

@@ -121,63 +121,77 @@ __device__ __forceinline__ float fx_finish(float acc, float bias, bool act) {
 }
 __device__ __forceinline__ float fx_clip(float v) { return v > 256.f ? 255.f : (v < -256.f ? -255.f : v); }
 
-// mode spec: RTL primitives on the textbook dataflow (all channels, aligned weights, 1x1 output conv, clip both)
+// mode spec: RTL primitives on the textbook dataflow (all channels, aligned weights, 1x1 output conv, clip both).
+// Two output channels per FFMA2.RM: acc2 = fma.rm.f32x2((a, a), (w[oc], w[oc+1]), acc2) with the weight pair read from the
+// interleaved half of the Q image.
+__device__ __forceinline__ f32x2 fxacc2(float a, f32x2 w2, f32x2 acc2) { return fma2_rd(pk2(a, a), w2, acc2); }
+
 __device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, const float (&x)[2][16], float (&y)[2][16]) {
     float a1[4][8], a2[8][4], sk[4][8];
+    const f32x2 magic2 = pk2(FX_MAGIC, FX_MAGIC);
 #pragma unroll
-    for (int oc = 0; oc < 4; ++oc)
+    for (int o2 = 0; o2 < 2; ++o2)
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            float acc = FX_MAGIC;
+            f32x2 acc = magic2;
 #pragma unroll
             for (int ic = 0; ic < 2; ++ic)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int i = 2 * p + k - 1;
-                    if (i >= 0) acc = fxacc(x[ic][i], Q[0 + (oc * 2 + ic) * 3 + k], acc);
+                    if (i >= 0) acc = fxacc2(x[ic][i], ldc2(Q + QI2_ENC + ((o2 * 2 + ic) * 3 + k) * 2), acc);
                 }
-            a1[oc][p] = fx_finish(acc, Q[QI_BIAS + 0 + oc], true);
+            float lo, hi;
+            upk2(acc, lo, hi);
+            a1[2 * o2][p] = fx_finish(lo, Q[QI_BIAS + 0 + 2 * o2], true);
+            a1[2 * o2 + 1][p] = fx_finish(hi, Q[QI_BIAS + 0 + 2 * o2 + 1], true);
         }
 #pragma unroll
-    for (int oc = 0; oc < 8; ++oc)
+    for (int o2 = 0; o2 < 4; ++o2)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            float acc = FX_MAGIC;
+            f32x2 acc = magic2;
 #pragma unroll
             for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int i = 2 * p + k - 1;
-                    if (i >= 0) acc = fxacc(a1[ic][i], Q[24 + (oc * 4 + ic) * 3 + k], acc);
+                    if (i >= 0) acc = fxacc2(a1[ic][i], ldc2(Q + QI2_BN + ((o2 * 4 + ic) * 3 + k) * 2), acc);
                 }
-            a2[oc][p] = fx_finish(acc, Q[QI_BIAS + 4 + oc], true);
+            float lo, hi;
+            upk2(acc, lo, hi);
+            a2[2 * o2][p] = fx_finish(lo, Q[QI_BIAS + 4 + 2 * o2], true);
+            a2[2 * o2 + 1][p] = fx_finish(hi, Q[QI_BIAS + 4 + 2 * o2 + 1], true);
         }
     // per-tap floor does not commute with weight folding: evaluate the 3 taps on the upsampled signal
 #pragma unroll
-    for (int oc = 0; oc < 4; ++oc)
+    for (int o2 = 0; o2 < 2; ++o2)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            float acc = FX_MAGIC;
+            f32x2 acc = magic2;
 #pragma unroll
             for (int ic = 0; ic < 8; ++ic)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int i = q + k - 1;
-                    if (i >= 0 && i < 8) acc = fxacc(a2[ic][i >> 1], Q[120 + (oc * 8 + ic) * 3 + k], acc);
+                    if (i >= 0 && i < 8) acc = fxacc2(a2[ic][i >> 1], ldc2(Q + QI2_DEC + ((o2 * 8 + ic) * 3 + k) * 2), acc);
                 }
-            sk[oc][q] = fx_sat16(fx_finish(acc, Q[QI_BIAS + 12 + oc], true) + a1[oc][q]);
+            float lo, hi;
+            upk2(acc, lo, hi);
+            sk[2 * o2][q] = fx_sat16(fx_finish(lo, Q[QI_BIAS + 12 + 2 * o2], true) + a1[2 * o2][q]);
+            sk[2 * o2 + 1][q] = fx_sat16(fx_finish(hi, Q[QI_BIAS + 12 + 2 * o2 + 1], true) + a1[2 * o2 + 1][q]);
         }
 #pragma unroll
-    for (int oc = 0; oc < 2; ++oc)
+    for (int p = 0; p < 8; ++p) {
+        f32x2 acc = magic2;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            float acc = FX_MAGIC;
-#pragma unroll
-            for (int ic = 0; ic < 4; ++ic) acc = fxacc(sk[ic][p], Q[216 + oc * 4 + ic], acc);
-            float v = fx_clip(fx_finish(acc, Q[QI_BIAS + 16 + oc], false));
-            y[oc][2 * p] = v;
-            y[oc][2 * p + 1] = v;
-        }
+        for (int ic = 0; ic < 4; ++ic) acc = fxacc2(sk[ic][p], ldc2(Q + QI2_OUT + ic * 2), acc);
+        float lo, hi;
+        upk2(acc, lo, hi);
+        const float v0 = fx_clip(fx_finish(lo, Q[QI_BIAS + 16], false)), v1 = fx_clip(fx_finish(hi, Q[QI_BIAS + 17], false));
+        y[0][2 * p] = v0; y[0][2 * p + 1] = v0;
+        y[1][2 * p] = v1; y[1][2 * p + 1] = v1;
+    }
 }
 
 // mode rtl_literal: what the committed RTL computes (oracle/fixed_point.c skewed_conv).

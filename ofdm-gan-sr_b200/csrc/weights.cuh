@@ -33,8 +33,11 @@ constexpr int GP_ENC_W = 0, GP_ENC_B = 24, GP_BN_W = 28, GP_BN_B = 124, GP_DEC_W
               GP_OUT_B = 256;
 constexpr int DP_C1_W = 0, DP_C1_B = 96, DP_C2_W = 104, DP_C2_B = 488, DP_FC_W = 504, DP_FC_B = 520;
 constexpr int OG_D_IMG = 528;
-constexpr int OG_Q_IMG = 256;
+constexpr int OG_Q_IMG = 512;
 constexpr int QI_BIAS = 232;
+// second half of the Q image: the same weights with the two output channels of a pair interleaved, [oc/2][ic][k][2], so one
+// 64-bit uniform load feeds a packed FFMA2 (two output channels per instruction)
+constexpr int QI2_ENC = 256, QI2_BN = 280, QI2_DEC = 376, QI2_OUT = 472;     // 24 + 96 + 96 + 8 floats
 
 static __constant__ __align__(16) float c_g[OG_G_IMG];
 static __constant__ __align__(16) float c_d[OG_D_IMG];
@@ -100,6 +103,17 @@ static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot,
     for (int i = 0; i < OG_Q_IMG; ++i) img[i] = 0.f;
     for (int i = 0; i < 226; ++i) img[i] = (float)wrom_host[i] * (1.0f / 128.0f);
     for (int i = 0; i < 18; ++i) img[QI_BIAS + i] = (float)brom_host[i];
+    auto pairs = [&](int dst, int wa, int OC, int IC, int K) {
+        for (int o2 = 0; o2 < OC / 2; ++o2)
+            for (int ic = 0; ic < IC; ++ic)
+                for (int k = 0; k < K; ++k)
+                    for (int h = 0; h < 2; ++h)
+                        img[dst + ((o2 * IC + ic) * K + k) * 2 + h] = (float)wrom_host[wa + ((2 * o2 + h) * IC + ic) * K + k] * (1.0f / 128.0f);
+    };
+    pairs(QI2_ENC, 0, 4, 2, 3);
+    pairs(QI2_BN, 24, 8, 4, 3);
+    pairs(QI2_DEC, 120, 4, 8, 3);
+    pairs(QI2_OUT, 216, 2, 4, 1);
     // pageable source: the runtime stages it before returning, so the stack buffer may die afterwards
     OG_CHECK(cudaMemcpyToSymbolAsync(c_q, img, sizeof img, 0, cudaMemcpyHostToDevice, s));
     return 0;
