@@ -19,85 +19,89 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float lrelu_sel(float v, float slope) { return lrelu(v, slope); }
 
 // ---------------------------------------------------------------------------------------------------- fp32
-// x[2][16] -> y[2][16].  If TAPE, also returns the activations the backward pass needs:
-//   a1[4][8] = lrelu(enc1), a2[8][4] = lrelu(bottleneck), z3pos bitmask (dec1 pre-activation > 0), sk[4][8] = skip sum
-template <bool TAPE>
-__device__ __forceinline__ void gen_fwd_f32(const float* __restrict__ W, float slope, const float (&x)[2][16],
-                                            float (&y)[2][16], float (&a1)[4][8], float (&a2)[8][4], float (&sk)[4][8],
-                                            uint32_t& z3pos) {
+// x[2][16] -> y[2][16], models/generator.py:180-208.  Two output channels per packed FFMA2: the input sample is the broadcast
+// scalar operand, the weight pair (w[oc], w[oc+1]) comes from the pair-interleaved half of the G image as one uniform load.
+__device__ __forceinline__ void gen_fwd_f32_infer(const float* __restrict__ W, float slope, const float (&x)[2][16],
+                                                  float (&y)[2][16]) {
+    float a1[4][8], a2[8][4], sk[4][8];
     // enc1: Conv1d(2->4, k3, s2, p1) + LeakyReLU
 #pragma unroll
-    for (int oc = 0; oc < 4; ++oc)
+    for (int o2 = 0; o2 < 2; ++o2)
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            float acc = W[GI_ENC_B + oc];
+            f32x2 acc = ldc2(W + GI_ENC_B + 2 * o2);
 #pragma unroll
             for (int ic = 0; ic < 2; ++ic)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int i = 2 * p + k - 1;
-                    if (i >= 0) acc = fmaf(W[GI_ENC_W + (oc * 2 + ic) * 3 + k], x[ic][i], acc);
+                    if (i >= 0) acc = fma2(pk2(x[ic][i], x[ic][i]), ldc2(W + GI2_ENC + ((o2 * 2 + ic) * 3 + k) * 2), acc);
                 }
-            a1[oc][p] = lrelu_sel(acc, slope);
+            float lo, hi;
+            upk2(acc, lo, hi);
+            a1[2 * o2][p] = lrelu(lo, slope);
+            a1[2 * o2 + 1][p] = lrelu(hi, slope);
         }
     // bottleneck: Conv1d(4->8, k3, s2, p1) + LeakyReLU
 #pragma unroll
-    for (int oc = 0; oc < 8; ++oc)
+    for (int o2 = 0; o2 < 4; ++o2)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            float acc = W[GI_BN_B + oc];
+            f32x2 acc = ldc2(W + GI_BN_B + 2 * o2);
 #pragma unroll
             for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int i = 2 * p + k - 1;
-                    if (i >= 0) acc = fmaf(W[GI_BN_W + (oc * 4 + ic) * 3 + k], a1[ic][i], acc);
+                    if (i >= 0) acc = fma2(pk2(a1[ic][i], a1[ic][i]), ldc2(W + GI2_BN + ((o2 * 4 + ic) * 3 + k) * 2), acc);
                 }
-            a2[oc][p] = lrelu_sel(acc, slope);
+            float lo, hi;
+            upk2(acc, lo, hi);
+            a2[2 * o2][p] = lrelu(lo, slope);
+            a2[2 * o2 + 1][p] = lrelu(hi, slope);
         }
     // upsample x2 + dec1 Conv1d(8->4, k3, s1, p1) + LeakyReLU, folded; + additive skip
-    z3pos = 0;
 #pragma unroll
-    for (int oc = 0; oc < 4; ++oc)
+    for (int o2 = 0; o2 < 2; ++o2)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            float e = W[GI_DEC_B + oc], o = e;
+            f32x2 e = ldc2(W + GI_DEC_B + 2 * o2), o = e;
 #pragma unroll
             for (int ic = 0; ic < 8; ++ic) {
-                const float* F = W + GI_DEC_F + (oc * 8 + ic) * 4;
-                if (p > 0) e = fmaf(F[0], a2[ic][p - 1], e);
-                e = fmaf(F[1], a2[ic][p], e);
-                o = fmaf(F[2], a2[ic][p], o);
-                if (p < 3) o = fmaf(F[3], a2[ic][p + 1], o);
+                const float* F = W + GI2_DEC + (o2 * 8 + ic) * 8;
+                if (p > 0) e = fma2(pk2(a2[ic][p - 1], a2[ic][p - 1]), ldc2(F + 0), e);
+                e = fma2(pk2(a2[ic][p], a2[ic][p]), ldc2(F + 2), e);
+                o = fma2(pk2(a2[ic][p], a2[ic][p]), ldc2(F + 4), o);
+                if (p < 3) o = fma2(pk2(a2[ic][p + 1], a2[ic][p + 1]), ldc2(F + 6), o);
             }
-            if (TAPE) z3pos |= (e > 0.f ? 1u : 0u) << (oc * 8 + 2 * p) | (o > 0.f ? 1u : 0u) << (oc * 8 + 2 * p + 1);
-            sk[oc][2 * p] = lrelu_sel(e, slope) + a1[oc][2 * p];
-            sk[oc][2 * p + 1] = lrelu_sel(o, slope) + a1[oc][2 * p + 1];
+            float e0, e1, o0, o1;
+            upk2(e, e0, e1);
+            upk2(o, o0, o1);
+            sk[2 * o2][2 * p] = lrelu(e0, slope) + a1[2 * o2][2 * p];
+            sk[2 * o2][2 * p + 1] = lrelu(o0, slope) + a1[2 * o2][2 * p + 1];
+            sk[2 * o2 + 1][2 * p] = lrelu(e1, slope) + a1[2 * o2 + 1][2 * p];
+            sk[2 * o2 + 1][2 * p + 1] = lrelu(o1, slope) + a1[2 * o2 + 1][2 * p + 1];
         }
     // upsample x2 + out_conv Conv1d(4->2, k3, s1, p1), folded; tanh
 #pragma unroll
-    for (int oc = 0; oc < 2; ++oc)
+    for (int p = 0; p < 8; ++p) {
+        f32x2 e = ldc2(W + GI_OUT_B), o = e;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            float e = W[GI_OUT_B + oc], o = e;
-#pragma unroll
-            for (int ic = 0; ic < 4; ++ic) {
-                const float* F = W + GI_OUT_F + (oc * 4 + ic) * 4;
-                if (p > 0) e = fmaf(F[0], sk[ic][p - 1], e);
-                e = fmaf(F[1], sk[ic][p], e);
-                o = fmaf(F[2], sk[ic][p], o);
-                if (p < 7) o = fmaf(F[3], sk[ic][p + 1], o);
-            }
-            y[oc][2 * p] = tanh_fast(e);
-            y[oc][2 * p + 1] = tanh_fast(o);
+        for (int ic = 0; ic < 4; ++ic) {
+            const float* F = W + GI2_OUT + ic * 8;
+            if (p > 0) e = fma2(pk2(sk[ic][p - 1], sk[ic][p - 1]), ldc2(F + 0), e);
+            e = fma2(pk2(sk[ic][p], sk[ic][p]), ldc2(F + 2), e);
+            o = fma2(pk2(sk[ic][p], sk[ic][p]), ldc2(F + 4), o);
+            if (p < 7) o = fma2(pk2(sk[ic][p + 1], sk[ic][p + 1]), ldc2(F + 6), o);
         }
-}
-
-__device__ __forceinline__ void gen_fwd_f32_infer(const float* __restrict__ W, float slope, const float (&x)[2][16],
-                                                  float (&y)[2][16]) {
-    float a1[4][8], a2[8][4], sk[4][8];
-    uint32_t z;
-    gen_fwd_f32<false>(W, slope, x, y, a1, a2, sk, z);
+        float e0, e1, o0, o1;
+        upk2(e, e0, e1);
+        upk2(o, o0, o1);
+        y[0][2 * p] = tanh_fast(e0);
+        y[0][2 * p + 1] = tanh_fast(o0);
+        y[1][2 * p] = tanh_fast(e1);
+        y[1][2 * p + 1] = tanh_fast(o1);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- fixed point

@@ -27,7 +27,9 @@ constexpr int GI_DEC_F = 132;    // [4][8][4] folded
 constexpr int GI_DEC_B = 260;    // [4]
 constexpr int GI_OUT_F = 264;    // [2][4][4] folded
 constexpr int GI_OUT_B = 296;    // [2]
-constexpr int OG_G_IMG = 304;
+// pair-interleaved copies of the four weight blocks, [oc/2][ic][k][2]: one 64-bit uniform load feeds a packed FFMA2
+constexpr int GI2_ENC = 304, GI2_BN = 328, GI2_DEC = 424, GI2_OUT = 552;   // 24 + 96 + 128 + 32 floats
+constexpr int OG_G_IMG = 584;
 // raw parameter offsets (torch order, include/ofdmgan.h)
 constexpr int GP_ENC_W = 0, GP_ENC_B = 24, GP_BN_W = 28, GP_BN_B = 124, GP_DEC_W = 132, GP_DEC_B = 228, GP_OUT_W = 232,
               GP_OUT_B = 256;
@@ -43,24 +45,36 @@ static __constant__ __align__(16) float c_g[OG_G_IMG];
 static __constant__ __align__(16) float c_d[OG_D_IMG];
 static __constant__ __align__(16) float c_q[OG_Q_IMG];
 
-static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
-    int i = threadIdx.x;
-    if (i < 132) { img[i] = p[i]; return; }                               // enc1 + bottleneck, verbatim
-    if (i < 132 + 128) {                                                  // dec1 folded
-        int j = i - 132, pair = j >> 2, t = j & 3;
+// value of entry i (< GI2_ENC) of the G image from the raw parameters
+__device__ __forceinline__ float g_img_base(const float* __restrict__ p, int i) {
+    if (i < 132) return p[i];                                              // enc1 + bottleneck, verbatim
+    if (i < 132 + 128) {                                                   // dec1 folded
+        const int j = i - 132, pair = j >> 2, t = j & 3;
         const float* w = p + GP_DEC_W + pair * 3;
-        img[i] = t == 0 ? w[0] : t == 1 ? w[1] + w[2] : t == 2 ? w[0] + w[1] : w[2];
-        return;
+        return t == 0 ? w[0] : t == 1 ? w[1] + w[2] : t == 2 ? w[0] + w[1] : w[2];
     }
-    if (i < 264) { img[i] = p[GP_DEC_B + (i - 260)]; return; }
+    if (i < 264) return p[GP_DEC_B + (i - 260)];
     if (i < 296) {
-        int j = i - 264, pair = j >> 2, t = j & 3;
+        const int j = i - 264, pair = j >> 2, t = j & 3;
         const float* w = p + GP_OUT_W + pair * 3;
-        img[i] = t == 0 ? w[0] : t == 1 ? w[1] + w[2] : t == 2 ? w[0] + w[1] : w[2];
-        return;
+        return t == 0 ? w[0] : t == 1 ? w[1] + w[2] : t == 2 ? w[0] + w[1] : w[2];
     }
-    if (i < 298) { img[i] = p[GP_OUT_B + (i - 296)]; return; }
-    if (i < OG_G_IMG) img[i] = 0.f;
+    if (i < 298) return p[GP_OUT_B + (i - 296)];
+    return 0.f;
+}
+
+static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
+    const int i = threadIdx.x;
+    if (i < GI2_ENC) { img[i] = g_img_base(p, i); return; }
+    if (i >= OG_G_IMG) return;
+    // pair-interleaved copies: entry ((o2*IC + ic)*K + k)*2 + h  <-  base[((2*o2+h)*IC + ic)*K + k]
+    int e, base, IC, K;
+    if (i < GI2_BN) { e = i - GI2_ENC; base = GI_ENC_W; IC = 2; K = 3; }
+    else if (i < GI2_DEC) { e = i - GI2_BN; base = GI_BN_W; IC = 4; K = 3; }
+    else if (i < GI2_OUT) { e = i - GI2_DEC; base = GI_DEC_F; IC = 8; K = 4; }
+    else { e = i - GI2_OUT; base = GI_OUT_F; IC = 4; K = 4; }
+    const int h = e & 1, r = e >> 1, k = r % K, ic = (r / K) % IC, o2 = r / (K * IC);
+    img[i] = g_img_base(p, base + ((2 * o2 + h) * IC + ic) * K + k);
 }
 
 static __global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
