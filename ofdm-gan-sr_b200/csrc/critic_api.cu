@@ -24,9 +24,8 @@ __global__ void __launch_bounds__(OG_THREADS, CAPI_PER_SM) k_disc_fwd(const floa
         tile_fill_f32(cand, base, B, t_a, lane);
         tile_fill_f32(cond, base, B, t_c, lane);
         __syncwarp();
-        float a1[8][8], s;
-        cs_conv1_fwd(c_d, slope, t_a, t_c, lane, a1);
-        cs_conv2_fwd<false>(c_d, slope, 0.f, a1, acc, lane, s);
+        uint64_t m1, m2;
+        const float s = cs_score_only(c_d, slope, t_a, t_c, acc, lane, m1, m2);
         if (base + lane < B) score[base + lane] = s;
     }
 }

@@ -61,33 +61,17 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
         }
         // (2) critic on (fake, noisy): d(-adv_w * D)/d fake, + rec_w * sign(fake - clean)/32 -> upstream gradient rows in t_c
         {
-            float dz1[8][8];
+            f32x2 dz1[4][8];
             {
                 uint64_t m1, m2;
-                float score;
-                {
-                    float a1[8][8];
-                    m1 = cs_conv1_fwd(WD, a.slope, t_y, t_x, lane, a1);
-                    m2 = cs_conv2_fwd<false>(WD, a.slope, 0.f, a1, acc, lane, score);
-                }
+                const float score = cs_score_only(WD, a.slope, t_y, t_x, acc, lane, m1, m2);
                 if (live) s_d += score;
                 cs_bwd_to_z1(WD, a.slope, live ? -a.adv_w : 0.f, m1, m2, dz1);
             }
 #pragma unroll 1
             for (int ic = 0; ic < 2; ++ic) {
-                const float* w = WD + DP_C1_W + ic * 3;
                 float row[16], y[16], c[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) row[i] = 0.f;
-#pragma unroll
-                for (int oc = 0; oc < 8; ++oc)
-#pragma unroll
-                    for (int p = 0; p < 8; ++p)
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const int i = 2 * p + k - 1;
-                            if (i >= 0) row[i] = fmaf(w[oc * 12 + k], dz1[oc][p], row[i]);
-                        }
+                cs_conv1T_row(WD, dz1, ic, row);
                 row_read(t_y, lane, ic, y);
                 row_read(t_c, lane, ic, c);
 #pragma unroll

@@ -34,7 +34,12 @@ constexpr int OG_G_IMG = 584;
 constexpr int GP_ENC_W = 0, GP_ENC_B = 24, GP_BN_W = 28, GP_BN_B = 124, GP_DEC_W = 132, GP_DEC_B = 228, GP_OUT_W = 232,
               GP_OUT_B = 256;
 constexpr int DP_C1_W = 0, DP_C1_B = 96, DP_C2_W = 104, DP_C2_B = 488, DP_FC_W = 504, DP_FC_B = 520;
-constexpr int OG_D_IMG = 528;
+// D image: the 521 raw parameters (+pad to 528), then pair-interleaved copies for packed FFMA2:
+//   DI2_C1   conv1.weight as [oc/2][ic][k][2]   (two output channels per instruction: forward, d/d input reduction)
+//   DI2_C2   conv2.weight as [oc/2][ic][k][2]   (forward)
+//   DI2_C2T  conv2.weight as [oc][ic/2][k][2]   (transposed conv of the backward pass: two INPUT channels per instruction)
+constexpr int DI2_C1 = 528, DI2_C2 = 624, DI2_C2T = 1008;                 // 96 + 384 + 384 floats
+constexpr int OG_D_IMG = 1392;
 constexpr int OG_Q_IMG = 512;
 constexpr int QI_BIAS = 232;
 // second half of the Q image: the same weights with the two output channels of a pair interleaved, [oc/2][ic][k][2], so one
@@ -78,8 +83,19 @@ static __global__ void prep_g_image(const float* __restrict__ p, float* __restri
 }
 
 static __global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
-    int i = threadIdx.x + blockIdx.x * blockDim.x;
-    if (i < OG_D_IMG) img[i] = i < OFDMGAN_D_NPARAMS ? p[i] : 0.f;
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i >= OG_D_IMG) return;
+    if (i < DI2_C1) { img[i] = i < OFDMGAN_D_NPARAMS ? p[i] : 0.f; return; }
+    if (i < DI2_C2) {                                            // ((o2*4 + ic)*3 + k)*2 + h <- conv1[2*o2+h][ic][k]
+        const int e = i - DI2_C1, h = e & 1, r = e >> 1, k = r % 3, ic = (r / 3) % 4, o2 = r / 12;
+        img[i] = p[DP_C1_W + ((2 * o2 + h) * 4 + ic) * 3 + k];
+    } else if (i < DI2_C2T) {                                    // ((o2*8 + ic)*3 + k)*2 + h <- conv2[2*o2+h][ic][k]
+        const int e = i - DI2_C2, h = e & 1, r = e >> 1, k = r % 3, ic = (r / 3) % 8, o2 = r / 24;
+        img[i] = p[DP_C2_W + ((2 * o2 + h) * 8 + ic) * 3 + k];
+    } else {                                                     // ((oc*4 + i2)*3 + k)*2 + h <- conv2[oc][2*i2+h][k]
+        const int e = i - DI2_C2T, h = e & 1, r = e >> 1, k = r % 3, i2 = (r / 3) % 4, oc = r / 12;
+        img[i] = p[DP_C2_W + (oc * 8 + 2 * i2 + h) * 3 + k];
+    }
 }
 
 // params258 may be a host or a device pointer
@@ -104,7 +120,7 @@ static int upload_d(const float* params521, int slot, cudaStream_t s) {
     void* img = nullptr;
     rc = scratch_for_slot(slot, OG_D_IMG * sizeof(float), 3, &img);
     if (rc) return rc;
-    prep_d_image<<<1, OG_D_IMG, 0, s>>>(dev, (float*)img);
+    prep_d_image<<<(OG_D_IMG + 255) / 256, 256, 0, s>>>(dev, (float*)img);
     OG_CHECK(cudaGetLastError());
     OG_CHECK(cudaMemcpyToSymbolAsync(c_d, img, OG_D_IMG * sizeof(float), 0,
                                      cudaMemcpyDeviceToDevice, s));
