@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 2
+#define OFDMGAN_ABI_VERSION 3
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -51,7 +51,15 @@ enum { OFDMGAN_SYM_GAUSSIAN = 0,          /* (randn+j randn)/sqrt2 per bin      
        OFDMGAN_SYM_QPSK = 1 };            /* QAMModulator('QPSK') + OFDMModulator     utils/ofdm_utils.py:105-109,281-329 */
 enum { OFDMGAN_SCALE_SQRT_N = 0,          /* ifft * sqrt(N)                           utils/dataset.py:247 */
        OFDMGAN_SCALE_N = 1 };             /* ifft * N                                 utils/ofdm_utils.py:320 */
-enum { OFDMGAN_IMPAIR_PA = 1, OFDMGAN_IMPAIR_IQ = 2, OFDMGAN_IMPAIR_PN = 4 };   /* apply_all order :571-605 */
+enum { OFDMGAN_IMPAIR_PA = 1, OFDMGAN_IMPAIR_IQ = 2, OFDMGAN_IMPAIR_PN = 4,     /* apply_all order :571-605 */
+       OFDMGAN_IMPAIR_SALEH = 8,          /* apply_pa_saleh :424-455 (in the PA position)      */
+       OFDMGAN_IMPAIR_DC = 16,            /* apply_dc_offset :524-543                           */
+       OFDMGAN_IMPAIR_CFO = 32 };         /* apply_cfo :546-568                                 */
+enum { OFDMGAN_CHAN_AWGN = 0,             /* ChannelModel._apply_awgn      :675-708 */
+       OFDMGAN_CHAN_RAYLEIGH = 1,         /* ChannelModel._apply_rayleigh  :710-740 : y = h x + n, h ~ CN(0,1) per frame */
+       OFDMGAN_CHAN_RICIAN = 2,           /* ChannelModel._apply_rician    :742-786 */
+       OFDMGAN_CHAN_MULTIPATH = 3 };      /* ChannelModel._apply_multipath :788-832 : np.convolve(x, h, 'same'), Rayleigh taps */
+#define OFDMGAN_MAX_TAPS 4
 enum { OFDMGAN_SNR_UNIFORM = 0,           /* np.random.uniform(lo, hi) per frame      utils/dataset.py:267 */
        OFDMGAN_SNR_GRID = 1,              /* snr = lo + step*((frame/frames_per_snr) % n_snr)  benchmark_comparison.py:179-182 */
        OFDMGAN_SNR_NONE = 2 };            /* no AWGN stage (NonLinearImpairments.apply_* on their own) */
@@ -83,6 +91,14 @@ typedef struct ofdmgan_chan_cfg {
     int32_t normalize;         /* OFDMGAN_NORM_* */
     int32_t equalizers;        /* != 0: the fused sweep also fills the OFDMGAN_METHOD_ZF / _MMSE rows (genie-aided equalisers of
                                   benchmark_comparison.py:218-226, utils/classical_equalizers.py:33-230) */
+    int32_t channel_type;      /* OFDMGAN_CHAN_* (fading is applied after the impairments, before the AWGN) */
+    float   rician_k;          /* K factor                                                   :745 */
+    int32_t n_taps;            /* multipath: number of taps (<= OFDMGAN_MAX_TAPS), distinct delays */
+    int32_t tap_delay[OFDMGAN_MAX_TAPS];
+    float   tap_amp[OFDMGAN_MAX_TAPS];     /* sqrt(power / sum(powers))                       :806-812 */
+    float   saleh_alpha_a, saleh_beta_a, saleh_alpha_p, saleh_beta_p;
+    float   dc_i, dc_q;        /* DC offset relative to sqrt(mean |x|^2)                     :541-543 */
+    float   cfo_step;          /* 2 pi cfo_hz / sample_rate (radians per sample)             :565-566 */
 } ofdmgan_chan_cfg;
 
 /* Host-generated randomness for parity runs, in the reference's np.random draw order per frame
@@ -96,6 +112,8 @@ typedef struct ofdmgan_chan_rand {
     const float*    noise;     /* [B][32]  randn Re[16], randn Im[16] */
     const float*    tx;        /* [B][32]  time-domain frame Re[16], Im[16]: replaces symbol generation + IFFT altogether
                                   (NonLinearImpairments.apply_* / ChannelModel.apply on caller-supplied signals) */
+    const float*    fade;      /* [B][8]   fading draws in the reference's order: rayleigh {randn, randn}; rician {uniform(0, 2 pi),
+                                  randn, randn}; multipath {randn, randn} per tap */
 } ofdmgan_chan_rand;
 
 /* per-SNR-bin, per-method accumulator row produced by ofdmgan_sim_gen_metrics (doubles):
@@ -140,12 +158,20 @@ int ofdmgan_chan_sim(const ofdmgan_chan_cfg* cfg_host, const ofdmgan_chan_rand* 
  * randomness).  sym/noise [B][32], pn [B][16], snr_db [B], bits [B]; any may be NULL. */
 int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t frame0, float* sym_dev,
                        uint32_t* bits_dev, float* pn_dev, float* snr_db_dev, float* noise_dev, int64_t B, void* stream);
+/* the fading draws of those frames in the ofdmgan_chan_rand.fade layout, [B][8] (ChannelModel.apply's channel_response is
+ * formed from them) */
+int ofdmgan_chan_fade_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t frame0, float* fade_dev, int64_t B, void* stream);
 /* Philox4x32-10 block (test hook): out[n][4] = philox(key=seed, ctr=(c0[i] lo/hi, c2, c3)) */
 int ofdmgan_philox_blocks(uint64_t seed, uint64_t ctr0, uint32_t c2, uint32_t c3, uint32_t* out_dev, int64_t n,
                           void* stream);
 
 /* ---- modulator API (utils/ofdm_utils.py QAMModulator / OFDMModulator as batched entry points) ------------------------ */
 /* complex values are interleaved (re, im) float pairs = torch.complex64 / numpy complex64 memory layout. */
+/* replaces QAMModulator(QPSK | QAM16 | QAM64).modulate / .demodulate, utils/ofdm_utils.py:137-222: bits_per_symbol in {2, 4, 6};
+ * constellation index = bits MSB first; QAM16/64 point = (levels[idx % sqrtM] + j levels[idx / sqrtM]) / norm (np.meshgrid order);
+ * hard decisions pick the nearest point, ties to the lowest index. */
+int ofdmgan_qam_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, int bits_per_symbol, void* stream);
+int ofdmgan_qam_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_symbols, int bits_per_symbol, void* stream);
 /* replaces QAMModulator('QPSK').modulate, utils/ofdm_utils.py:163-193: bits_dev[2n] (0/1 bytes, MSB first) -> sym_dev[n] */
 int ofdmgan_qpsk_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, void* stream);
 /* replaces QAMModulator('QPSK').demodulate, :195-222: nearest constellation point, ties to the lowest index */

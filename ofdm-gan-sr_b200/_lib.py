@@ -35,12 +35,16 @@ class ChanCfg(ctypes.Structure):
         ("snr_mode", ctypes.c_int32), ("snr_lo", c_f), ("snr_hi", c_f), ("snr_step", c_f),
         ("n_snr", ctypes.c_int32), ("frames_per_snr", c_i64), ("normalize", ctypes.c_int32),
         ("equalizers", ctypes.c_int32),
+        ("channel_type", ctypes.c_int32), ("rician_k", ctypes.c_float), ("n_taps", ctypes.c_int32),
+        ("tap_delay", ctypes.c_int32 * 4), ("tap_amp", ctypes.c_float * 4),
+        ("saleh_alpha_a", ctypes.c_float), ("saleh_beta_a", ctypes.c_float), ("saleh_alpha_p", ctypes.c_float),
+        ("saleh_beta_p", ctypes.c_float), ("dc_i", ctypes.c_float), ("dc_q", ctypes.c_float), ("cfo_step", ctypes.c_float),
     ]
 
 
 class ChanRand(ctypes.Structure):
     """`ofdmgan_chan_rand`: device pointers to host-generated draws (any may be NULL)."""
-    _fields_ = [("sym", c_p), ("bits", c_p), ("pn", c_p), ("snr_db", c_p), ("noise", c_p), ("tx", c_p)]
+    _fields_ = [("sym", c_p), ("bits", c_p), ("pn", c_p), ("snr_db", c_p), ("noise", c_p), ("tx", c_p), ("fade", c_p)]
 
 
 _SIGNATURES = {
@@ -55,6 +59,9 @@ _SIGNATURES = {
     "ofdmgan_chan_sim": (ctypes.c_int, [c_p, c_p, c_u64, c_u64, c_p, c_p, c_p, c_i64, c_p]),
     "ofdmgan_chan_draws": (ctypes.c_int, [c_p, c_u64, c_u64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
     "ofdmgan_philox_blocks": (ctypes.c_int, [c_u64, c_u64, ctypes.c_uint32, ctypes.c_uint32, c_p, c_i64, c_p]),
+    "ofdmgan_chan_fade_draws": (ctypes.c_int, [c_p, c_u64, c_u64, c_p, c_i64, c_p]),
+    "ofdmgan_qam_modulate": (ctypes.c_int, [c_p, c_p, c_i64, ctypes.c_int, c_p]),
+    "ofdmgan_qam_demodulate": (ctypes.c_int, [c_p, c_p, c_i64, ctypes.c_int, c_p]),
     "ofdmgan_qpsk_modulate": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_qpsk_demodulate": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_ofdm_modulate": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f, c_f, c_p, c_p]),
@@ -86,7 +93,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 2:
+        if L.ofdmgan_abi_version() != 3:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

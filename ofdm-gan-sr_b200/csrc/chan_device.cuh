@@ -22,6 +22,7 @@ struct SimArgs {
     const float* snr_db;
     const float* noise;
     const float* tx;         // injected time-domain frames (device, nullable)
+    const float* fade;       // injected fading draws [B][8] (device, nullable)
     float* clean;            // outputs (device, nullable)
     float* noisy;
     float* snr_out;
@@ -181,7 +182,99 @@ __device__ __forceinline__ void tx_frame(const SimArgs& a, int64_t b, uint64_t f
     }
 }
 
+// fading draws of a frame: Philox block 21 (4 normals), block 22 (4 more, multipath), block 12 word 2 (Rician LOS phase)
+__device__ __forceinline__ void fade_draws(const SimArgs& a, int64_t b, uint64_t frame, float (&f)[8]) {
+    if (a.fade) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = a.fade[b * 8 + j];
+        return;
+    }
+    float n0[4], n1[4];
+    draw_normals(a, frame, 21u, n0);
+    draw_normals(a, frame, 22u, n1);
+    if (a.cfg.channel_type == OFDMGAN_CHAN_RICIAN) {
+        uint32_t x12[4];
+        philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
+        f[0] = 6.283185307179586f * u_half(x12[2]);
+        f[1] = n0[0]; f[2] = n0[1]; f[3] = n0[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[4 + j] = n1[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { f[j] = n0[j]; f[4 + j] = n1[j]; }
+    }
+}
+
+// DC offset, CFO (the tail of apply_all, utils/ofdm_utils.py:524-568) and the fading channels (:710-832), in place
+__device__ __forceinline__ void late_stages(const SimArgs& a, int64_t b, uint64_t frame, float (&nr)[16], float (&ni)[16]) {
+    const ofdmgan_chan_cfg& c = a.cfg;
+    if (c.impair & OFDMGAN_IMPAIR_DC) {
+        float P = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P = fmaf(nr[i], nr[i], fmaf(ni[i], ni[i], P));
+        const float mag = sqrtf(P * 0.0625f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { nr[i] = fmaf(mag, c.dc_i, nr[i]); ni[i] = fmaf(mag, c.dc_q, ni[i]); }
+    }
+    if (c.impair & OFDMGAN_IMPAIR_CFO) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float s, co;
+            sincosf(c.cfo_step * (float)i, &s, &co);
+            const float xr = nr[i], xi = ni[i];
+            nr[i] = xr * co - xi * s;
+            ni[i] = xr * s + xi * co;
+        }
+    }
+    if (c.channel_type == OFDMGAN_CHAN_AWGN) return;
+    float f[8];
+    fade_draws(a, b, frame, f);
+    const float r2 = 0.70710678118654752f;
+    if (c.channel_type == OFDMGAN_CHAN_MULTIPATH) {
+        // np.convolve(x, h, 'same'): y[n] = sum_t h_t x[n + off - d_t], off = (len(h) - 1) / 2 = max_delay / 2
+        int maxd = 0;
+        for (int t = 0; t < c.n_taps; ++t) maxd = c.tap_delay[t] > maxd ? c.tap_delay[t] : maxd;
+        const int off = maxd / 2;
+        float yr[16], yi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { yr[i] = 0.f; yi[i] = 0.f; }
+        for (int t = 0; t < c.n_taps; ++t) {
+            const float hr = c.tap_amp[t] * f[2 * t] * r2, hi = c.tap_amp[t] * f[2 * t + 1] * r2;
+            const int sh = off - c.tap_delay[t];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float xr = 0.f, xi = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j == i + sh) { xr = nr[j]; xi = ni[j]; }
+                yr[i] = fmaf(hr, xr, fmaf(-hi, xi, yr[i]));
+                yi[i] = fmaf(hr, xi, fmaf(hi, xr, yi[i]));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { nr[i] = yr[i]; ni[i] = yi[i]; }
+        return;
+    }
+    float hr, hi;
+    if (c.channel_type == OFDMGAN_CHAN_RAYLEIGH) {
+        hr = f[0] * r2; hi = f[1] * r2;
+    } else {                                                     // Rician: sqrt(K/(K+1)) e^{j theta} + sqrt(1/(K+1)) CN(0,1)
+        const float los = sqrtf(c.rician_k / (c.rician_k + 1.0f)), nl = sqrtf(1.0f / (c.rician_k + 1.0f)) * r2;
+        float s, co;
+        sincosf(f[0], &s, &co);
+        hr = fmaf(nl, f[1], los * co);
+        hi = fmaf(nl, f[2], los * s);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float xr = nr[i], xi = ni[i];
+        nr[i] = hr * xr - hi * xi;
+        ni[i] = hr * xi + hi * xr;
+    }
+}
+
 // impairments + AWGN on a copy of the clean frame -> nr/ni
+// LATE (compile time): also the DC-offset / CFO stages and the fading channels - kept out of the headline instantiations
+template <bool LATE>
 __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint64_t frame, float snr_db,
                                                const float (&cr)[16], const float (&ci)[16], float (&nr)[16],
                                                float (&ni)[16]) {
@@ -197,6 +290,19 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
             const float yp = p == 3.0f ? t * t * t : fast_ex2(p * fast_lg2(t));     // (|x|/A)^(2p)
             const float gain = fast_ex2(ninv2p * fast_lg2(1.0f + yp));            // (1+.)^(-1/2p); phase preserved
             nr[i] *= gain; ni[i] *= gain;
+        }
+    }
+    if (LATE && (c.impair & OFDMGAN_IMPAIR_SALEH)) {             // AM/AM + AM/PM: x * alpha_a/(1+beta_a r^2) * e^{j alpha_p r^2/(1+beta_p r^2)}
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float r2 = nr[i] * nr[i] + ni[i] * ni[i];
+            const float gain = c.saleh_alpha_a / (1.0f + c.saleh_beta_a * r2);
+            const float phi = c.saleh_alpha_p * r2 / (1.0f + c.saleh_beta_p * r2);
+            float s, co;
+            __sincosf(phi, &s, &co);
+            const float xr = nr[i] * gain, xi = ni[i] * gain;
+            nr[i] = xr * co - xi * s;
+            ni[i] = xr * s + xi * co;
         }
     }
     if (c.impair & OFDMGAN_IMPAIR_IQ) {
@@ -226,6 +332,7 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
             }
         }
     }
+    if (LATE) late_stages(a, b, frame, nr, ni);
     if (c.snr_mode == OFDMGAN_SNR_NONE) return;
     float P = 0.f;
 #pragma unroll

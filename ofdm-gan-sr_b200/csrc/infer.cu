@@ -158,6 +158,14 @@ __global__ void k_chan_draws(const __grid_constant__ SimArgs a, float* sym, uint
     }
 }
 
+__global__ void k_fade_draws(const __grid_constant__ SimArgs a, float* fade) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    float f[8];
+    fade_draws(a, b, a.frame0 + (uint64_t)b, f);
+    for (int j = 0; j < 8; ++j) fade[b * 8 + j] = f[j];
+}
+
 __global__ void k_philox_blocks(PhiloxKeys keys, uint64_t ctr0, uint32_t c2, uint32_t c3, uint32_t* out, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -187,6 +195,14 @@ static int check_cfg(const ofdmgan_chan_cfg* c, int* n_snr) {
     if (!c) return OFDMGAN_E_ARG;
     if (c->normalize < 0 || c->normalize > 2 || c->ifft_scale < 0 || c->ifft_scale > 1 || c->pilot_spacing < 0) return OFDMGAN_E_ARG;
     if ((c->impair & OFDMGAN_IMPAIR_PA) && !(c->pa_saturation > 0.f && c->pa_smoothness > 0.f)) return OFDMGAN_E_ARG;
+    if (c->impair & ~63) return OFDMGAN_E_ARG;
+    if (c->channel_type < OFDMGAN_CHAN_AWGN || c->channel_type > OFDMGAN_CHAN_MULTIPATH) return OFDMGAN_E_ARG;
+    if (c->channel_type == OFDMGAN_CHAN_RICIAN && !(c->rician_k >= 0.f)) return OFDMGAN_E_ARG;
+    if (c->channel_type == OFDMGAN_CHAN_MULTIPATH) {
+        if (c->n_taps < 1 || c->n_taps > OFDMGAN_MAX_TAPS) return OFDMGAN_E_ARG;
+        for (int t = 0; t < c->n_taps; ++t)
+            if (c->tap_delay[t] < 0 || c->tap_delay[t] > 15) return OFDMGAN_E_ARG;
+    }
     if (c->snr_mode == OFDMGAN_SNR_GRID) {
         if (c->n_snr < 1 || c->n_snr > OFDMGAN_MAX_SNR_BINS || c->frames_per_snr < 1) return OFDMGAN_E_ARG;
         *n_snr = c->n_snr;
@@ -279,6 +295,19 @@ int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t
     a.frame0 = frame0;
     a.B = B;
     k_chan_draws<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, sym_dev, bits_dev, pn_dev, snr_db_dev, noise_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_chan_fade_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t frame0, float* fade_dev, int64_t B, void* stream) {
+    if (!cfg_host || B < 0) return OFDMGAN_E_ARG;
+    if (B == 0) return 0;
+    if (!fade_dev) return OFDMGAN_E_ARG;
+    SimArgs a{};
+    a.cfg = *cfg_host;
+    a.keys = philox_keys(seed);
+    a.frame0 = frame0;
+    a.B = B;
+    k_fade_draws<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, fade_dev);
     return (int)cudaGetLastError();
 }
 

@@ -24,6 +24,41 @@ __global__ void k_qpsk_demod(const float2* __restrict__ sym, uint8_t* __restrict
     }
 }
 
+// QAM16 / QAM64 (utils/ofdm_utils.py:137-161): levels = -sqrtM+1, -sqrtM+3, ..., sqrtM-1; I, Q = meshgrid(levels, levels);
+// constellation = (I + jQ).flatten() / norm  =>  point[idx] = (levels[idx % sqrtM] + j levels[idx / sqrtM]) / norm.
+template <int BPS>
+__global__ void k_qam_mod(const uint8_t* __restrict__ bits, float2* __restrict__ sym, int64_t n) {
+    constexpr int SQ = 1 << (BPS / 2);
+    constexpr float INV_NORM = BPS == 4 ? 0.31622776601683794f : 0.1543033499620919f;     // 1/sqrt(10), 1/sqrt(42)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int idx = 0;
+#pragma unroll
+        for (int b = 0; b < BPS; ++b) idx = (idx << 1) | (bits[i * BPS + b] & 1);
+        sym[i] = make_float2((float)(2 * (idx % SQ) - SQ + 1) * INV_NORM, (float)(2 * (idx / SQ) - SQ + 1) * INV_NORM);
+    }
+}
+
+// nearest level per axis; a tie between two levels goes to the lower one (np.argmin returns the first minimum, and a lower
+// level index on either axis is a lower constellation index)
+template <int BPS>
+__global__ void k_qam_demod(const float2* __restrict__ sym, uint8_t* __restrict__ bits, int64_t n) {
+    constexpr int SQ = 1 << (BPS / 2);
+    constexpr float NORM = BPS == 4 ? 3.1622776601683795f : 6.48074069840786f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 s = sym[i];
+        int axis[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const float t = ((a ? s.y : s.x) * NORM + (float)(SQ - 1)) * 0.5f;       // position in level-index units
+            int k = (int)ceilf(t - 0.5f);                                            // round half DOWN: ties to the lower level
+            axis[a] = k < 0 ? 0 : (k > SQ - 1 ? SQ - 1 : k);
+        }
+        const int idx = axis[1] * SQ + axis[0];
+#pragma unroll
+        for (int b = 0; b < BPS; ++b) bits[i * BPS + b] = (idx >> (BPS - 1 - b)) & 1;
+    }
+}
+
 __device__ __forceinline__ bool is_pilot(int k, int spacing) { return spacing > 0 && (k % spacing) == 0; }
 
 // :281-329.  One OFDM symbol per thread.
@@ -101,6 +136,28 @@ int ofdmgan_qpsk_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_s
     if (n_symbols == 0) return 0;
     if (!bits_dev || !sym_dev || (reinterpret_cast<uintptr_t>(bits_dev) & 1u) || (reinterpret_cast<uintptr_t>(sym_dev) & 7u)) return OFDMGAN_E_ARG;
     k_qpsk_demod<<<grid_for(n_symbols, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(sym_dev), bits_dev, n_symbols);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_qam_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, int bits_per_symbol, void* stream) {
+    if (bits_per_symbol == 2) return ofdmgan_qpsk_modulate(bits_dev, sym_dev, n_symbols, stream);
+    if (n_symbols < 0 || (bits_per_symbol != 4 && bits_per_symbol != 6)) return OFDMGAN_E_ARG;
+    if (n_symbols == 0) return 0;
+    if (!bits_dev || !sym_dev || (reinterpret_cast<uintptr_t>(sym_dev) & 7u)) return OFDMGAN_E_ARG;
+    const int grid = grid_for(n_symbols, 256, 8);
+    if (bits_per_symbol == 4) k_qam_mod<4><<<grid, 256, 0, (cudaStream_t)stream>>>(bits_dev, reinterpret_cast<float2*>(sym_dev), n_symbols);
+    else k_qam_mod<6><<<grid, 256, 0, (cudaStream_t)stream>>>(bits_dev, reinterpret_cast<float2*>(sym_dev), n_symbols);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_qam_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_symbols, int bits_per_symbol, void* stream) {
+    if (bits_per_symbol == 2) return ofdmgan_qpsk_demodulate(sym_dev, bits_dev, n_symbols, stream);
+    if (n_symbols < 0 || (bits_per_symbol != 4 && bits_per_symbol != 6)) return OFDMGAN_E_ARG;
+    if (n_symbols == 0) return 0;
+    if (!bits_dev || !sym_dev || (reinterpret_cast<uintptr_t>(sym_dev) & 7u)) return OFDMGAN_E_ARG;
+    const int grid = grid_for(n_symbols, 256, 8);
+    if (bits_per_symbol == 4) k_qam_demod<4><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(sym_dev), bits_dev, n_symbols);
+    else k_qam_demod<6><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(sym_dev), bits_dev, n_symbols);
     return (int)cudaGetLastError();
 }
 

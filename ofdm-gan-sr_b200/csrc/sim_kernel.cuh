@@ -118,7 +118,8 @@ __device__ __forceinline__ void cta_lockstep(int level) {
 }
 
 // EQ: also fill the ZF / MMSE rows (genie-aided equalisers, equalizer_device.cuh)
-template <int SRC, int GEN, bool EQ>
+// LATE: Saleh PA / DC offset / CFO stages and the fading channels compiled in (chan_device.cuh late_stages)
+template <int SRC, int GEN, bool EQ, bool LATE>
 __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ SimArgs a) {
     constexpr bool BITS = SRC != SRC_GAUSS;
     constexpr int NMETH = EQ ? 4 : 2;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(ST, SIM_PER_SM) k_sim(const __grid_constant__ 
         float cr[16], ci[16], nr[16], ni[16];
         tx_frame<SRC>(a, bb, frame, bits, cr, ci);
         cta_lockstep(2);
-        impair_channel(a, bb, frame, snr_db, cr, ci, nr, ni);
+        impair_channel<LATE>(a, bb, frame, snr_db, cr, ci, nr, ni);
         normalise(a.cfg.normalize, cr, ci, nr, ni);
         cta_lockstep(1);
 
@@ -293,7 +294,7 @@ static __global__ void k_reduce_partials(const double* __restrict__ partials, in
     metrics[i] += (s0 + s1) + (s2 + s3);
 }
 
-template <int SRC, int GEN, bool EQ>
+template <int SRC, int GEN, bool EQ, bool LATE>
 static int sim_launch_one(const SimCall& c) {
     cudaStream_t s = c.stream;
     int slot = 0, rc;
@@ -305,7 +306,7 @@ static int sim_launch_one(const SimCall& c) {
     if (rc) return rc;
     const int grid = grid_for(c.B, ST, SIM_PER_SM);
     // opt in to > 48 KB of dynamic shared memory (per device; a host-side table write, no launch)
-    OG_CHECK(cudaFuncSetAttribute(k_sim<SRC, GEN, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM));
+    OG_CHECK(cudaFuncSetAttribute(k_sim<SRC, GEN, EQ, LATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM));
     const int n = c.n_snr * NM * NC;
     void* partials = nullptr;
     if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
@@ -314,13 +315,13 @@ static int sim_launch_one(const SimCall& c) {
     a.keys = philox_keys(c.seed);
     a.frame0 = c.frame0;
     a.B = c.B;
-    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; a.tx = c.rand->tx; }
+    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; a.tx = c.rand->tx; a.fade = c.rand->fade; }
     a.clean = c.clean; a.noisy = c.noisy; a.snr_out = c.snr;
     a.wslot = slot;
     a.slope = c.slope;
     a.partials = (double*)partials;
     a.n_snr = c.n_snr;
-    k_sim<SRC, GEN, EQ><<<grid, ST, SIM_SMEM, s>>>(a);
+    k_sim<SRC, GEN, EQ, LATE><<<grid, ST, SIM_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
     if (partials) {
         k_reduce_partials<<<(n + 63) / 64, 64, 0, s>>>((const double*)partials, grid, n, c.metrics);
@@ -332,12 +333,17 @@ static int sim_launch_one(const SimCall& c) {
 template <int SRC>
 static int sim_launch_src(const SimCall& c) {
     const bool eq = c.cfg->equalizers != 0;
+    // the rarely used stages live in their own instantiations so the headline kernels do not carry them
+    const bool late = c.cfg->channel_type != OFDMGAN_CHAN_AWGN ||
+                      (c.cfg->impair & (OFDMGAN_IMPAIR_SALEH | OFDMGAN_IMPAIR_DC | OFDMGAN_IMPAIR_CFO)) != 0;
     switch (c.gen_kind) {
-        case -1: return sim_launch_one<SRC, -1, false>(c);
-        case OFDMGAN_GEN_F32: return eq ? sim_launch_one<SRC, OFDMGAN_GEN_F32, true>(c) : sim_launch_one<SRC, OFDMGAN_GEN_F32, false>(c);
-        // the equaliser rows are built with the fp32 generator only (the comparison benchmark_comparison.py makes)
-        case OFDMGAN_GEN_Q_SPEC: return eq ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC, false>(c);
-        case OFDMGAN_GEN_Q_RTL: return eq ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL, false>(c);
+        case -1: return late ? sim_launch_one<SRC, -1, false, true>(c) : sim_launch_one<SRC, -1, false, false>(c);
+        case OFDMGAN_GEN_F32:
+            if (late) return eq ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_F32, false, true>(c);
+            return eq ? sim_launch_one<SRC, OFDMGAN_GEN_F32, true, false>(c) : sim_launch_one<SRC, OFDMGAN_GEN_F32, false, false>(c);
+        // the equaliser rows / late stages are built with the fp32 generator only
+        case OFDMGAN_GEN_Q_SPEC: return (eq || late) ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC, false, false>(c);
+        case OFDMGAN_GEN_Q_RTL: return (eq || late) ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL, false, false>(c);
         default: return OFDMGAN_E_ARG;
     }
 }

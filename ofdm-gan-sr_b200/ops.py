@@ -12,7 +12,9 @@ from ._lib import (CRITIC_OUT, D_NPARAMS, G_NPARAMS, GEN_F32, GEN_OUT, GEN_Q_RTL
 
 SYM_GAUSSIAN, SYM_QPSK = 0, 1
 SCALE_SQRT_N, SCALE_N = 0, 1
-IMPAIR_PA, IMPAIR_IQ, IMPAIR_PN = 1, 2, 4
+IMPAIR_PA, IMPAIR_IQ, IMPAIR_PN, IMPAIR_SALEH, IMPAIR_DC, IMPAIR_CFO = 1, 2, 4, 8, 16, 32
+CHAN_AWGN, CHAN_RAYLEIGH, CHAN_RICIAN, CHAN_MULTIPATH = 0, 1, 2, 3
+CHANNEL_TYPES = {"awgn": 0, "rayleigh": 1, "rician": 2, "multipath": 3}
 SNR_UNIFORM, SNR_GRID, SNR_NONE = 0, 1, 2
 NORM_NONE, NORM_JOINT, NORM_SEPARATE = 0, 1, 2
 
@@ -20,7 +22,8 @@ NORM_NONE, NORM_JOINT, NORM_SEPARATE = 0, 1, 2
 def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j, ifft_scale=SCALE_SQRT_N,
              nonlinear=False, pa=None, iq=None, pn=None, pa_saturation=1.0, pa_smoothness=3.0, iq_imbalance_db=1.0,
              iq_phase_deg=5.0, phase_noise_dbchz=-80.0, sample_rate=1e6, snr_mode=SNR_UNIFORM, snr_lo=0.0, snr_hi=30.0,
-             snr_step=5.0, n_snr=1, frames_per_snr=1, normalize=NORM_JOINT, equalizers=False):
+             snr_step=5.0, n_snr=1, frames_per_snr=1, normalize=NORM_JOINT, equalizers=False, channel_type=CHAN_AWGN,
+             rician_k=3.0, delays=(0, 1, 2), powers=(1.0, 0.5, 0.25), saleh=None, dc_offset=None, cfo_hz=None):
     """ChanCfg from the reference's user-facing parameters: SyntheticOFDMDataset.__init__ (utils/dataset.py:195-206),
     NonLinearImpairments defaults (utils/ofdm_utils.py:394-521), run_benchmark's SNR grid
     (benchmark_comparison.py:179-182)."""
@@ -40,6 +43,24 @@ def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pi
     c.snr_mode, c.snr_lo, c.snr_hi, c.snr_step = snr_mode, snr_lo, snr_hi, snr_step
     c.n_snr, c.frames_per_snr, c.normalize = n_snr, frames_per_snr, normalize
     c.equalizers = 1 if equalizers else 0        # also fill the ZF / MMSE rows of the fused sweep
+    # fading channels (ChannelModel, utils/ofdm_utils.py:710-832) and the remaining impairments (:424-455, :524-568)
+    c.channel_type = CHANNEL_TYPES[channel_type] if isinstance(channel_type, str) else int(channel_type)
+    c.rician_k = float(rician_k)
+    if len(delays) != len(powers) or len(delays) > 4:
+        raise OfdmGanError("multipath: up to 4 taps, one power per delay")
+    c.n_taps = len(delays)
+    tot = float(sum(powers))
+    for t, (d, p) in enumerate(zip(delays, powers)):
+        c.tap_delay[t], c.tap_amp[t] = int(d), math.sqrt(p / tot)
+    if saleh is not None:                          # (alpha_a, beta_a, alpha_p, beta_p)
+        c.impair |= IMPAIR_SALEH
+        c.saleh_alpha_a, c.saleh_beta_a, c.saleh_alpha_p, c.saleh_beta_p = (float(v) for v in saleh)
+    if dc_offset is not None:                      # (dc_i, dc_q) relative to sqrt(mean |x|^2)
+        c.impair |= IMPAIR_DC
+        c.dc_i, c.dc_q = float(dc_offset[0]), float(dc_offset[1])
+    if cfo_hz is not None:
+        c.impair |= IMPAIR_CFO
+        c.cfo_step = 2.0 * math.pi * float(cfo_hz) / float(sample_rate)
     return c
 
 
@@ -131,7 +152,7 @@ def _dev(device):
     return device
 
 
-def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None, snr_db=None, noise=None, tx=None,
+def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None, snr_db=None, noise=None, tx=None, fade=None,
              want_clean=True, want_noisy=True, want_snr=True):
     """frames frame0..frame0+B-1 of SyntheticOFDMDataset / run_benchmark -> (clean, noisy, snr) CUDA tensors.
     Any of the draw tensors may be injected (host-generated randomness in the reference's draw order)."""
@@ -142,7 +163,7 @@ def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None
         snr = torch.empty(B, dtype=torch.float32, device=device) if want_snr else None
         rand = None
         keep = []
-        if any(a is not None for a in (sym, bits, pn, snr_db, noise, tx)):
+        if any(a is not None for a in (sym, bits, pn, snr_db, noise, tx, fade)):
             def f32(a, shape):
                 if a is None:
                     return None
@@ -155,6 +176,7 @@ def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None
             rand.snr_db = f32(snr_db, (B,))
             rand.noise = f32(noise, (B, 32))
             rand.tx = f32(tx, (B, 32))
+            rand.fade = f32(fade, (B, 8))
             if bits is not None:
                 tb = torch.as_tensor(np.ascontiguousarray(bits, dtype=np.uint32).view(np.int32)).to(device).contiguous()
                 keep.append(tb)
@@ -177,6 +199,15 @@ def chan_draws(cfg, B, seed=0, frame0=0, device=None):
         check(_lib.lib().ofdmgan_chan_draws(ctypes.byref(cfg), seed, frame0, dptr(sym), dptr(bits), dptr(pn), dptr(snr),
                                             dptr(noise), B, stream_ptr(device)))
     return dict(sym=sym, bits=bits, pn=pn, snr_db=snr, noise=noise)
+
+
+def chan_fade_draws(cfg, B, seed=0, frame0=0, device=None):
+    """[B,8] fading draws of frames frame0.. in the ofdmgan_chan_rand.fade layout."""
+    device = _dev(device)
+    with torch.cuda.device(device):
+        fade = torch.empty(B, 8, dtype=torch.float32, device=device)
+        check(_lib.lib().ofdmgan_chan_fade_draws(ctypes.byref(cfg), seed, frame0, dptr(fade), B, stream_ptr(device)))
+    return fade
 
 
 def philox_blocks(seed, ctr0, c2, c3, n, device=None):
@@ -274,6 +305,24 @@ def _c64(t, device=None):
     if device is None and not t.is_cuda:
         raise OfdmGanError("expected a CUDA tensor: libofdmgan has no CPU path")
     return t.to(device=device if device is not None else t.device, dtype=torch.complex64).contiguous()
+
+
+def qam_modulate(bits, bits_per_symbol):
+    """bits: uint8 CUDA tensor of 0/1 (MSB first) -> complex64 symbols; bits_per_symbol 2 (QPSK), 4 (QAM16) or 6 (QAM64)."""
+    if not bits.is_cuda:
+        raise OfdmGanError("expected a CUDA tensor: libofdmgan has no CPU path")
+    bits = bits.to(torch.uint8).contiguous().view(-1)
+    n = bits.numel() // bits_per_symbol
+    sym = torch.empty(n, dtype=torch.complex64, device=bits.device)
+    check(_lib.lib().ofdmgan_qam_modulate(dptr(bits), ctypes.c_void_p(sym.data_ptr()), n, bits_per_symbol, stream_ptr(bits.device)))
+    return sym
+
+
+def qam_demodulate(symbols, bits_per_symbol):
+    sym = _c64(symbols).view(-1)
+    bits = torch.empty(bits_per_symbol * sym.numel(), dtype=torch.uint8, device=sym.device)
+    check(_lib.lib().ofdmgan_qam_demodulate(ctypes.c_void_p(sym.data_ptr()), dptr(bits), sym.numel(), bits_per_symbol, stream_ptr(sym.device)))
+    return bits
 
 
 def qpsk_modulate(bits):

@@ -24,9 +24,8 @@ class SyntheticOFDMDataset(torch.utils.data.Dataset):
                  iq_phase_deg: float = 5.0, phase_noise_dbchz: float = -80, seed: int = 0, device=None, symbol_source: str = "gaussian"):
         if frame_length != 16:
             raise OfdmGanError("libofdmgan builds 16-sample frames only (the MiniGenerator / RTL frame length)")
-        if channel_type != "awgn":
-            raise OfdmGanError(f"channel_type '{channel_type}' is not built: the reference's training and benchmark paths use "
-                               "'awgn' (train.py:636, benchmark_comparison.py:52); see DESIGN.md 'next'")
+        if channel_type.lower() not in ops.CHANNEL_TYPES:
+            raise ValueError(f"Unknown channel type: {channel_type}")
         self.n_samples, self.frame_length, self.snr_range = n_samples, frame_length, tuple(snr_range)
         self.nonlinear, self.pa_saturation = nonlinear, pa_saturation
         self.iq_imbalance_db, self.iq_phase_deg, self.phase_noise_dbchz = iq_imbalance_db, iq_phase_deg, phase_noise_dbchz
@@ -34,7 +33,8 @@ class SyntheticOFDMDataset(torch.utils.data.Dataset):
         src = dict(gaussian=dict(), qpsk=dict(symbol_source=ops.SYM_QPSK, n_fft=16, cp_len=0, ifft_scale=ops.SCALE_SQRT_N))[symbol_source]
         self.cfg = ops.make_cfg(nonlinear=nonlinear, pa_saturation=pa_saturation, iq_imbalance_db=iq_imbalance_db,
                                 iq_phase_deg=iq_phase_deg, phase_noise_dbchz=phase_noise_dbchz, snr_mode=ops.SNR_UNIFORM,
-                                snr_lo=float(snr_range[0]), snr_hi=float(snr_range[1]), normalize=ops.NORM_JOINT, **src)
+                                snr_lo=float(snr_range[0]), snr_hi=float(snr_range[1]), normalize=ops.NORM_JOINT,
+                                channel_type=channel_type.lower(), **src)
 
     def __len__(self) -> int:
         return self.n_samples

@@ -12,6 +12,7 @@ Randomness comes from Philox4x32-10(seed, frame index): pass `seed=` / `frame0=`
 counter otherwise advances so that successive calls see fresh noise, like successive np.random calls.
 """
 import itertools
+import math
 from typing import Any, Dict, Tuple
 
 import numpy as np
@@ -37,7 +38,7 @@ def _back(t, was_numpy, np_dtype):
 
 
 class QAMModulator:
-    """utils/ofdm_utils.py:90-222.  'QPSK' (the scheme of config/config.yaml:14) is built; QAM16 / QAM64 raise."""
+    """utils/ofdm_utils.py:90-222: QPSK (the scheme of config/config.yaml:14), QAM16, QAM64."""
 
     CONSTELLATIONS = {"QPSK": {"bits_per_symbol": 2}, "QAM16": {"bits_per_symbol": 4}, "QAM64": {"bits_per_symbol": 6}}
 
@@ -46,24 +47,24 @@ class QAMModulator:
         if self.modulation not in self.CONSTELLATIONS:
             raise ValueError(f"Unsupported modulation: {modulation}")
         self.bits_per_symbol = self.CONSTELLATIONS[self.modulation]["bits_per_symbol"]
-        self.constellation = np.array([1 + 1j, 1 - 1j, -1 + 1j, -1 - 1j]) / np.sqrt(2) if self.modulation == "QPSK" else None
-
-    def _check(self):
-        if self.modulation != "QPSK":
-            raise OfdmGanError(f"{self.modulation} is not built (DESIGN.md 'next'); QPSK is")
+        if self.modulation == "QPSK":
+            self.constellation = np.array([1 + 1j, 1 - 1j, -1 + 1j, -1 - 1j]) / np.sqrt(2)
+        else:                                                    # utils/ofdm_utils.py:150-161
+            sq = int(np.sqrt(2 ** self.bits_per_symbol))
+            I, Q = np.meshgrid(np.arange(-sq + 1, sq, 2), np.arange(-sq + 1, sq, 2))
+            self.constellation = (I + 1j * Q).flatten() / np.sqrt({4: 10, 6: 42}[self.bits_per_symbol])
 
     def modulate(self, bits):
-        """bits (0/1, MSB first; a trailing odd bit is dropped) -> complex symbols."""
-        self._check()
+        """bits (0/1, MSB first; trailing bits that do not fill a symbol are dropped) -> complex symbols."""
         b, was_np = _to_dev(bits, torch.uint8)
         b = b.reshape(-1)
-        return _back(ops.qpsk_modulate(b[:(b.numel() // 2) * 2]), was_np, np.complex128)
+        n = b.numel() // self.bits_per_symbol
+        return _back(ops.qam_modulate(b[:n * self.bits_per_symbol], self.bits_per_symbol), was_np, np.complex128)
 
     def demodulate(self, symbols):
         """hard decisions: nearest constellation point, ties to the lowest index -> bits (flattened, MSB first)."""
-        self._check()
         s, was_np = _to_dev(symbols, torch.complex64)
-        return _back(ops.qpsk_demodulate(s), was_np, np.int64)
+        return _back(ops.qam_demodulate(s, self.bits_per_symbol), was_np, np.int64)
 
 
 class OFDMModulator:
@@ -117,14 +118,31 @@ def _run(tx, seed, frame0, **cfg_kw):
 
 
 class NonLinearImpairments:
-    """utils/ofdm_utils.py:378-605: Rapp PA, IQ imbalance, Wiener phase noise and their chain (apply_all with the DC-offset and
-    CFO stages disabled, which is how every caller in the reference uses it: dataset.py:262-263, benchmark_comparison.py:104-106)."""
+    """utils/ofdm_utils.py:378-605: Rapp and Saleh PA, IQ imbalance, Wiener phase noise, DC offset, CFO and the apply_all chain."""
 
     @staticmethod
     def apply_pa_rapp(signal, saturation_level: float = 1.0, smoothness: float = 3.0):
         tx, restore = _frames_of(signal, True)
         return restore(_run(tx, 0, 0, pa=True, iq=False, pn=False, pa_saturation=saturation_level, pa_smoothness=smoothness,
                             snr_mode=ops.SNR_NONE))
+
+    @staticmethod
+    def apply_pa_saleh(signal, alpha_a: float = 2.1587, beta_a: float = 1.1517, alpha_p: float = 4.0033, beta_p: float = 9.1040):
+        """Saleh AM/AM + AM/PM model (utils/ofdm_utils.py:424-455)."""
+        tx, restore = _frames_of(signal, True)
+        return restore(_run(tx, 0, 0, pa=False, iq=False, pn=False, saleh=(alpha_a, beta_a, alpha_p, beta_p), snr_mode=ops.SNR_NONE))
+
+    @staticmethod
+    def apply_dc_offset(signal, dc_offset_i: float = 0.01, dc_offset_q: float = 0.01):
+        """DC offset relative to the frame's RMS amplitude (utils/ofdm_utils.py:524-543)."""
+        tx, restore = _frames_of(signal, False)
+        return restore(_run(tx, 0, 0, pa=False, iq=False, pn=False, dc_offset=(dc_offset_i, dc_offset_q), snr_mode=ops.SNR_NONE))
+
+    @staticmethod
+    def apply_cfo(signal, cfo_hz: float = 100, sample_rate: float = 1e6):
+        """Carrier frequency offset: sample n rotated by 2 pi cfo n / fs (utils/ofdm_utils.py:546-568)."""
+        tx, restore = _frames_of(signal, False)
+        return restore(_run(tx, 0, 0, pa=False, iq=False, pn=False, cfo_hz=cfo_hz, sample_rate=sample_rate, snr_mode=ops.SNR_NONE))
 
     @staticmethod
     def apply_iq_imbalance(signal, amplitude_imbalance_db: float = 1.0, phase_imbalance_deg: float = 5.0):
@@ -142,29 +160,58 @@ class NonLinearImpairments:
     def apply_all(signal, pa_enabled: bool = True, pa_saturation: float = 1.0, iq_imbalance_enabled: bool = True, iq_amplitude_db: float = 1.0,
                   iq_phase_deg: float = 5.0, phase_noise_enabled: bool = True, phase_noise_dbchz: float = -80, dc_offset_enabled: bool = False,
                   cfo_enabled: bool = False, seed: int = 0, frame0=None):
-        if dc_offset_enabled or cfo_enabled:
-            raise OfdmGanError("DC offset / CFO stages are not built (disabled by every caller in the reference); DESIGN.md 'next'")
-        tx, restore = _frames_of(signal, not phase_noise_enabled)
+        tx, restore = _frames_of(signal, not (phase_noise_enabled or dc_offset_enabled or cfo_enabled))
         return restore(_run(tx, seed, frame0, pa=pa_enabled, iq=iq_imbalance_enabled, pn=phase_noise_enabled, pa_saturation=pa_saturation,
                             iq_imbalance_db=iq_amplitude_db, iq_phase_deg=iq_phase_deg, phase_noise_dbchz=phase_noise_dbchz,
+                            dc_offset=(0.01, 0.01) if dc_offset_enabled else None, cfo_hz=100 if cfo_enabled else None,
                             snr_mode=ops.SNR_NONE))
 
 
 class ChannelModel:
-    """utils/ofdm_utils.py:612-832.  'awgn' (per-frame measured signal power, :675-708) is built; the fading models raise."""
+    """utils/ofdm_utils.py:612-832: 'awgn' (per-frame measured signal power), 'rayleigh', 'rician' (k_factor=), 'multipath'
+    (delays=, powers=; np.convolve(x, h, 'same') with independent Rayleigh taps).  The fading coefficient(s) are per frame."""
 
     def __init__(self, channel_type: str = "awgn"):
         self.channel_type = channel_type.lower()
 
     def apply(self, signal, snr_db: float, seed: int = 0, frame0=None, **kwargs) -> Tuple[Any, Dict[str, Any]]:
-        if self.channel_type not in ("awgn", "rayleigh", "rician", "multipath"):
+        if self.channel_type not in ops.CHANNEL_TYPES:
             raise ValueError(f"Unknown channel type: {self.channel_type}")
-        if self.channel_type != "awgn":
-            raise OfdmGanError(f"channel '{self.channel_type}' is not built (DESIGN.md 'next'); 'awgn' is")
         tx, restore = _frames_of(signal, False)
-        noisy = _run(tx, seed, frame0, pa=False, iq=False, pn=False, snr_mode=ops.SNR_GRID, snr_lo=float(snr_db), snr_step=0.0, n_snr=1)
-        power = (tx * tx).sum(dim=1) / 16.0                       # mean |x|^2 per frame
-        noise_power = power / (10.0 ** (float(snr_db) / 10.0))
-        info = {"type": "awgn", "snr_db": snr_db, "noise_power": noise_power if noise_power.numel() > 1 else float(noise_power),
-                "channel_response": np.array([1.0])}
+        if frame0 is None:
+            frame0 = next(_frame_counter) * (1 << 32)
+        k = float(kwargs.get("k_factor", 3.0))
+        delays, powers = list(kwargs.get("delays", [0, 1, 2])), list(kwargs.get("powers", [1.0, 0.5, 0.25]))
+        cfg = ops.make_cfg(normalize=ops.NORM_NONE, pa=False, iq=False, pn=False, snr_mode=ops.SNR_GRID, snr_lo=float(snr_db), snr_step=0.0,
+                           n_snr=1, channel_type=self.channel_type, rician_k=k, delays=delays, powers=powers)
+        B = tx.shape[0]
+        _, noisy, _ = ops.chan_sim(cfg, B, seed=seed, frame0=frame0, device=tx.device, tx=tx, want_clean=False, want_snr=False)
+        info: Dict[str, Any] = {"type": self.channel_type, "snr_db": snr_db}
+        x = torch.complex(tx[:, :16], tx[:, 16:])
+        if self.channel_type == "awgn":
+            faded, info["channel_response"] = x, np.array([1.0])
+        else:
+            f = ops.chan_fade_draws(cfg, B, seed=seed, frame0=frame0, device=tx.device)
+            if self.channel_type == "rayleigh":
+                h = torch.complex(f[:, 0], f[:, 1]) / math.sqrt(2.0)
+            elif self.channel_type == "rician":
+                h = math.sqrt(k / (k + 1)) * torch.polar(torch.ones_like(f[:, 0]), f[:, 0]) + \
+                    math.sqrt(1 / (k + 1)) * torch.complex(f[:, 1], f[:, 2]) / math.sqrt(2.0)
+                info["k_factor"] = k
+            else:
+                pw = np.asarray(powers, dtype=np.float64) / np.sum(powers)
+                h = torch.zeros(B, max(delays) + 1, dtype=torch.complex64, device=tx.device)
+                for t, (d, p) in enumerate(zip(delays, pw)):
+                    h[:, d] = math.sqrt(p) * torch.complex(f[:, 2 * t], f[:, 2 * t + 1]) / math.sqrt(2.0)
+                info["delays"], info["powers"] = delays, pw.tolist()
+            if self.channel_type != "multipath":
+                faded = h[:, None] * x
+                info["channel_magnitude"] = h.abs() if B > 1 else float(h.abs()[0])
+            else:
+                faded = None
+            info["channel_response"] = h if B > 1 else h[0]
+        if faded is not None:
+            power = (faded.real ** 2 + faded.imag ** 2).mean(dim=1)
+            noise_power = power / (10.0 ** (float(snr_db) / 10.0))
+            info["noise_power"] = noise_power if B > 1 else float(noise_power[0])
         return restore(noisy), info

@@ -39,6 +39,10 @@ class ChanCfg(ctypes.Structure):
         ("snr_lo", ctypes.c_float), ("snr_hi", ctypes.c_float), ("snr_step", ctypes.c_float),
         ("n_snr", ctypes.c_int32), ("frames_per_snr", ctypes.c_int64), ("normalize", ctypes.c_int32),
         ("equalizers", ctypes.c_int32),
+        ("channel_type", ctypes.c_int32), ("rician_k", ctypes.c_float), ("n_taps", ctypes.c_int32),
+        ("tap_delay", ctypes.c_int32 * 4), ("tap_amp", ctypes.c_float * 4),
+        ("saleh_alpha_a", ctypes.c_float), ("saleh_beta_a", ctypes.c_float), ("saleh_alpha_p", ctypes.c_float),
+        ("saleh_beta_p", ctypes.c_float), ("dc_i", ctypes.c_float), ("dc_q", ctypes.c_float), ("cfo_step", ctypes.c_float),
     ]
 
 

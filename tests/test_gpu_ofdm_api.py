@@ -46,8 +46,6 @@ def test_qpsk_modulate_demodulate_bit_exact(api):
     with pytest.raises(ValueError):
         u.QAMModulator("PSK8")
     with pytest.raises(pkg.OfdmGanError):
-        u.QAMModulator("QAM16").modulate(r["bits"])
-    with pytest.raises(pkg.OfdmGanError):
         q.modulate(torch.zeros(8, dtype=torch.uint8))             # CPU tensor: no fallback
 
 
@@ -135,10 +133,6 @@ def test_random_stages_surface_and_statistics(api):
     assert isinstance(one, np.ndarray) and one.shape == (16,) and one.dtype == np.complex128
     with pytest.raises(pkg.OfdmGanError):
         NL.apply_phase_noise(r["x_long"])                          # frame-coupled stage: 16-sample frames only
-    with pytest.raises(pkg.OfdmGanError):
-        NL.apply_all(r["x"], cfo_enabled=True)
-    with pytest.raises(pkg.OfdmGanError):
-        u.ChannelModel("rayleigh").apply(r["x"], 10.0)
     with pytest.raises(ValueError):
         u.ChannelModel("bogus").apply(r["x"], 10.0)
 
@@ -204,3 +198,82 @@ def test_fused_equaliser_rows_vs_oracle_and_pieces(api):
     assert list(res) == ["GAN", "ZF", "MMSE", "NoEQ"] and res["ZF"][10.0]["evm"] < -130 < res["MMSE"][10.0]["evm"] < res["NoEQ"][10.0]["evm"]
     with pytest.raises(pkg.OfdmGanError):
         ops.sim_gen_metrics(ops.make_cfg(**kw), 64, gen_kind=1, wrom=np.zeros(2048, np.int8), brom=np.zeros(64, np.int16))
+
+
+# ------------------------------------------------------------------------------------------------ remaining models
+@pytest.fixture(scope="module")
+def api2(api):
+    return dict(np.load(os.path.join(GOLDEN, "ref_api2.npz")))
+
+
+@pytest.mark.parametrize("tag,name", [("q16", "QAM16"), ("q64", "QAM64")])
+def test_qam16_qam64_match_reference(api, api2, tag, name):
+    pkg, u, _ = api
+    q = u.QAMModulator(name)
+    assert_close(c2(q.constellation), c2(api2[tag + "_const"]), 1e-12, name + " constellation")
+    syms = q.modulate(api2[tag + "_bits"])
+    assert syms.shape == api2[tag + "_syms"].shape
+    assert_close(c2(syms), c2(api2[tag + "_syms"]), 1e-6, name + " symbols")
+    # includes the symmetric tie at 0 and out-of-range points.  Points 5 and 6 of the fixture sit exactly half-way between two
+    # asymmetric levels (2/sqrt(10)): the reference's decision there is whatever float64 rounding of |s-c|^2 happens to give -
+    # not a property to reproduce - so they are left out of the comparison.
+    keep = np.ones(300, bool)
+    keep[5:7] = False
+    got = q.demodulate(api2[tag + "_noisy"]).reshape(300, -1)
+    assert np.array_equal(got[keep], api2[tag + "_demod"].reshape(300, -1)[keep])
+    bits = torch.randint(0, 2, (q.bits_per_symbol * 500_000,), device="cuda", dtype=torch.uint8)
+    assert torch.equal(q.demodulate(q.modulate(bits)), bits)
+
+
+def test_saleh_dc_cfo_match_reference(api, api2):
+    pkg, u, _ = api
+    NL, r = u.NonLinearImpairments, api2
+    assert_close(c2(NL.apply_pa_saleh(r["x"])), c2(r["saleh"]), TOL, "Saleh defaults")
+    assert_close(c2(NL.apply_pa_saleh(r["x"], 1.5, 0.8, 2.0, 5.0)), c2(r["saleh2"]), TOL, "Saleh custom")
+    assert_close(c2(NL.apply_dc_offset(r["x"], 0.01, 0.01)), c2(r["dc"]), TOL, "DC offset")
+    assert_close(c2(NL.apply_dc_offset(r["x"], -0.05, 0.2)), c2(r["dc2"]), TOL, "DC offset custom")
+    assert_close(c2(NL.apply_cfo(r["x"], 100, 1e6)), c2(r["cfo"]), TOL, "CFO 100 Hz")
+    assert_close(c2(NL.apply_cfo(r["x"], 25000, 1e6)), c2(r["cfo2"]), TOL, "CFO 25 kHz")
+    ops = pkg.ops
+    cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, dc_offset=(0.01, 0.01), cfo_hz=100, normalize=0, snr_mode=ops.SNR_NONE)
+    _, y, _ = ops.chan_sim(cfg, 24, tx=tx_of(r["x"]), pn=r["all_dc_d"])
+    got = y.cpu().numpy()
+    assert_close(np.stack([got[:, 0], got[:, 1]]), c2(r["all_dc"]), TOL, "apply_all with DC + CFO")
+
+
+@pytest.mark.parametrize("kind,kw,nf", [("rayleigh", {}, 2), ("rician", dict(k_factor=4.0), 3), ("multipath", {}, 6),
+                                        ("multipath", dict(delays=[0, 3], powers=[2.0, 1.0]), 4)])
+def test_fading_channels_match_reference_with_its_draws(api, api2, kind, kw, nf):
+    pkg, u, _ = api
+    ops, r = pkg.ops, api2
+    tag = {"rayleigh": "ray", "rician": "ric"}.get(kind, "mp2" if kw else "mp")
+    d = r[tag + "_d"]
+    fade = np.zeros((24, 8))
+    fade[:, :nf] = d[:, :nf]
+    cfg = ops.make_cfg(normalize=0, snr_mode=ops.SNR_GRID, snr_lo=15.0, snr_step=0.0, n_snr=1, channel_type=kind,
+                       rician_k=kw.get("k_factor", 3.0), delays=kw.get("delays", (0, 1, 2)), powers=kw.get("powers", (1.0, 0.5, 0.25)))
+    _, y, _ = ops.chan_sim(cfg, 24, tx=tx_of(r["x"]), fade=fade, noise=d[:, nf:])
+    got = y.cpu().numpy()
+    assert_close(np.stack([got[:, 0], got[:, 1]]), c2(r[tag]), TOL, kind)
+
+
+def test_fading_channel_surface_and_statistics(api, api2):
+    pkg, u, _ = api
+    x = torch.as_tensor(api2["x"]).cuda().repeat(4000, 1)
+    y, info = u.ChannelModel("rayleigh").apply(x, 300.0, seed=2, frame0=0)                # 300 dB: fading only
+    h = info["channel_response"]
+    assert h.shape == (96000,) and info["type"] == "rayleigh"
+    assert abs(float((h.abs() ** 2).mean()) - 1.0) < 0.02                               # h ~ CN(0, 1)
+    assert_close(c2((y / x.to(torch.complex64)).cpu().numpy()[:, 0]), c2(h.cpu().numpy()), 1e-4, "y = h x")
+    y, info = u.ChannelModel("rician").apply(x, 300.0, k_factor=10.0, seed=2, frame0=0)
+    assert abs(float((info["channel_response"].abs() ** 2).mean()) - 1.0) < 0.02 and info["k_factor"] == 10.0
+    assert float(info["channel_magnitude"].std()) < 0.35                                  # strong LOS: little spread
+    y, info = u.ChannelModel("multipath").apply(x, 300.0, seed=2, frame0=0)
+    assert info["channel_response"].shape == (96000, 3) and abs(sum(info["powers"]) - 1.0) < 1e-12
+    one, info1 = u.ChannelModel("rayleigh").apply(api2["x"][0], 10.0)
+    assert isinstance(one, np.ndarray) and one.shape == (16,) and isinstance(info1["channel_magnitude"], float)
+    ds = u.SyntheticOFDMDataset(n_samples=256, channel_type="rayleigh", seed=1)
+    b = ds.batch(0, 256)
+    assert b["noisy"].shape == (256, 2, 16) and torch.isfinite(b["noisy"]).all()
+    with pytest.raises(ValueError):
+        u.SyntheticOFDMDataset(channel_type="bogus")
