@@ -2,8 +2,9 @@
 from .ofdm_utils import ChannelModel, NonLinearImpairments, OFDMModulator, QAMModulator
 from .classical_equalizers import MMSEEqualizer, ZeroForcingEqualizer
 from .dataset import GPUBatchLoader, SyntheticOFDMDataset, create_dataloader, generate_test_samples
-from .quantization import (FakeQuantize, QuantizationConfig, compute_scale, dequantize_tensor, export_q_roms, float_to_q88,
+from .quantization import (FakeQuantize, QuantizationConfig, compute_layer_crc, compute_scale, dequantize_tensor, export_q_roms,
+                           export_weights_fpga, float_to_q88,
                            q88_to_float, quantize_tensor)
 
 __all__ = ["ZeroForcingEqualizer", "MMSEEqualizer", "QAMModulator", "OFDMModulator", "NonLinearImpairments", "ChannelModel", "SyntheticOFDMDataset", "GPUBatchLoader", "create_dataloader", "generate_test_samples", "QuantizationConfig", "compute_scale", "quantize_tensor",
-           "dequantize_tensor", "FakeQuantize", "export_q_roms", "float_to_q88", "q88_to_float"]
+           "dequantize_tensor", "FakeQuantize", "export_weights_fpga", "compute_layer_crc", "export_q_roms", "float_to_q88", "q88_to_float"]

@@ -4,6 +4,11 @@ ROM export that feeds the integer generator kernel (rtl/ofdmGAN/weight_rom.v lay
 These functions touch a few hundred weights once per export: they are host-side tensor arithmetic, not part of the
 per-frame hot path.  The per-frame integer arithmetic lives in libofdmgan (ofdmgan_gen_fwd_q, ofdmgan_quantize_q88).
 """
+import binascii
+import json
+from pathlib import Path
+from typing import Any, Dict
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -57,6 +62,55 @@ class FakeQuantize(nn.Module):
                 self.scale = compute_scale(x, self.n_bits, self.per_channel, self.channel_dim)
         dq = dequantize_tensor(quantize_tensor(x, self.scale, self.n_bits), self.scale)
         return x + (dq - x).detach()
+
+
+# ---- weight export (utils/quantization.py:259-453): int8 weights + float32 scales / biases + CRC32 + metadata.json ------------
+def compute_crc32(data: bytes) -> str:
+    return f"{binascii.crc32(data) & 0xffffffff:08x}"
+
+
+def compute_layer_crc(tensor: torch.Tensor) -> str:
+    """CRC32 of a tensor's bytes (utils/quantization.py:443-453)."""
+    return compute_crc32(tensor.detach().cpu().numpy().tobytes())
+
+
+def _export_layer(name: str, layer: nn.Module, out: Path, config: QuantizationConfig) -> Dict[str, Any]:
+    stem = name.replace(".", "_")
+    weight = layer.weight.detach().cpu()
+    scale = compute_scale(weight, config.weight_bits, config.per_channel, channel_dim=0)
+    w_int8 = quantize_tensor(weight, scale, config.weight_bits).to(torch.int8).numpy().flatten()
+    w_int8.tofile(out / f"{stem}_weights.bin")
+    scale.squeeze().numpy().astype(np.float32).tofile(out / f"{stem}_scale.bin")
+    bias_info = None
+    if layer.bias is not None:
+        layer.bias.detach().cpu().numpy().astype(np.float32).tofile(out / f"{stem}_bias.bin")
+        bias_info = {"file": f"{stem}_bias.bin", "shape": list(layer.bias.shape)}
+    info = {"type": "Conv1d" if isinstance(layer, nn.Conv1d) else "Linear", "weight_file": f"{stem}_weights.bin",
+            "scale_file": f"{stem}_scale.bin", "bias": bias_info, "weight_shape": list(weight.shape)}
+    if isinstance(layer, nn.Conv1d):
+        info.update(kernel_size=layer.kernel_size[0], stride=layer.stride[0], padding=layer.padding[0], in_channels=layer.in_channels,
+                    out_channels=layer.out_channels)
+    else:
+        info.update(in_features=layer.in_features, out_features=layer.out_features)
+    info["crc32"] = compute_crc32(w_int8.tobytes())
+    return info
+
+
+def export_weights_fpga(model: nn.Module, output_dir: str, config: QuantizationConfig = None) -> Dict[str, Any]:
+    """Same files, bytes and metadata.json as the reference's exporter (train.py:530-531 calls it after training): per layer
+    `<name>_weights.bin` (int8, per-channel or per-tensor symmetric scale), `<name>_scale.bin`, `<name>_bias.bin` (float32), the
+    CRC32 of the weight bytes.  Host-side file output of a few hundred bytes: not part of the device path."""
+    config = config or QuantizationConfig()
+    out = Path(output_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    metadata = {"config": {"weight_bits": config.weight_bits, "activation_bits": config.activation_bits, "per_channel": config.per_channel},
+                "layers": {}}
+    for name, module in model.named_modules():
+        if isinstance(module, (nn.Conv1d, nn.Linear)):
+            metadata["layers"][name] = _export_layer(name, module, out, config)
+    with open(out / "metadata.json", "w") as f:
+        json.dump(metadata, f, indent=2)
+    return metadata
 
 
 # ---- ROMs for the integer generator --------------------------------------------------------------------------------
