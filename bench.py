@@ -258,7 +258,12 @@ def main():
     ffma = ops.ffma_peak(8192, device=dev)
     flop_frame = FLOP_SIM + FLOP_GEN
     achieved = F * flop_frame / (float(np.mean(per_step_ms)) * 1e-3) / 1e12
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and F == FRAMES_PER_GPU:                # dram bytes per launch of this kernel at this size, from the ncu capture
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma, "traffic": traffic,
                 "kernel": "og::k_sim<SRC_GAUSS>", "algorithmic_flop_per_frame": flop_frame, "frames_per_launch": F,
                 "peak_source": "FFMA issue-rate microbenchmark ofdmgan_ffma_peak, same run (148 SMs x 128 lanes x 2 flop x clock)",
                 "note": "inputs are generated on-chip and outputs reduced on-chip: HBM traffic per launch is the per-CTA metric "
