@@ -342,3 +342,22 @@ def test_frame_metrics_vs_oracle(ops):
 def test_ffma_peak_is_sane(ops):
     t = ops.ffma_peak(2048)
     assert 20.0 < t < 90.0, t          # B200: 148 SMs x 128 lanes x 2 flop x ~1.9 GHz = 72 TFLOP/s
+
+
+def test_calls_on_different_streams_stay_correct(ops, ref_fp32):
+    """The weight images are one per device: calls on other streams are ordered by the library (CallGuard), so interleaving two
+    streams with DIFFERENT weights must still give each call its own weights."""
+    rng = np.random.default_rng(0)
+    x = cu(rng.standard_normal((200_000, 2, 16)).astype(np.float32))
+    gp_a = ref_fp32["gparams"]
+    gp_b = (ref_fp32["gparams"] * -0.7 + 0.05).astype(np.float32)
+    ref_a, ref_b = ops.gen_fwd_f32(x, gp_a).clone(), ops.gen_fwd_f32(x, gp_b).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(6):
+        with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+            outs.append(ops.gen_fwd_f32(x, gp_a if i % 2 == 0 else gp_b))
+    torch.cuda.synchronize()
+    for i, y in enumerate(outs):
+        assert torch.equal(y, ref_a if i % 2 == 0 else ref_b)
