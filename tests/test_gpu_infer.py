@@ -361,3 +361,13 @@ def test_calls_on_different_streams_stay_correct(ops, ref_fp32):
     torch.cuda.synchronize()
     for i, y in enumerate(outs):
         assert torch.equal(y, ref_a if i % 2 == 0 else ref_b)
+
+
+def test_sweep_beyond_2_pow_27_frames(ops, ref_fp32):
+    """64-bit frame indexing: a single launch over 2^27 + 5 frames starting near 2^40 accounts for every frame."""
+    cfg = ops.make_cfg(snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=1 << 20, normalize=1)
+    B = (1 << 27) + 5
+    m = host(ops.sim_gen_metrics(cfg, B, gparams=ref_fp32["gparams"], seed=1, frame0=(1 << 40) - 3))
+    assert m[:, 0, 0].sum() == B and m[:, 1, 0].sum() == B
+    expect = np.bincount((((1 << 40) - 3 + np.arange(B, dtype=np.int64)) >> 20) % 7, minlength=7)
+    assert np.array_equal(m[:, 0, 0], expect)
