@@ -86,24 +86,47 @@ __device__ __forceinline__ void acc_add(Acc<NMETH>& a, int m, float mse, float e
     if (BITS) a.errs[m] += (float)errs;
 }
 
-// fold the thread's running sums into the CTA table (shared, double).  Warp-uniform bins take the shuffle path.
+// fold the thread's running sums into the CTA table (shared, double).  Warp-uniform bins (the common case) are
+// transpose-reduced: P-1 shuffles leave column (lane % P) of the warp total in every lane, then one atomic per column.
 template <bool BITS, int NMETH>
 __device__ __forceinline__ void acc_flush(Acc<NMETH>& a, double* table, int lane) {
     const unsigned full = 0xffffffffu;
+    constexpr int NCOL = BITS ? NC : NC - 2;                         // columns 5, 6 (bit errors, bits) only with a payload
+    constexpr int NV = NMETH * NCOL, P = NV <= 16 ? 16 : 32;
     const int bin0 = __shfl_sync(full, a.bin, 0);
     const bool uniform = __all_sync(full, a.bin == bin0);
+    float v[P];
 #pragma unroll
     for (int m = 0; m < NMETH; ++m) {
         const float col[NC] = {(float)a.count, a.mse[m], a.mse2[m], a.evm[m], a.evm2[m], a.errs[m], a.nbits, a.ratio[m]};
+        int j = 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (!BITS && (c == 5 || c == 6)) continue;
-            if (uniform) {
-                const float s = warp_sum(col[c]);
-                if (lane == 0 && a.bin >= 0) atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)s);
-            } else if (a.bin >= 0 && col[c] != 0.f) {
-                atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)col[c]);
+            v[m * NCOL + j++] = col[c];
+        }
+    }
+#pragma unroll
+    for (int i = NV; i < P; ++i) v[i] = 0.f;
+    if (uniform) {
+#pragma unroll
+        for (int s = P / 2; s >= 1; s >>= 1) {
+            const bool upper = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const float send = upper ? v[i] : v[i + s], keep = upper ? v[i + s] : v[i];
+                v[i] = keep + __shfl_xor_sync(full, send, s);
             }
+        }
+        if (P == 16) v[0] += __shfl_xor_sync(full, v[0], 16);
+        const int q = lane & (P - 1), m = q / NCOL, j = q - m * NCOL;
+        const int c = BITS ? j : (j < 5 ? j : 7);
+        if (lane < NV && bin0 >= 0) atomicAdd(&table[(bin0 * NM + m) * NC + c], (double)v[0]);
+    } else if (a.bin >= 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int m = q / NCOL, j = q - m * NCOL, c = BITS ? j : (j < 5 ? j : 7);
+            if (v[q] != 0.f) atomicAdd(&table[(a.bin * NM + m) * NC + c], (double)v[q]);
         }
     }
     acc_reset(a, a.bin);
