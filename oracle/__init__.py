@@ -135,6 +135,19 @@ def gen_fwd_q(x, wrom, brom, mode):
     return y
 
 
+def disc_fwd_q(cand, cond, wrom, brom, mode):
+    """Fixed-point critic score per frame (int16 Q8.8): mode 0 spec, 1 rtl_literal steady state, 2 first frame after reset."""
+    cand = np.ascontiguousarray(cand, dtype=np.int16).reshape(-1, 2, 16)
+    cond = np.ascontiguousarray(cond, dtype=np.int16).reshape(-1, 2, 16)
+    W = np.ascontiguousarray(wrom, dtype=np.int8)
+    Bq = np.ascontiguousarray(brom, dtype=np.int16)
+    assert W.size == 2048 and Bq.size == 64 and cand.shape == cond.shape
+    score = np.empty(cand.shape[0], dtype=np.int16)
+    rc = lib().oracle_disc_fwd_q(_p(cand), _p(cond), _p(W), _p(Bq), _p(score), ctypes.c_int64(cand.shape[0]), int(mode))
+    assert rc == 0
+    return score
+
+
 def digest_i16(y):
     y = np.ascontiguousarray(y, dtype=np.int16)
     s, x = ctypes.c_uint64(0), ctypes.c_uint64(0)

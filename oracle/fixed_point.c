@@ -133,3 +133,90 @@ void oracle_digest_i16(const int16_t* y, int64_t n, uint64_t* sum_out, uint64_t*
     }
     *sum_out = s; *xor_out = xr;
 }
+
+/* ================================================================== fixed-point critic ===================
+ * rtl/ofdmGAN/discriminator_mini.v (the only executable definition; utils/quantization.py has no integer forward):
+ *   :66-74    ROM bases: weights conv1 256 ([8][4][3]), conv2 352 ([16][8][3]), dense 736 ([16]); biases 32 / 40 / 56
+ *   :126-134  three parallel taps, each `(a*w) >>> 7` before the sum        :284-291 / :365-367  stride 2, zero pad 1
+ *   :311-321  + sign-extended bias, saturate to int16, LeakyReLU (r>>>2)+(r>>>4)   (same at :388-398 for conv2)
+ *   :418-432  sum pool over the 4 positions into 32 bits; :447 the dense stage reads pool[15:0] (16-bit wrap)
+ *   :458-466  dense taps `(pool*w) >>> 7` + bias; :488-495 saturate the accumulator into the int16 score
+ * mode 0 ("spec"): those primitives on the dataflow of models/discriminator.py:112-152 (all channels, aligned weights).
+ *   No reference fixture pins this mode.
+ * mode 1 ("rtl_literal", steady state): what the committed RTL computes.  Weights lag the data by one loop iteration
+ *   (synchronous ROM read); out_ch_cnt is not reset between states, so CONV2 computes channels 7..15 only, POOL sums
+ *   channel 15 only, and the dense stage therefore sees one non-zero input, multiplied by the lagging weight ROM[750].
+ *   The very first conv1 iteration multiplies by the address left by the previous frame's dense stage (ROM[751..753]);
+ *   mode 2 is the first frame after reset (that address is 0).  PINNED by the five runs of
+ *   rtl/ofdmGAN/tb_discriminator_mini.vcd (tests/golden/rtl_critic_vectors.json: scores and all 846 accumulate-stage
+ *   entries per run, through oracle/rtl_cycle_emulator.py) and by that emulator on random ROMs and frames. */
+static void load_critic_input(const int16_t* cand, const int16_t* cond, int32_t x[4][18]) {
+    memset(x, 0, sizeof(int32_t) * 4 * 18);
+    for (int c = 0; c < 2; ++c)
+        for (int p = 0; p < 16; ++p) { x[c][p + 1] = cand[c * 16 + p]; x[c + 2][p + 1] = cond[c * 16 + p]; }
+}
+
+static int16_t critic_q_spec(const int16_t* cand, const int16_t* cond, const int8_t* W, const int16_t* Bq) {
+    int32_t x[4][18], c1[8][10];
+    load_critic_input(cand, cond, x);
+    memset(c1, 0, sizeof c1);
+    for (int oc = 0; oc < 8; ++oc)
+        for (int op = 0; op < 8; ++op) {
+            int32_t acc = 0;
+            for (int ic = 0; ic < 4; ++ic)
+                for (int k = 0; k < 3; ++k) acc += tap(x[ic][2 * op + k], W[256 + (oc * 4 + ic) * 3 + k]);
+            c1[oc][op + 1] = lrelu_q(sat16(acc + Bq[32 + oc]));
+        }
+    int32_t dense = 0;
+    for (int oc = 0; oc < 16; ++oc) {
+        int32_t pool = 0;
+        for (int op = 0; op < 4; ++op) {
+            int32_t acc = 0;
+            for (int ic = 0; ic < 8; ++ic)
+                for (int k = 0; k < 3; ++k) acc += tap(c1[ic][2 * op + k], W[352 + (oc * 8 + ic) * 3 + k]);
+            pool += lrelu_q(sat16(acc + Bq[40 + oc]));
+        }
+        dense += tap((int16_t)pool, W[736 + oc]);
+    }
+    return (int16_t)sat16(dense + Bq[56]);
+}
+
+static int16_t critic_q_rtl(const int16_t* cand, const int16_t* cond, const int8_t* W, const int16_t* Bq, int stale) {
+    int32_t x[4][18], c1[8][10];
+    load_critic_input(cand, cond, x);
+    memset(c1, 0, sizeof c1);
+    for (int oc = 0; oc < 8; ++oc)
+        for (int op = 0; op < 8; ++op) {
+            int32_t acc = 0;
+            for (int it = 0; it < 4; ++it) {
+                int a;                                   /* the weight triple addressed by the previous iteration */
+                if (it > 0) a = 256 + oc * 12 + (it - 1) * 3;
+                else if (op > 0 || oc == 7) a = 256 + oc * 12 + 9;     /* the last channel is recomputed by the flush passes */
+                else if (oc > 0) a = 256 + (oc - 1) * 12 + 9;
+                else a = stale;
+                for (int k = 0; k < 3; ++k) acc += tap(x[it][2 * op + k], W[(a + k) & 2047]);
+            }
+            c1[oc][op + 1] = lrelu_q(sat16(acc + Bq[32 + oc]));
+        }
+    int32_t pool = 0;
+    for (int op = 0; op < 4; ++op) {
+        int32_t acc = 0;
+        for (int it = 0; it < 8; ++it) {
+            const int a = 352 + 15 * 24 + (it > 0 ? (it - 1) * 3 : 21);
+            for (int k = 0; k < 3; ++k) acc += tap(c1[it][2 * op + k], W[a + k]);
+        }
+        pool += lrelu_q(sat16(acc + Bq[40 + 15]));
+    }
+    return (int16_t)sat16(tap((int16_t)pool, W[750]) + Bq[56]);
+}
+
+/* cand, cond: [B][2][16] int16 Q8.8; score: [B] int16 Q8.8.  mode as above. */
+int oracle_disc_fwd_q(const int16_t* cand, const int16_t* cond, const int8_t* W, const int16_t* Bq, int16_t* score,
+                      int64_t B, int mode) {
+    if (mode < 0 || mode > 2) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; ++b)
+        score[b] = mode == 0 ? critic_q_spec(cand + b * 32, cond + b * 32, W, Bq)
+                             : critic_q_rtl(cand + b * 32, cond + b * 32, W, Bq, mode == 1 ? 751 : 0);
+    return 0;
+}

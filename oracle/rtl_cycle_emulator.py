@@ -317,3 +317,209 @@ class GeneratorMiniRTL:
                 out.append(self.data_out)
         self.clock()
         return out, cycles
+
+
+# =====================================================================================================================
+# Fixed-point critic: cycle-level emulation of rtl/ofdmGAN/discriminator_mini.v
+#   :165-211  state register / next-state logic        :216-256  candidate / condition loading
+#   :261-479  pipelined conv1, conv2, sum-pool, dense   :484-500  score register (saturated dense accumulator)
+#   :104-134  three weight-ROM ports + bias ROM (synchronous, one-cycle latency), per-tap `>>> 7`
+# Pinned against tests/golden/rtl_critic_vectors.json (5 scores + every accumulate-stage entry of the committed Icarus
+# run rtl/ofdmGAN/tb_discriminator_mini.vcd) by tests/test_oracle_fixed_point.py.
+# =====================================================================================================================
+(DS_IDLE, DS_LOAD_CAND, DS_LOAD_COND, DS_CONV1, DS_CONV2, DS_POOL, DS_DENSE, DS_OUTPUT, DS_DONE) = range(9)
+D_IN_CH, D_C1_CH, D_C1_LEN, D_C2_CH, D_C2_LEN = 4, 8, 8, 16, 4
+D_WADDR_C1, D_WADDR_C2, D_WADDR_DENSE = 256, 352, 736
+D_BADDR_C1, D_BADDR_C2, D_BADDR_DENSE = 32, 40, 56
+
+
+class DiscriminatorMiniRTL:
+    def __init__(self, weights, biases):
+        self.W = [0] * 2048
+        self.B = [0] * 64
+        for k, v in (weights.items() if isinstance(weights, dict) else enumerate(weights)):
+            self.W[int(k)] = int(v)
+        for k, v in (biases.items() if isinstance(biases, dict) else enumerate(biases)):
+            self.B[int(k)] = int(v)
+        self.reset()
+
+    def reset(self):
+        self.state = DS_IDLE
+        self.load_ch_cnt = self.load_pos_cnt = 0
+        self.out_ch_cnt = self.out_pos_cnt = self.in_ch_iter = self.pipe_flush = 0
+        self.weight_addr_base = self.bias_addr = 0
+        self.dense_acc = 0
+        self.data_k = [0, 0, 0]
+        self.weight_k = [0, 0, 0]
+        self.bias_data = 0
+        self.s2 = dict(valid=0, out_ch=0, out_pos=0, last=0)
+        self.s3 = dict(valid=0, out_ch=0, out_pos=0, last=0, ksum=0)
+        self.accum = [0] * 16
+        self.input_buf = _Buf2D(D_IN_CH, FRAME_LEN + 2)
+        self.conv1_buf = _Buf2D(D_C1_CH, D_C1_LEN + 2)
+        self.conv2_buf = _Buf2D(D_C2_CH, D_C2_LEN)
+        self.pool_buf = [0] * D_C2_CH
+        self.score_out, self.score_valid = 0, 0
+        self.trace = []
+
+    def _next_state(self, start, cand_valid, cond_valid):
+        s, oc, op, it, fl = self.state, self.out_ch_cnt, self.out_pos_cnt, self.in_ch_iter, self.pipe_flush
+        full = self.load_ch_cnt == 1 and self.load_pos_cnt == FRAME_LEN - 1
+        if s == DS_IDLE:
+            return DS_LOAD_CAND if start else s
+        if s == DS_LOAD_CAND:
+            return DS_LOAD_COND if full and cand_valid else s
+        if s == DS_LOAD_COND:
+            return DS_CONV1 if full and cond_valid else s
+        if s == DS_CONV1:
+            return DS_CONV2 if (oc == D_C1_CH - 1 and op == D_C1_LEN - 1 and it == D_IN_CH - 1 and fl == 2) else s
+        if s == DS_CONV2:
+            return DS_POOL if (oc == D_C2_CH - 1 and op == D_C2_LEN - 1 and it == D_C1_CH - 1 and fl == 2) else s
+        if s == DS_POOL:
+            return DS_DENSE if (oc == D_C2_CH - 1 and op == D_C2_LEN - 1) else s
+        if s == DS_DENSE:
+            return DS_OUTPUT if (oc == D_C2_CH - 1 and fl == 2) else s
+        if s == DS_OUTPUT:
+            return DS_DONE
+        return DS_IDLE
+
+    def clock(self, start=0, cand_in=0, cand_valid=0, cond_in=0, cond_valid=0):
+        st = self.state
+        nxt = self._next_state(start, cand_valid, cond_valid)
+        upd, wr, acc_upd, pool_upd = {}, [], {}, {}
+        new_weight_k = [self.W[(self.weight_addr_base + i) & 0x7FF] for i in range(3)]
+        new_bias = self.B[self.bias_addr & 0x3F]
+
+        # ---- input loading (discriminator_mini.v:216-256)
+        if st == DS_IDLE and start:
+            upd["load_ch_cnt"] = upd["load_pos_cnt"] = 0
+            for r in range(D_IN_CH):
+                for c in range(FRAME_LEN + 2):
+                    wr.append((self.input_buf, r, c, 0))
+        elif st == DS_LOAD_CAND and cand_valid:
+            wr.append((self.input_buf, self.load_ch_cnt, self.load_pos_cnt + 1, _s(cand_in, 16)))
+            if self.load_pos_cnt == FRAME_LEN - 1:
+                upd["load_pos_cnt"] = 0
+                upd["load_ch_cnt"] = 0 if self.load_ch_cnt == 1 else (self.load_ch_cnt + 1) & 3
+            else:
+                upd["load_pos_cnt"] = (self.load_pos_cnt + 1) & 31
+        elif st == DS_LOAD_COND and cond_valid:
+            wr.append((self.input_buf, self.load_ch_cnt + 2, self.load_pos_cnt + 1, _s(cond_in, 16)))
+            if self.load_pos_cnt == FRAME_LEN - 1:
+                upd["load_pos_cnt"] = 0
+                upd["load_ch_cnt"] = (self.load_ch_cnt + 1) & 3
+            else:
+                upd["load_pos_cnt"] = (self.load_pos_cnt + 1) & 31
+
+        # ---- processing (discriminator_mini.v:261-479)
+        oc, op, it, fl = self.out_ch_cnt, self.out_pos_cnt, self.in_ch_iter, self.pipe_flush
+        s2, s3 = self.s2, self.s3
+        new_s2, new_s3 = dict(s2), dict(s3)
+        mults = [self.data_k[i] * self.weight_k[i] for i in range(3)]
+        kernel_sum = _s((mults[0] >> 7) + (mults[1] >> 7) + (mults[2] >> 7), 32)
+
+        def conv_stage(src, in_ch, out_ch, out_len, waddr, baddr, store):
+            upd["weight_addr_base"] = (waddr + oc * (in_ch * 3) + it * 3) & 0x7FF
+            upd["bias_addr"] = (baddr + oc) & 0x3F
+            upd["data_k"] = [src.rd(it, op * 2 + k) for k in range(3)]
+            new_s2.update(valid=1, out_ch=oc, out_pos=op, last=int(it == in_ch - 1))
+            new_s3.update(valid=s2["valid"], out_ch=s2["out_ch"], out_pos=s2["out_pos"], last=s2["last"], ksum=kernel_sum)
+            if s3["valid"]:
+                self.trace.append([st, s3["out_ch"], s3["out_pos"], s3["last"], s3["ksum"]])
+                a = s3["out_ch"] & 15
+                if s3["last"]:
+                    store(s3["out_ch"], s3["out_pos"], _lrelu16(_sat16(_s(self.accum[a] + s3["ksum"] + self.bias_data, 32))))
+                    acc_upd[a] = 0
+                else:
+                    acc_upd[a] = _s(self.accum[a] + s3["ksum"], 32)
+            if it == in_ch - 1:
+                upd["in_ch_iter"] = 0
+                if op == out_len - 1:
+                    upd["out_pos_cnt"] = 0
+                    if oc == out_ch - 1:
+                        upd["pipe_flush"] = (fl + 1) & 7
+                    else:
+                        upd["out_ch_cnt"] = (oc + 1) & 31
+                else:
+                    upd["out_pos_cnt"] = (op + 1) & 31
+            else:
+                upd["in_ch_iter"] = (it + 1) & 31
+
+        if st in (DS_IDLE, DS_LOAD_CAND, DS_LOAD_COND):
+            upd.update(out_ch_cnt=0, out_pos_cnt=0, in_ch_iter=0, pipe_flush=0, dense_acc=0)
+            new_s2["valid"] = new_s3["valid"] = 0
+            for i in range(16):
+                acc_upd[i] = 0
+                pool_upd[i] = 0
+        elif st == DS_CONV1:
+            conv_stage(self.input_buf, D_IN_CH, D_C1_CH, D_C1_LEN, D_WADDR_C1, D_BADDR_C1,
+                       lambda c, p, v: wr.append((self.conv1_buf, c, p + 1, v)))
+        elif st == DS_CONV2:
+            if oc == 0 and op == 0 and it == 0 and fl == 0:            # :359-362 (the later assignments override valid)
+                for i in range(16):
+                    acc_upd[i] = 0
+            conv_stage(self.conv1_buf, D_C1_CH, D_C2_CH, D_C2_LEN, D_WADDR_C2, D_BADDR_C2,
+                       lambda c, p, v: wr.append((self.conv2_buf, c, p, v)))
+        elif st == DS_POOL:
+            new_s2["valid"] = new_s3["valid"] = 0
+            upd["pipe_flush"] = 0
+            pool_upd[oc & 15] = _s(self.pool_buf[oc & 15] + self.conv2_buf.rd(oc, op), 32)
+            if op == D_C2_LEN - 1:
+                upd["out_pos_cnt"] = 0
+                upd["out_ch_cnt"] = 0 if oc == D_C2_CH - 1 else (oc + 1) & 31
+            else:
+                upd["out_pos_cnt"] = (op + 1) & 31
+        elif st == DS_DENSE:
+            upd["weight_addr_base"] = (D_WADDR_DENSE + oc) & 0x7FF
+            upd["bias_addr"] = D_BADDR_DENSE
+            upd["data_k"] = [_s(self.pool_buf[oc & 15], 16), self.data_k[1], self.data_k[2]]
+            new_s2.update(valid=1, out_ch=oc, last=int(oc == D_C2_CH - 1))
+            new_s3.update(valid=s2["valid"], out_ch=s2["out_ch"], last=s2["last"], ksum=_s(mults[0] >> 7, 32))
+            if s3["valid"]:
+                self.trace.append([st, s3["out_ch"], s3["out_pos"], s3["last"], s3["ksum"]])
+                upd["dense_acc"] = _s(self.dense_acc + s3["ksum"] + (self.bias_data if s3["last"] else 0), 32)
+            if oc == D_C2_CH - 1:
+                upd["pipe_flush"] = (fl + 1) & 7
+            else:
+                upd["out_ch_cnt"] = (oc + 1) & 31
+
+        # ---- score register (:484-500)
+        if st == DS_OUTPUT:
+            new_score, new_valid = _sat16(self.dense_acc), 1
+        else:
+            new_score, new_valid = self.score_out, 0
+
+        for b, r, c, v in wr:
+            b.wr(r, c, v)
+        for k, v in acc_upd.items():
+            self.accum[k] = v
+        for k, v in pool_upd.items():
+            self.pool_buf[k] = v
+        for k, v in upd.items():
+            setattr(self, k, v)
+        self.s2, self.s3 = new_s2, new_s3
+        self.weight_k, self.bias_data = new_weight_k, new_bias
+        self.score_out, self.score_valid = new_score, new_valid
+        self.state = nxt
+
+    def run_frame(self, cand32, cond32, max_cycles=5000):
+        """Drive one (candidate, condition) pair as tb_discriminator_mini.v:run_test does.  Returns (score, cycles)."""
+        assert len(cand32) == 32 and len(cond32) == 32
+        for _ in range(3):
+            self.clock()
+        self.clock(start=1)
+        cycles, ia, ib, score = 1, 0, 0, None
+        while self.state != DS_DONE and cycles < max_cycles:
+            if self.state == DS_LOAD_CAND and ia < 32:
+                self.clock(cand_in=cand32[ia], cand_valid=1)
+                ia += 1
+            elif self.state == DS_LOAD_COND and ib < 32:
+                self.clock(cond_in=cond32[ib], cond_valid=1)
+                ib += 1
+            else:
+                self.clock()
+            cycles += 1
+            if self.score_valid:
+                score = self.score_out
+        self.clock()
+        return score, cycles

@@ -30,6 +30,12 @@ def rtl_vectors():
     return json.load(open(os.path.join(GOLDEN, "rtl_generator_vectors.json")))
 
 
+@pytest.fixture(scope="session")
+def rtl_critic_vectors():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "rtl_critic_vectors.json")))
+
+
 def assert_close(got, ref, rtol=1e-5, name=""):
     """|got-ref| <= rtol * max(|ref|, scale) with scale = max|ref| over the tensor: the 1e-5 relative bound of
     BASELINE.json's north_star, taken relative to the tensor's scale so exact zeros do not demand exactness."""
