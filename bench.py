@@ -295,7 +295,24 @@ def main():
             gbs = Q_FRAMES * Q_BYTES / (ms * 1e-3) / 1e9
             also["fixed_point_" + tag] = {"frames_per_s": Q_FRAMES * world / (ms * 1e-3), "ms_per_launch": ms, "frames": Q_FRAMES,
                                           "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak}
-        del xq, yq
+        # ---- integer critic (discriminator_mini.v) over the same frames as candidate, the generator's output as condition
+        Wrom[256:752] = np.clip(np.rint(rng.standard_normal(496) * 30), -128, 127)
+        Brom[32:57] = rng.integers(-64, 64, 25)
+        for mode, tag in ((ops.GEN_Q_SPEC, "spec"), (ops.GEN_Q_RTL, "rtl_literal")):
+            for _ in range(3):
+                sq = ops.disc_fwd_q(yq, xq, Wrom, Brom, mode=mode)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                sq = ops.disc_fwd_q(yq, xq, Wrom, Brom, mode=mode)   # 2 GiB read per launch >> 126 MB L2
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / K
+            gbs = Q_FRAMES * 130 / (ms * 1e-3) / 1e9                  # 64 + 64 bytes in, 2 bytes out per frame
+            also["fixed_point_critic_" + tag] = {"frames_per_s": Q_FRAMES * world / (ms * 1e-3), "ms_per_launch": ms,
+                                                 "frames": Q_FRAMES, "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak}
+        del xq, yq, sq
         # ---- config 1 at scale: fp32 MiniGenerator forward over HBM-resident frames (256 B of traffic per frame)
         xf = torch.randn(Q_FRAMES, 2, 16, generator=g, device=dev)
         for _ in range(3):
@@ -395,7 +412,7 @@ def main():
                          "fp32_tflops_per_gpu": tflops, "fp32_frac_of_ffma_peak": tflops / ffma,
                          "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"]}
-        launches += 2 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
+        launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 3
+#define OFDMGAN_ABI_VERSION 4
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -145,6 +145,13 @@ int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float
  * order-independent (sum, xor) digest of the output words used by the full-size parity test. */
 int ofdmgan_gen_fwd_q(const int16_t* x_dev, const int8_t* wrom_host, const int16_t* brom_host, int16_t* y_dev,
                       int64_t B, int mode, uint64_t* digest_dev, void* stream);
+/* Integer critic: replaces rtl/ofdmGAN/discriminator_mini.v:261-500 (+ weight_rom.v: weights 256..751, biases 32..56).
+ * cand, cond: [B][2][16] int16 device; score: [B] int16 device (Q8.8); ROMs are HOST pointers (2048 int8 / 64 int16).
+ * mode OFDMGAN_GEN_Q_SPEC = the RTL's arithmetic primitives on the dataflow of models/discriminator.py:112-152;
+ * OFDMGAN_GEN_Q_RTL = what the committed RTL computes in steady state (lagging weight reads, counters that are not reset
+ * between states: only conv2 channel 15 reaches the pool). */
+int ofdmgan_disc_fwd_q(const int16_t* cand_dev, const int16_t* cond_dev, const int8_t* wrom_host,
+                       const int16_t* brom_host, int16_t* score_dev, int64_t B, int mode, void* stream);
 /* float -> Q8.8 by truncation toward zero, (x*256).astype(int16): proof/verification.py:297-298 */
 int ofdmgan_quantize_q88(const float* x_dev, int16_t* q_dev, int64_t n, void* stream);
 int ofdmgan_dequantize_q88(const int16_t* q_dev, float* x_dev, int64_t n, void* stream);

@@ -124,6 +124,18 @@ def gen_fwd_q(x_q88, wrom, brom, mode=GEN_Q_SPEC, want_digest=False):
     return y
 
 
+def disc_fwd_q(cand_q88, cond_q88, wrom, brom, mode=GEN_Q_SPEC):
+    """Integer critic score per frame ([B] int16, Q8.8): rtl/ofdmGAN/discriminator_mini.v, mode as for gen_fwd_q."""
+    a, c = frames(cand_q88, torch.int16), frames(cond_q88, torch.int16)
+    if a.shape != c.shape or a.device != c.device:
+        raise OfdmGanError("candidate and condition must have the same shape and device")
+    W, Bq = _roms(wrom, brom)
+    score = torch.empty(a.shape[0], dtype=torch.int16, device=a.device)
+    check(_lib.lib().ofdmgan_disc_fwd_q(dptr(a), dptr(c), W.ctypes.data_as(ctypes.c_void_p), Bq.ctypes.data_as(ctypes.c_void_p),
+                                        dptr(score), a.shape[0], mode, stream_ptr(a.device)))
+    return score
+
+
 def quantize_q88(x):
     if not x.is_cuda:
         raise OfdmGanError("quantize_q88 needs a CUDA tensor")
