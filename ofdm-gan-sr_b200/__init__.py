@@ -4,8 +4,8 @@ Hand-written CUDA kernels behind the C ABI of include/ofdmgan.h (lib/libofdmgan.
 reference's own Python call surface:
 
     models.MiniGenerator / MiniDiscriminator / compute_gradient_penalty      (models/generator.py, discriminator.py)
-    utils.ofdm_utils  QAMModulator, OFDMModulator, NonLinearImpairments, ChannelModel
-    utils.dataset     SyntheticOFDMDataset (+ batched GPU frame source)
+    utils.ofdm_utils  QAMModulator, OFDMModulator, NonLinearImpairments, ChannelModel, ImageOFDMConverter
+    utils.dataset     SyntheticOFDMDataset, OFDMDataset (+ batched GPU frame source)
     utils.quantization  compute_scale / quantize_tensor / dequantize_tensor / FakeQuantize / Q-ROM export
     train_step.CWGANGPStep   the 5-critic + 1-generator step of train.py:327-344, data-parallel over NCCL
     sweep.run_benchmark      the SNR x trial loop of benchmark_comparison.py:179-250, sharded by frame index

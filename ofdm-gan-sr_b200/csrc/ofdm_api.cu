@@ -59,6 +59,48 @@ __global__ void k_qam_demod(const float2* __restrict__ sym, uint8_t* __restrict_
     }
 }
 
+// 32- and 64-point transforms (OFDMModulator's class default is 64 sub-carriers): same radix-2 network as fft_inplace with a
+// 64-point twiddle table; cos(2 pi k / 64) for k = 0..16, the rest by symmetry
+__device__ __forceinline__ constexpr float tw64_q(int k) {
+    return k == 0 ? 1.f : k == 1 ? 0.99518472667219693f : k == 2 ? 0.98078528040323043f : k == 3 ? 0.95694033573220882f
+         : k == 4 ? 0.92387953251128674f : k == 5 ? 0.88192126434835505f : k == 6 ? 0.83146961230254524f
+         : k == 7 ? 0.77301045336273699f : k == 8 ? 0.70710678118654752f : k == 9 ? 0.63439328416364549f
+         : k == 10 ? 0.55557023301960218f : k == 11 ? 0.47139673682599764f : k == 12 ? 0.38268343236508977f
+         : k == 13 ? 0.29028467725446233f : k == 14 ? 0.19509032201612825f : k == 15 ? 0.098017140329560604f : 0.f;
+}
+__device__ __forceinline__ constexpr float tw64_c(int k) { return k <= 16 ? tw64_q(k) : -tw64_q(32 - k); }   // k in 0..31
+__device__ __forceinline__ constexpr float tw64_s(int k) { return k <= 16 ? tw64_q(16 - k) : tw64_q(k - 16); }
+
+template <int N, int SIGN>
+__device__ __forceinline__ void fft_any(float (&re)[N], float (&im)[N]) {
+    if constexpr (N <= 16) {
+        fft_inplace<N, SIGN>(re, im);
+    } else {
+        constexpr int LOG = N == 64 ? 6 : 5;
+        float tr[N], ti[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { tr[i] = re[bitrev(i, LOG)]; ti[i] = im[bitrev(i, LOG)]; }
+#pragma unroll
+        for (int st = 1; st <= LOG; ++st) {
+            const int h = 1 << (st - 1);
+#pragma unroll
+            for (int q = 0; q < N / 2; ++q) {
+                const int j = q & (h - 1), a = ((q >> (st - 1)) << st) + j, b = a + h;
+                const int tw = j * (32 >> (st - 1));                 // index into the 64-point table
+                const float wr = tw64_c(tw), wi = (float)SIGN * tw64_s(tw);
+                float xr, xi;
+                if (tw == 0) { xr = tr[b]; xi = ti[b]; }
+                else if (tw == 16) { xr = -(float)SIGN * ti[b]; xi = (float)SIGN * tr[b]; }
+                else { xr = tr[b] * wr - ti[b] * wi; xi = tr[b] * wi + ti[b] * wr; }
+                tr[b] = tr[a] - xr; ti[b] = ti[a] - xi;
+                tr[a] = tr[a] + xr; ti[a] = ti[a] + xi;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { re[i] = tr[i]; im[i] = ti[i]; }
+    }
+}
+
 __device__ __forceinline__ bool is_pilot(int k, int spacing) { return spacing > 0 && (k % spacing) == 0; }
 
 // :281-329.  One OFDM symbol per thread.
@@ -77,7 +119,7 @@ __global__ void __launch_bounds__(128) k_ofdm_mod(const float2* __restrict__ sym
                 ++d;
             }
         }
-        fft_inplace<N, +1>(Xr, Xi);                              // unscaled inverse = np.fft.ifft * N
+        fft_any<N, +1>(Xr, Xi);                              // unscaled inverse = np.fft.ifft * N
         float2* o = out + s * (N + cp);
         for (int i = 0; i < cp; ++i) {                           // cyclic prefix: the last cp samples first
             float r = 0.f, q = 0.f;
@@ -100,7 +142,7 @@ __global__ void __launch_bounds__(128) k_ofdm_demod(const float2* __restrict__ s
         const float2* in = sig + s * (N + cp) + cp;
 #pragma unroll
         for (int j = 0; j < N; ++j) { const float2 v = in[j]; Xr[j] = v.x; Xi[j] = v.y; }
-        fft_inplace<N, -1>(Xr, Xi);
+        fft_any<N, -1>(Xr, Xi);
         int64_t d = s * n_data, p = s * n_pilot;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
@@ -164,7 +206,7 @@ int ofdmgan_qam_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_sy
 int ofdmgan_ofdm_modulate(const float* sym_dev, int64_t n_symbols, int n_fft, int cp_len, int pilot_spacing, float pilot_re, float pilot_im,
                           float* out_dev, void* stream) {
     if (n_symbols < 0 || cp_len < 0 || pilot_spacing < 0) return OFDMGAN_E_ARG;
-    if (n_fft != 8 && n_fft != 16) return n_fft > 0 ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
+    if (n_fft != 8 && n_fft != 16 && n_fft != 32 && n_fft != 64) return n_fft > 0 ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
     if (cp_len > n_fft) return OFDMGAN_E_ARG;
     const int n_data = n_fft - pilots_of(n_fft, pilot_spacing);
     if (n_data < 1) return OFDMGAN_E_ARG;
@@ -176,19 +218,19 @@ int ofdmgan_ofdm_modulate(const float* sym_dev, int64_t n_symbols, int n_fft, in
     if (cp_len == 0) cp_len = n_fft;
     const int grid = grid_for(n_ofdm, 128, 8);
     cudaStream_t s = (cudaStream_t)stream;
-    if (n_fft == 16)
-        k_ofdm_mod<16><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sym_dev), n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re,
-                                            pilot_im, reinterpret_cast<float2*>(out_dev));
-    else
-        k_ofdm_mod<8><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sym_dev), n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re,
-                                           pilot_im, reinterpret_cast<float2*>(out_dev));
+    const float2* in = reinterpret_cast<const float2*>(sym_dev);
+    float2* out = reinterpret_cast<float2*>(out_dev);
+    if (n_fft == 64) k_ofdm_mod<64><<<grid, 128, 0, s>>>(in, n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re, pilot_im, out);
+    else if (n_fft == 32) k_ofdm_mod<32><<<grid, 128, 0, s>>>(in, n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re, pilot_im, out);
+    else if (n_fft == 16) k_ofdm_mod<16><<<grid, 128, 0, s>>>(in, n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re, pilot_im, out);
+    else k_ofdm_mod<8><<<grid, 128, 0, s>>>(in, n_symbols, n_ofdm, cp_len, pilot_spacing, n_data, pilot_re, pilot_im, out);
     return (int)cudaGetLastError();
 }
 
 int ofdmgan_ofdm_demodulate(const float* sig_dev, int64_t n_ofdm, int n_fft, int cp_len, int pilot_spacing, float pilot_re, float pilot_im,
                             float* data_dev, float* chan_dev, void* stream) {
     if (n_ofdm < 0 || cp_len < 0 || pilot_spacing < 0) return OFDMGAN_E_ARG;
-    if (n_fft != 8 && n_fft != 16) return n_fft > 0 ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
+    if (n_fft != 8 && n_fft != 16 && n_fft != 32 && n_fft != 64) return n_fft > 0 ? OFDMGAN_E_UNSUPPORTED : OFDMGAN_E_ARG;
     if (cp_len > n_fft || (pilot_re == 0.f && pilot_im == 0.f && pilot_spacing > 0 && chan_dev)) return OFDMGAN_E_ARG;
     const int n_pilot = pilots_of(n_fft, pilot_spacing), n_data = n_fft - n_pilot;
     if (n_data < 1) return OFDMGAN_E_ARG;
@@ -196,12 +238,12 @@ int ofdmgan_ofdm_demodulate(const float* sig_dev, int64_t n_ofdm, int n_fft, int
     if (!sig_dev || !data_dev || (reinterpret_cast<uintptr_t>(sig_dev) & 7u) || (reinterpret_cast<uintptr_t>(data_dev) & 7u)) return OFDMGAN_E_ARG;
     const int grid = grid_for(n_ofdm, 128, 8);
     cudaStream_t s = (cudaStream_t)stream;
-    if (n_fft == 16)
-        k_ofdm_demod<16><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sig_dev), n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re,
-                                              pilot_im, reinterpret_cast<float2*>(data_dev), reinterpret_cast<float2*>(chan_dev));
-    else
-        k_ofdm_demod<8><<<grid, 128, 0, s>>>(reinterpret_cast<const float2*>(sig_dev), n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re,
-                                             pilot_im, reinterpret_cast<float2*>(data_dev), reinterpret_cast<float2*>(chan_dev));
+    const float2* in = reinterpret_cast<const float2*>(sig_dev);
+    float2 *data = reinterpret_cast<float2*>(data_dev), *chan = reinterpret_cast<float2*>(chan_dev);
+    if (n_fft == 64) k_ofdm_demod<64><<<grid, 128, 0, s>>>(in, n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re, pilot_im, data, chan);
+    else if (n_fft == 32) k_ofdm_demod<32><<<grid, 128, 0, s>>>(in, n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re, pilot_im, data, chan);
+    else if (n_fft == 16) k_ofdm_demod<16><<<grid, 128, 0, s>>>(in, n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re, pilot_im, data, chan);
+    else k_ofdm_demod<8><<<grid, 128, 0, s>>>(in, n_ofdm, cp_len, pilot_spacing, n_data, n_pilot, pilot_re, pilot_im, data, chan);
     return (int)cudaGetLastError();
 }
 

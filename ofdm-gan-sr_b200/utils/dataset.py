@@ -54,6 +54,85 @@ class SyntheticOFDMDataset(torch.utils.data.Dataset):
         return {"noisy": b["noisy"][0], "clean": b["clean"][0], "snr": b["snr"][0]}
 
 
+class OFDMDataset(torch.utils.data.Dataset):
+    """utils/dataset.py:38-182: (noisy, clean) pairs made from image files.  Same constructor, plus `seed` / `device`.
+
+    The clean frame of an image (first `frame_length` samples of its OFDM signal, normalised to [-1, 1]) is computed once
+    for the whole directory on the GPU; a sample then is that frame, rescaled, through the channel at a uniform SNR
+    (kernel (1) with the transmit frame injected), and the reference's joint normalisation
+    max(max|noisy|, max|clean_normalised|) (dataset.py:143-147 - the clean frame is *not* rescaled there; kept).
+    Decoding the files stays with PIL, exactly as in the reference (`_load_image`, dataset.py:168-182)."""
+
+    def __init__(self, image_dir: str, frame_length: int = 16, modulation: str = "QPSK", n_subcarriers: int = 8, cp_length: int = 2,
+                 snr_range: Tuple[float, float] = (0, 30), channel_type: str = "awgn", samples_per_image: int = 10, transform=None,
+                 seed: int = 0, device=None):
+        from pathlib import Path
+
+        from .ofdm_utils import ImageOFDMConverter
+        if frame_length != 16:
+            raise OfdmGanError("libofdmgan builds 16-sample frames only (the MiniGenerator / RTL frame length)")
+        if channel_type.lower() not in ops.CHANNEL_TYPES:
+            raise ValueError(f"Unknown channel type: {channel_type}")
+        self.image_dir, self.frame_length, self.snr_range = Path(image_dir), frame_length, tuple(snr_range)
+        self.channel_type, self.samples_per_image, self.transform = channel_type.lower(), samples_per_image, transform
+        self.seed, self.device, self.epoch = seed, device, 0
+        self.converter = ImageOFDMConverter(modulation=modulation, n_subcarriers=n_subcarriers, cp_length=cp_length, frame_length=frame_length)
+        self.image_files = self._find_images()
+        self.cfg = ops.make_cfg(pa=False, iq=False, pn=False, snr_mode=ops.SNR_UNIFORM, snr_lo=float(snr_range[0]),
+                                snr_hi=float(snr_range[1]), normalize=ops.NORM_NONE, channel_type=self.channel_type)
+        self._clean, self._factor = None, None
+
+    def _find_images(self):
+        images = []
+        if self.image_dir.exists():
+            for ext in (".png", ".jpg", ".jpeg", ".bmp", ".tiff"):
+                images.extend(self.image_dir.glob(f"*{ext}"))
+                images.extend(self.image_dir.glob(f"*{ext.upper()}"))
+        return sorted(images)
+
+    def _load_image(self, path):
+        import numpy as np
+        from PIL import Image
+        image = Image.open(path)
+        if image.mode != "L":
+            image = image.convert("L")
+        if image.size[0] * image.size[1] > 4096:
+            image = image.resize((64, 64), Image.Resampling.LANCZOS)
+        return np.array(image)
+
+    def clean_frames(self):
+        """([n_images, 2, 16] normalised clean frames, [n_images] normalisation factors), device-resident, built once"""
+        if self._clean is None:
+            self._clean, self._factor, _ = self.converter.images_to_ofdm([self._load_image(p) for p in self.image_files])
+        return self._clean, self._factor
+
+    def __len__(self) -> int:
+        return len(self.image_files) * self.samples_per_image
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch
+
+    def batch(self, start: int, B: int) -> Dict[str, torch.Tensor]:
+        clean_all, factor_all = self.clean_frames()
+        idx = torch.arange(start, start + B, device=clean_all.device) // self.samples_per_image
+        clean_n, factor = clean_all[idx], factor_all[idx]
+        tx = (clean_n * factor[:, None, None]).reshape(B, 32).contiguous()               # back to signal scale, Re[16] | Im[16]
+        _, noisy, snr = ops.chan_sim(self.cfg, B, seed=self.seed, frame0=self.epoch * len(self) + start, device=clean_all.device,
+                                     tx=tx, want_clean=False)
+        m = torch.maximum(noisy.abs().amax(dim=(1, 2)), clean_n.abs().amax(dim=(1, 2)))
+        m = torch.where(m > 0, m, torch.ones_like(m))[:, None, None]
+        noisy, clean = noisy / m, clean_n / m
+        if self.transform:
+            noisy, clean = self.transform(noisy, clean)
+        return {"noisy": noisy, "clean": clean, "snr": snr}
+
+    def __getitem__(self, idx: int) -> Dict[str, torch.Tensor]:
+        if idx < 0 or idx >= len(self):
+            raise IndexError(idx)
+        b = self.batch(idx, 1)
+        return {"noisy": b["noisy"][0], "clean": b["clean"][0], "snr": b["snr"][0]}
+
+
 class GPUBatchLoader:
     """Iterates a SyntheticOFDMDataset in device-resident batches: the replacement for DataLoader(num_workers=0) at
     train.py:660 (the dict it yields is what train.py:327-329 consumes; `.to(device)` is then a no-op).

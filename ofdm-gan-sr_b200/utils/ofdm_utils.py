@@ -68,7 +68,7 @@ class QAMModulator:
 
 
 class OFDMModulator:
-    """utils/ofdm_utils.py:229-371.  n_subcarriers in {8, 16} are built (config/config.yaml:11 uses 8)."""
+    """utils/ofdm_utils.py:229-371.  n_subcarriers in {8, 16, 32, 64} are built (config/config.yaml:11 uses 8, the class default is 64)."""
 
     def __init__(self, n_subcarriers: int = 64, cp_length: int = 16, pilot_spacing: int = 8, pilot_value: complex = 1 + 0j):
         self.n_subcarriers, self.cp_length, self.pilot_spacing, self.pilot_value = n_subcarriers, cp_length, pilot_spacing, pilot_value
@@ -215,3 +215,90 @@ class ChannelModel:
             noise_power = power / (10.0 ** (float(snr_db) / 10.0))
             info["noise_power"] = noise_power if B > 1 else float(noise_power[0])
         return restore(noisy), info
+
+
+class ImageOFDMConverter:
+    """utils/ofdm_utils.py:839-1024: image -> bits -> QAM -> OFDM -> [2, L] float32 I/Q, and back.
+
+    Bit (un)packing, the constellation map and the IFFT/FFT all run on the GPU (`images_to_ofdm` converts a whole list of
+    images with one launch per stage); decoding image files stays with the caller (PIL), as in the reference."""
+
+    def __init__(self, modulation: str = "QAM16", n_subcarriers: int = 64, cp_length: int = 16, frame_length: int = 1024):
+        self.qam = QAMModulator(modulation)
+        self.ofdm = OFDMModulator(n_subcarriers, cp_length)
+        self.frame_length = frame_length
+        self.modulation = modulation
+
+    @staticmethod
+    def _gray(image: np.ndarray) -> np.ndarray:
+        image = np.asarray(image)
+        if image.ndim == 3:                                      # 0.299 R + 0.587 G + 0.114 B, truncated (ofdm_utils.py:901-903)
+            image = np.dot(image[..., :3], [0.299, 0.587, 0.114]).astype(np.uint8)
+        return image
+
+    def _signal(self, pixels_dev: torch.Tensor) -> torch.Tensor:
+        """uint8 pixels (CUDA, flat) -> complex64 OFDM signal padded / truncated to frame_length"""
+        shifts = torch.arange(7, -1, -1, device=pixels_dev.device, dtype=torch.uint8)
+        bits = ((pixels_dev[:, None] >> shifts) & 1).reshape(-1)                 # np.unpackbits: MSB first
+        sig = self.ofdm.modulate(self.qam.modulate(bits))
+        out = torch.zeros(self.frame_length, dtype=torch.complex64, device=sig.device)
+        n = min(self.frame_length, sig.numel())
+        out[:n] = sig[:n]
+        return out
+
+    def image_to_ofdm(self, image: np.ndarray, normalize: bool = True):
+        image = self._gray(image)
+        pixels = torch.as_tensor(np.ascontiguousarray(image.reshape(-1).astype(np.uint8))).cuda()
+        sig = self._signal(pixels)
+        iq = torch.stack([sig.real, sig.imag], dim=0)
+        peak = iq.abs().max()
+        max_val = float(peak) if normalize else 1.0
+        if normalize and max_val > 0:
+            iq = iq / peak                                       # tensor / tensor: a true division, the peak maps to exactly 1
+        n_bits = pixels.numel() * 8
+        metadata = {"original_shape": image.shape, "n_pixels": pixels.numel(), "n_bits": n_bits,
+                    "n_qam_symbols": n_bits // self.qam.bits_per_symbol, "signal_length": self.frame_length,
+                    "normalization_factor": max_val}
+        return iq.cpu().numpy().astype(np.float32), metadata
+
+    def images_to_ofdm(self, images, normalize: bool = True):
+        """list of images -> ([n, 2, L] float32 CUDA tensor, [n] normalisation factors, list of metadata)"""
+        sigs, metas = [], []
+        for im in images:
+            im = self._gray(im)
+            sig = self._signal(torch.as_tensor(np.ascontiguousarray(im.reshape(-1).astype(np.uint8))).cuda())
+            sigs.append(torch.stack([sig.real, sig.imag], dim=0))
+            metas.append({"original_shape": im.shape, "n_pixels": im.size, "n_bits": im.size * 8,
+                          "n_qam_symbols": im.size * 8 // self.qam.bits_per_symbol, "signal_length": self.frame_length})
+        iq = torch.stack(sigs) if sigs else torch.zeros(0, 2, self.frame_length, device="cuda")
+        factor = iq.abs().amax(dim=(1, 2)) if normalize else torch.ones(iq.shape[0], device=iq.device)
+        if normalize:
+            iq = iq / torch.where(factor > 0, factor, torch.ones_like(factor))[:, None, None]
+        for m, f in zip(metas, factor.tolist()):
+            m["normalization_factor"] = f
+        return iq, factor, metas
+
+    def ofdm_to_image(self, iq_signal, original_shape, denormalize_factor: float = 1.0) -> np.ndarray:
+        iq, _ = _to_dev(iq_signal, torch.float32)
+        iq = iq * float(denormalize_factor)
+        sig = torch.complex(iq[0], iq[1])
+        n_sym = sig.numel() // self.ofdm.samples_per_symbol
+        data, _ = self.ofdm.demodulate(sig[:n_sym * self.ofdm.samples_per_symbol])
+        bits = self.qam.demodulate(data).to(torch.uint8)
+        n_pixels = int(np.prod(original_shape))
+        need = n_pixels * 8
+        if bits.numel() >= need:
+            bits = bits[:need]
+        else:
+            bits = torch.cat([bits, torch.zeros(need - bits.numel(), dtype=torch.uint8, device=bits.device)])
+        weights = (1 << torch.arange(7, -1, -1, device=bits.device, dtype=torch.int32))
+        pixels = (bits.view(-1, 8).to(torch.int32) * weights).sum(dim=1).to(torch.uint8)      # np.packbits
+        return pixels.cpu().numpy().reshape(original_shape)
+
+    def to_tensor(self, iq_signal: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.asarray(iq_signal)).unsqueeze(0).float()
+
+    def from_tensor(self, tensor: torch.Tensor) -> np.ndarray:
+        if tensor.dim() == 3:
+            tensor = tensor[0]
+        return tensor.detach().cpu().numpy()

@@ -69,7 +69,7 @@ def test_ofdm_modulator_matches_reference(api, tag, N, cp, sp, pv):
         back = back.view(-1, 2, m.n_data_subcarriers)[:, 0].reshape(-1)
     assert torch.equal(q.demodulate(back), bits)
     with pytest.raises(pkg.OfdmGanError):
-        u.OFDMModulator(64, 16, 8).modulate(r[tag + "_in"])       # valid upstream, not built here
+        u.OFDMModulator(128, 16, 8).modulate(r[tag + "_in"])      # valid upstream, not built here (8/16/32/64 are)
 
 
 def test_memoryless_impairments_match_reference(api):
