@@ -99,6 +99,96 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def torch_eager_bar(gp, dp, clean, noisy, K):
+    """The same box without custom kernels: MiniGenerator / MiniDiscriminator (models/generator.py:180-208,
+    models/discriminator.py:112-152) and the 5+1 CWGAN-GP step of train.py:201-305 written with stock PyTorch CUDA ops
+    (F.conv1d, autograd incl. the double backward of the penalty, torch.optim.Adam), fp32, TF32 off.  Returns timings and
+    the largest difference between its generator output and libofdmgan's on the same frames."""
+    import torch
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True                        # let cuDNN pick its fastest algorithm for these shapes
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def split(v, shapes):
+        out, o = [], 0
+        for sh in shapes:
+            n = int(np.prod(sh))
+            out.append(v[o:o + n].view(*sh).clone().requires_grad_(True))
+            o += n
+        return out
+
+    G = split(gp, [(4, 2, 3), (4,), (8, 4, 3), (8,), (4, 8, 3), (4,), (2, 4, 3), (2,)])
+    D = split(dp, [(8, 4, 3), (8,), (16, 8, 3), (16,), (1, 16), (1,)])
+
+    up = [lambda t: F.interpolate(t, scale_factor=2, mode="nearest")]
+
+    def gen(x):
+        e1 = F.leaky_relu(F.conv1d(x, G[0], G[1], stride=2, padding=1), 0.2)
+        b = F.leaky_relu(F.conv1d(e1, G[2], G[3], stride=2, padding=1), 0.2)
+        d1 = F.leaky_relu(F.conv1d(up[0](b), G[4], G[5], padding=1), 0.2) + e1
+        return torch.tanh(F.conv1d(up[0](d1), G[6], G[7], padding=1))
+
+    def disc(c, cond):
+        h = F.leaky_relu(F.conv1d(torch.cat([c, cond], dim=1), D[0], D[1], stride=2, padding=1), 0.2)
+        h = F.leaky_relu(F.conv1d(h, D[2], D[3], stride=2, padding=1), 0.2)
+        return F.linear(h.sum(dim=2), D[4], D[5])
+
+    opt_g = torch.optim.Adam(G, lr=2e-4, betas=(0.0, 0.9))
+    opt_d = torch.optim.Adam(D, lr=2e-4, betas=(0.0, 0.9))
+
+    def step():
+        for _ in range(5):
+            with torch.no_grad():
+                fake = gen(noisy)
+            alpha = torch.rand(clean.shape[0], 1, 1, device=clean.device)
+            inter = (alpha * clean + (1 - alpha) * fake).requires_grad_(True)
+            grad = torch.autograd.grad(disc(inter, noisy).sum(), inter, create_graph=True)[0]
+            gp_term = ((grad.reshape(grad.shape[0], -1).norm(2, dim=1) - 1) ** 2).mean()
+            d_loss = disc(fake, noisy).mean() - disc(clean, noisy).mean() + 10.0 * gp_term
+            opt_d.zero_grad(set_to_none=True)
+            d_loss.backward()
+            opt_d.step()
+        fake = gen(noisy)
+        g_loss = -disc(fake, noisy).mean() + 100.0 * F.l1_loss(fake, clean)
+        opt_g.zero_grad(set_to_none=True)
+        g_loss.backward()
+        opt_g.step()
+
+    with torch.no_grad():
+        y = gen(noisy)
+    import ofdm_gan_sr_b200 as pkg
+    diff = float((y - pkg.ops.gen_fwd_f32(noisy, gp)).abs().max())
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def fwd():
+        with torch.no_grad():
+            gen(noisy)
+
+    B = clean.shape[0]
+    out = {"what": "stock PyTorch CUDA eager (F.conv1d + autograd + torch.optim.Adam), fp32, same B200, same batch; 'as_written' "
+                   "upsamples with nn.Upsample(nearest) like models/generator.py:141,154 (9.8 ms per call at this batch, "
+                   "tools/eager_probe.py), 'tuned' replaces it by repeat_interleave",
+           "frames": B, "gen_fwd_max_abs_diff_vs_libofdmgan": diff}
+    for tag, fn in (("as_written", up[0]), ("tuned", lambda t: t.repeat_interleave(2, dim=2))):
+        up[0] = fn
+        ms_fwd, ms_step = timed(fwd, K), timed(step, max(2, K // 2))
+        out[tag] = {"gen_fwd_frames_per_s": B / (ms_fwd * 1e-3), "gen_fwd_ms": ms_fwd,
+                    "train_samples_per_s": B / (ms_step * 1e-3), "train_ms_per_step": ms_step}
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -413,6 +503,9 @@ def main():
                          "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"]}
         launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
+        if rank == 0:
+            also["torch_eager"] = torch_eager_bar(gp_d, torch.as_tensor(dp_h, device=dev), clean, noisy, K)
+        barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
