@@ -467,6 +467,19 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1)) / K
         st = trainer.stats()
         assert np.isfinite(st["d_loss"]) and np.isfinite(st["g_loss"])
+        ms_nccl = None
+        if world > 1 and trainer.comm is not None:               # the same step with dist.all_reduce + the Adam kernel, for comparison
+            t2 = CWGANGPStep(gp_h, dp_h, device=dev, exchange="nccl")
+            for _ in range(3):
+                t2.step(clean, noisy)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(K):
+                t2.step(clean, noisy)
+            f1.record()
+            barrier()
+            ms_nccl = max_over_ranks(f0.elapsed_time(f1)) / K
         tflops = Bt * FLOP_TRAIN / (ms * 1e-3) / 1e12
         # end to end: every step's batch comes from pinned host memory (H2D inside the timed region, double-buffered on a copy
         # stream so the transfer of batch i+1 overlaps the compute of batch i - what a prefetching loader does), and the step's
@@ -501,7 +514,9 @@ def main():
         also["train"] = {"samples_per_s": Bt * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": Bt, "n_critic": 5,
                          "fp32_tflops_per_gpu": tflops, "fp32_frac_of_ffma_peak": tflops / ffma,
                          "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
-                         "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"]}
+                         "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"],
+                         "exchange": "none (1 GPU)" if world == 1 else ("peer-memory all-reduce fused with Adam" if trainer.comm is not None else "nccl"),
+                         "ms_per_step_with_nccl_exchange": ms_nccl}
         launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
         if rank == 0:
             also["torch_eager"] = torch_eager_bar(gp_d, torch.as_tensor(dp_h, device=dev), clean, noisy, K)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 4
+#define OFDMGAN_ABI_VERSION 5
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -39,6 +39,7 @@ extern "C" {
 #define OFDMGAN_E_ARG (-1)                /* null pointer / bad enum / bad size */
 #define OFDMGAN_E_STREAMS (-2)            /* reserved (stream bookkeeping failure) */
 #define OFDMGAN_E_UNSUPPORTED (-3)        /* valid in the reference but not built here (named in DESIGN.md) */
+#define OFDMGAN_E_COMM (-4)               /* a data-parallel peer did not arrive within the wait limit */
 
 /* Parameter packing = torch parameters()/state_dict order, flattened (models/generator.py:129-164,
  * models/discriminator.py:78-100):
@@ -258,6 +259,22 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
  * python floats the optimizer holds (1-beta is formed in double before narrowing, as ATen does). */
 int ofdmgan_adam(float* p_dev, float* m_dev, float* v_dev, const float* g_dev, int n, double lr, double beta1,
                  double beta2, double eps, int step, float grad_scale, void* stream);
+
+/* ---- data-parallel exchange fused with the optimiser ---------------------------------------------------- */
+/* replaces, for one-process-per-GPU replicas on one node, the pair  all_reduce(grad buffer) ; optimizer.step()  that ends
+ * train.py:253 / train.py:297 under data parallelism: ONE launch stores this rank's n floats into every peer's exchange block
+ * over NVLink peer memory, waits for all ranks, sums them in rank order (bit-identical on every rank), writes the total back
+ * to g_dev and applies ofdmgan_adam's update to the first n_params entries (n_params may be 0: plain all-reduce).
+ * Setup: every rank calls ofdmgan_comm_create (allocates its exchange block, returns a 64-byte CUDA IPC handle), the host
+ * side all-gathers the handles (torch.distributed), every rank calls ofdmgan_comm_connect with the world x 64 bytes.
+ * All ranks must issue the same sequence of ofdmgan_allreduce_adam calls.  n <= 1024. */
+typedef struct ofdmgan_comm ofdmgan_comm;
+int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handle64);
+int ofdmgan_comm_connect(ofdmgan_comm* comm, const void* all_handles);
+int ofdmgan_comm_destroy(ofdmgan_comm* comm);
+int ofdmgan_comm_check(ofdmgan_comm* comm, void* stream);   /* synchronises; OFDMGAN_E_COMM if a wait ever timed out */
+int ofdmgan_allreduce_adam(ofdmgan_comm* comm, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params,
+                           double lr, double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
 
 /* ---- measurement helper -------------------------------------------------------------------------------- */
 /* FP32 FFMA issue-rate microbenchmark (denominator of the fp32 roofline): runs `iters`

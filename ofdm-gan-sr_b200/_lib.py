@@ -55,6 +55,12 @@ _SIGNATURES = {
     "ofdmgan_gen_bwd_f32": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_f, c_p]),
     "ofdmgan_gen_fwd_q": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, ctypes.c_int, c_p, c_p]),
     "ofdmgan_disc_fwd_q": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, ctypes.c_int, c_p]),
+    "ofdmgan_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_p]),
+    "ofdmgan_comm_connect": (ctypes.c_int, [c_p, c_p]),
+    "ofdmgan_comm_destroy": (ctypes.c_int, [c_p]),
+    "ofdmgan_comm_check": (ctypes.c_int, [c_p, c_p]),
+    "ofdmgan_allreduce_adam": (ctypes.c_int, [c_p, c_p, ctypes.c_int, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                              ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_float, c_p]),
     "ofdmgan_quantize_q88": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_dequantize_q88": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_chan_sim": (ctypes.c_int, [c_p, c_p, c_u64, c_u64, c_p, c_p, c_p, c_i64, c_p]),
@@ -94,7 +100,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 4:
+        if L.ofdmgan_abi_version() != 5:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

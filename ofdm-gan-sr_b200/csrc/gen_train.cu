@@ -198,18 +198,10 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_bwd(const fl
 // torch.optim.Adam._single_tensor_adam, fp32 state, no amsgrad / weight decay (oracle/fp32_models.c oracle_adam).
 // Written with explicit round-to-nearest ops so nothing is contracted into an FMA the eager reference does not have.
 __global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, int n,
-                       float step_size, float bc2_sqrt, float w, float b2, float omb2, float eps, float grad_scale) {
+                       AdamCoef c, float grad_scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float gi = __fmul_rn(g[i], grad_scale);
-    float mi = m[i], vi = v[i];
-    mi = w < 0.5f ? __fadd_rn(mi, __fmul_rn(w, __fsub_rn(gi, mi)))
-                  : __fsub_rn(gi, __fmul_rn(__fsub_rn(gi, mi), __fsub_rn(1.0f, w)));       // lerp_(grad, 1-beta1)
-    vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(__fmul_rn(omb2, gi), gi));                 // mul_(b2).addcmul_(g,g,1-b2)
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
-    p[i] = __fsub_rn(p[i], __fmul_rn(step_size, __fdiv_rn(mi, denom)));                    // addcdiv_(m, denom, -step_size)
-    m[i] = mi;
-    v[i] = vi;
+    adam_one(p[i], m[i], v[i], __fmul_rn(g[i], grad_scale), c);
 }
 
 }  // namespace og
@@ -284,9 +276,7 @@ int ofdmgan_adam(float* p_dev, float* m_dev, float* v_dev, const float* g_dev, i
                  double eps, int step, float grad_scale, void* stream) {
     if (!p_dev || !m_dev || !v_dev || !g_dev || n < 0 || step < 1) return OFDMGAN_E_ARG;
     if (n == 0) return 0;
-    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
-    k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p_dev, m_dev, v_dev, g_dev, n, (float)(lr / bc1), (float)sqrt(bc2),
-                                                               (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
+    k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p_dev, m_dev, v_dev, g_dev, n, adam_coef(lr, beta1, beta2, eps, step),
                                                                grad_scale);
     return (int)cudaGetLastError();
 }

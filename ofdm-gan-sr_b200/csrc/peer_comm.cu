@@ -1,0 +1,157 @@
+// libofdmgan: gradient all-reduce fused with Adam over NVLink / NVSwitch peer memory (sm_100a).
+//
+// The training step of train.py:201-305 ends each of its 5 + 1 optimiser steps with a sum of a 528- / 264-float buffer over
+// the data-parallel ranks followed by Adam on 521 / 258 parameters.  At 2 KB the collective is pure latency (NCCL: ~25 us per
+// call at 8 ranks, a fifth of the step).  Here one 1024-thread CTA per rank does all of it in one launch:
+//   1. every rank stores its buffer straight into slot [parity][rank] of EVERY peer's exchange block (P2P stores over
+//      NVLink), fences, then publishes a sequence number in each peer's flag word;
+//   2. waits until all `world` flags of its own block show that sequence number;
+//   3. sums the `world` slots in rank order - the same order on every rank, so replicas stay bit-identical - writes the total
+//      back to the caller's buffer (loss statistics ride along) and applies Adam to the parameters.
+// Two slot sets alternate by sequence parity: a rank can start step s+1 while a peer still reads step s, and cannot reach step
+// s+2 before that peer has sent its step s+1 contribution, i.e. after it finished reading step s.
+// Exchange blocks are cudaMalloc'ed by the library and shared between the one-process-per-GPU ranks through CUDA IPC handles
+// that the host side swaps over torch.distributed.
+#include <cstring>
+
+#include "common.cuh"
+#include "train_common.cuh"
+
+namespace og {
+
+constexpr int PC_MAX_WORLD = 16;
+constexpr int PC_MAX_N = 1024;                                   // floats per message (critic 528, generator 264)
+constexpr long long PC_SPIN_LIMIT = 4000000000ll;                // ~2 s of SM clocks: a peer that never arrives is an error, not a hang
+
+struct PeerBlock {                                               // one per rank, device memory
+    float slot[2][PC_MAX_WORLD][PC_MAX_N];
+    unsigned int flag[2][PC_MAX_WORLD];
+    int error;                                                   // sticky: set when a wait timed out
+};
+
+struct PeerPtrs { PeerBlock* p[PC_MAX_WORLD]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned int* a, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* a) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys(const float* a) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(a) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int rank, int world, unsigned int seq, float* __restrict__ g,
+                                                         int n, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                         int n_params, AdamCoef coef, float grad_scale) {
+    const int par = seq & 1u, tid = threadIdx.x;
+    PeerBlock* mine = peers.p[rank];
+    __shared__ int timed_out;
+    if (tid == 0) timed_out = 0;
+    // 1. scatter this rank's message into every peer's block (own block included)
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float x = g[i];
+        for (int r = 0; r < world; ++r) peers.p[r]->slot[par][rank][i] = x;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(&peers.p[tid]->flag[par][rank], seq);
+    // 2. wait for every rank's message
+    if (tid < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&mine->flag[par][tid]) != seq) {
+            if (clock64() - t0 > PC_SPIN_LIMIT) { timed_out = 1; mine->error = 1; break; }
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+    if (timed_out) return;
+    // 3. fixed-order sum, statistics and gradients back to the caller, Adam on the parameters
+    for (int i = tid; i < n; i += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < world; ++r) s += ld_sys(&mine->slot[par][r][i]);
+        g[i] = s;
+        if (i < n_params) adam_one(p[i], m[i], v[i], __fmul_rn(s, grad_scale), coef);
+    }
+}
+
+}  // namespace og
+
+using namespace og;
+
+struct ofdmgan_comm {
+    int rank, world, device;
+    unsigned int seq;
+    PeerBlock* local;
+    PeerPtrs peers;
+    bool connected;
+};
+
+extern "C" {
+
+int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handle64) {
+    if (!out || !ipc_handle64 || world < 1 || world > PC_MAX_WORLD || rank < 0 || rank >= world) return OFDMGAN_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ofdmgan_comm* c = new ofdmgan_comm();
+    c->rank = rank; c->world = world; c->seq = 0; c->connected = false;
+    OG_CHECK(cudaGetDevice(&c->device));
+    OG_CHECK(cudaMalloc((void**)&c->local, sizeof(PeerBlock)));
+    OG_CHECK(cudaMemset(c->local, 0, sizeof(PeerBlock)));
+    cudaIpcMemHandle_t h;
+    OG_CHECK(cudaIpcGetMemHandle(&h, c->local));
+    memcpy(ipc_handle64, &h, 64);
+    for (int r = 0; r < PC_MAX_WORLD; ++r) c->peers.p[r] = nullptr;
+    c->peers.p[rank] = c->local;
+    OG_CHECK(cudaDeviceSynchronize());                           // the zeroed block must be in place before any peer writes to it
+    *out = c;
+    return 0;
+}
+
+int ofdmgan_comm_connect(ofdmgan_comm* c, const void* all_handles) {
+    if (!c || !all_handles) return OFDMGAN_E_ARG;
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + 64 * r, 64);
+        void* ptr = nullptr;
+        OG_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peers.p[r] = (PeerBlock*)ptr;
+    }
+    c->connected = true;
+    return 0;
+}
+
+int ofdmgan_comm_destroy(ofdmgan_comm* c) {
+    if (!c) return 0;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peers.p[r]) cudaIpcCloseMemHandle(c->peers.p[r]);
+    cudaFree(c->local);
+    delete c;
+    return 0;
+}
+
+// 0 while every wait so far completed; OFDMGAN_E_COMM after a peer failed to arrive within the spin limit.  Synchronises the stream.
+int ofdmgan_comm_check(ofdmgan_comm* c, void* stream) {
+    if (!c) return OFDMGAN_E_ARG;
+    int err = 0;
+    OG_CHECK(cudaMemcpyAsync(&err, &c->local->error, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    OG_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return err ? OFDMGAN_E_COMM : 0;
+}
+
+int ofdmgan_allreduce_adam(ofdmgan_comm* c, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params, double lr,
+                           double beta1, double beta2, double eps, int step, float grad_scale, void* stream) {
+    if (!c || !c->connected || !g_dev || n < 1 || n > PC_MAX_N || n_params < 0 || n_params > n) return OFDMGAN_E_ARG;
+    if (n_params > 0 && (!p_dev || !m_dev || !v_dev || step < 1)) return OFDMGAN_E_ARG;
+    c->seq += 1;
+    k_allreduce_adam<<<1, 1024, 0, (cudaStream_t)stream>>>(c->peers, c->rank, c->world, c->seq, g_dev, n, p_dev, m_dev, v_dev, n_params,
+                                                           adam_coef(lr, beta1, beta2, eps, n_params > 0 ? step : 1), grad_scale);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

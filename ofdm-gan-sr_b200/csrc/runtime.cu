@@ -151,6 +151,7 @@ const char* ofdmgan_error_string(int code) {
     if (code == OFDMGAN_E_ARG) return "ofdmgan: invalid argument";
     if (code == OFDMGAN_E_STREAMS) return "ofdmgan: too many distinct streams in use";
     if (code == OFDMGAN_E_UNSUPPORTED) return "ofdmgan: configuration not supported by this build";
+    if (code == OFDMGAN_E_COMM) return "ofdmgan: a data-parallel peer did not arrive (exchange wait timed out)";
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "ofdmgan: unknown error";
 }

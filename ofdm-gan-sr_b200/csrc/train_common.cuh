@@ -52,4 +52,24 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // resident CTAs per SM of the 255-register training kernels (2 x 128 threads)
 constexpr int TRAIN_PER_SM = 2;
 
+// ---- Adam: torch.optim.Adam._single_tensor_adam, fp32 state, no amsgrad / weight decay (oracle/fp32_models.c oracle_adam).
+// Explicit round-to-nearest ops so nothing is contracted into an FMA the eager reference does not have.
+struct AdamCoef { float step_size, bc2_sqrt, w, b2, omb2, eps; };
+static inline AdamCoef adam_coef(double lr, double beta1, double beta2, double eps, int step) {
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    return AdamCoef{(float)(lr / bc1), (float)sqrt(bc2), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps};
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void adam_one(float& p, float& m, float& v, float gi, const AdamCoef& c) {
+    float mi = m, vi = v;
+    mi = c.w < 0.5f ? __fadd_rn(mi, __fmul_rn(c.w, __fsub_rn(gi, mi)))
+                    : __fsub_rn(gi, __fmul_rn(__fsub_rn(gi, mi), __fsub_rn(1.0f, c.w)));     // lerp_(grad, 1-beta1)
+    vi = __fadd_rn(__fmul_rn(vi, c.b2), __fmul_rn(__fmul_rn(c.omb2, gi), gi));               // mul_(b2).addcmul_(g,g,1-b2)
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), c.bc2_sqrt), c.eps);
+    p = __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(mi, denom)));                          // addcdiv_(m, denom, -step_size)
+    m = mi;
+    v = vi;
+}
+#endif
+
 }  // namespace og

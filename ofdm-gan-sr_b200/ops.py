@@ -452,6 +452,46 @@ def adam(p, m, v, g, lr, beta1, beta2, eps, step, grad_scale=1.0):
                                   stream_ptr(p.device)))
 
 
+class PeerComm:
+    """Exchange blocks of the data-parallel ranks of ONE node, mapped into each other through CUDA IPC (include/ofdmgan.h,
+    "data-parallel exchange fused with the optimiser").  Needs an initialised torch.distributed group with one process per GPU;
+    the 64-byte handles travel through one all_gather on that group."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.device = _dev(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._h = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().ofdmgan_comm_create(self.rank, self.world, ctypes.byref(self._h), ctypes.cast(handle, ctypes.c_void_p)))
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+            every = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine, group=group)
+            blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in every)
+            check(_lib.lib().ofdmgan_comm_connect(self._h, ctypes.c_char_p(blob)))
+        dist.barrier(group)                                      # nobody sends before everybody has mapped everybody
+        self.group = group
+
+    def allreduce_adam(self, g, p=None, m=None, v=None, lr=0.0, beta1=0.0, beta2=0.0, eps=0.0, step=1, grad_scale=1.0):
+        """g <- sum over ranks of g (fixed rank order), then Adam on p / m / v with the first p.numel() entries of the sum."""
+        n_params = 0 if p is None else p.numel()
+        check(_lib.lib().ofdmgan_allreduce_adam(self._h, dptr(g), g.numel(), dptr(p), dptr(m), dptr(v), n_params, lr, beta1, beta2, eps,
+                                                step, grad_scale, stream_ptr(g.device)))
+
+    def check(self):
+        """Synchronise and raise if a peer ever failed to arrive."""
+        check(_lib.lib().ofdmgan_comm_check(self._h, stream_ptr(self.device)))
+
+    def close(self):
+        if self._h:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)                             # no peer may still be writing into a block that is about to go
+            _lib.lib().ofdmgan_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
 def ffma_peak(iters=4096, device=None):
     device = _dev(device)
     out = ctypes.c_double(0)

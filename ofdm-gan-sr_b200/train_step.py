@@ -21,7 +21,7 @@ class CWGANGPStep:
     """
 
     def __init__(self, gparams, dparams, lr_g=2e-4, lr_d=2e-4, betas=(0.0, 0.9), eps=1e-8, n_critic=5, gp_weight=10.0,
-                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops):
+                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops, exchange="auto"):
         """`backend` is the kernel namespace (default: libofdmgan through `ops`).  It exists so the host-side logic
         of this class (sharding, all-reduce, optimiser bookkeeping) can be exercised by the CPU test-suite with a
         stand-in; the product never passes anything but `ops`."""
@@ -46,6 +46,23 @@ class CWGANGPStep:
         self._dout = torch.zeros(max(n_critic, 1), CRITIC_OUT, dtype=torch.float32, device=self.device)
         self._gout = torch.zeros(GEN_OUT, dtype=torch.float32, device=self.device)
         self._fake = None
+        # gradient exchange: "peer" = all-reduce fused with Adam over NVLink peer memory (one launch, ops.PeerComm),
+        # "nccl" = dist.all_reduce then the Adam kernel, "auto" = peer when the ranks can map each other's memory
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError(f"exchange must be 'auto', 'peer' or 'nccl', got {exchange!r}")
+        self.comm = None
+        if self.distributed and backend is ops and exchange != "nccl":
+            try:
+                self.comm = ops.PeerComm(process_group, self.device)
+            except OfdmGanError:
+                if exchange == "peer":
+                    raise
+            # all ranks must agree: one rank without peer access sends everybody to NCCL
+            ok = torch.tensor([1 if self.comm is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 0 and self.comm is not None:
+                self.comm.close()
+                self.comm = None
 
     def _flat(self, t, n):
         if isinstance(t, torch.nn.Module):
@@ -76,6 +93,19 @@ class CWGANGPStep:
         if self.distributed:
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
 
+    def _reduce_and_update(self, buf, p, m, v, lr, t):
+        """sum `buf` (gradients + loss statistics) over the ranks, then Adam on p with its first p.numel() entries"""
+        if self.comm is not None:
+            self.comm.allreduce_adam(buf, p, m, v, lr, self.betas[0], self.betas[1], self.eps, t)
+        else:
+            self._allreduce(buf)
+            self.k.adam(p, m, v, buf, lr, self.betas[0], self.betas[1], self.eps, t)
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+
     def step(self, clean, noisy, alphas=None):
         """One trainer iteration on this rank's shard of the batch (train.py:327-344).
 
@@ -91,16 +121,16 @@ class CWGANGPStep:
             self.k.critic_step(clean, noisy, self._fake, self.d, alpha=None if alphas is None else alphas[c], seed=self.seed,
                             sample0=self.rank * B, alpha_iter=self.d_steps, gp_weight=self.gp_weight, slope=self.slope,
                             b_global=Bg, out=out)
-            self._allreduce(out)
             self.d_steps += 1
-            self.k.adam(self.d, self.d_m, self.d_v, out, self.lr_d, self.betas[0], self.betas[1], self.eps, self.d_steps)
+            self._reduce_and_update(out, self.d, self.d_m, self.d_v, self.lr_d, self.d_steps)
         self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
-        self._allreduce(self._gout)
         self.g_steps += 1
-        self.k.adam(self.g, self.g_m, self.g_v, self._gout, self.lr_g, self.betas[0], self.betas[1], self.eps, self.g_steps)
+        self._reduce_and_update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self.g_steps)
 
     def stats(self):
         """The scalars train.py:255-261,301-305 log, from the last step: one device->host copy."""
+        if self.comm is not None:
+            self.comm.check()
         d = self._dout[:, D_NPARAMS:D_NPARAMS + 5]
         g = self._gout[G_NPARAMS:G_NPARAMS + 3]
         packed = torch.cat([d.reshape(-1), g]).cpu()
@@ -113,4 +143,4 @@ class CWGANGPStep:
     # kernels launched by one step() (for bench.py's gpu_launches): G fwd 2 (weight image + kernel), per critic iteration
     # 4 (image, k_critic, finalize, adam), generator step 6 (2 images, k_gen_step, finalize, adam)... see DESIGN.md
     def launches_per_step(self):
-        return 2 + self.n_critic * 4 + 5
+        return 2 + self.n_critic * 4 + 5                         # (the fused exchange kernel takes the Adam kernel's place)
