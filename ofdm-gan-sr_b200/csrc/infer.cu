@@ -383,7 +383,7 @@ int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int3
     OG_CHECK(cudaMemsetAsync(partials, 0, (size_t)grid * n * sizeof(double), s));
     k_frame_metrics<<<grid, OG_THREADS, 0, s>>>(est_dev, ref_dev, bin_dev, method, n_snr, B, (double*)partials);
     OG_CHECK(cudaGetLastError());
-    k_reduce_partials<<<(n + 127) / 128, 128, 0, s>>>((const double*)partials, grid, n, metrics_dev);
+    reduce_partials_launch((const double*)partials, grid, n, metrics_dev, s);
     return (int)cudaGetLastError();
 }
 
