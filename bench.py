@@ -454,7 +454,9 @@ def main():
         Bt = TRAIN_FRAMES_PER_GPU
         tcfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
         clean, noisy, _ = ops.chan_sim(tcfg, Bt, seed=0, frame0=rank * Bt, device=dev)
-        trainer = CWGANGPStep(gp_h, dp_h, device=dev)
+        # one GPU: the iteration is replayed as one CUDA graph (device-resident step counters); several GPUs: eager launches with the
+        # peer-memory exchange
+        trainer = CWGANGPStep(gp_h, dp_h, device=dev, graph=(world == 1))
         for _ in range(3):
             trainer.step(clean, noisy)
         barrier()
@@ -467,6 +469,22 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1)) / K
         st = trainer.stats()
         assert np.isfinite(st["d_loss"]) and np.isfinite(st["g_loss"])
+        ms_eager = small = None
+        if world == 1:                                           # the same iteration launched eagerly, and the reference's default batch of 64
+            def timed_steps(tr, c, n_, reps):
+                for _ in range(3):
+                    tr.step(c, n_)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(reps):
+                    tr.step(c, n_)
+                g1.record()
+                torch.cuda.synchronize()
+                return g0.elapsed_time(g1) / reps
+            ms_eager = timed_steps(CWGANGPStep(gp_h, dp_h, device=dev), clean, noisy, K)
+            c64, n64 = clean[:64].contiguous(), noisy[:64].contiguous()
+            small = {"batch": 64, "ms_per_step_graph": timed_steps(CWGANGPStep(gp_h, dp_h, device=dev, graph=True), c64, n64, 50),
+                     "ms_per_step_eager": timed_steps(CWGANGPStep(gp_h, dp_h, device=dev), c64, n64, 50)}
         ms_nccl = None
         if world > 1 and trainer.comm is not None:               # the same step with dist.all_reduce + the Adam kernel, for comparison
             t2 = CWGANGPStep(gp_h, dp_h, device=dev, exchange="nccl")
@@ -516,7 +534,9 @@ def main():
                          "e2e_samples_per_s": e2e_train, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"],
                          "exchange": "none (1 GPU)" if world == 1 else ("peer-memory all-reduce fused with Adam" if trainer.comm is not None else "nccl"),
-                         "ms_per_step_with_nccl_exchange": ms_nccl}
+                         "ms_per_step_with_nccl_exchange": ms_nccl,
+                         "launch": "one CUDA graph per iteration" if trainer.use_graph else "eager, 27 launches per iteration",
+                         "ms_per_step_eager": ms_eager, "reference_default_batch": small}
         launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
         if rank == 0:
             also["torch_eager"] = torch_eager_bar(gp_d, torch.as_tensor(dp_h, device=dev), clean, noisy, K)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 5
+#define OFDMGAN_ABI_VERSION 6
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -247,6 +247,12 @@ int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const fl
                         uint64_t seed, uint64_t sample0, uint32_t alpha_iter, const float* dparams521,
                         float gp_weight, float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev,
                         void* stream);
+/* The same with the alpha counter read from device memory (*alpha_iter_dev) at run time instead of being baked into the launch:
+ * together with ofdmgan_adam_ctr it makes the whole iteration of train.py:327-344 replayable as ONE CUDA graph
+ * (no per-step host scalars).  Always draws alpha from Philox. */
+int ofdmgan_critic_step_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed,
+                            uint64_t sample0, const int32_t* alpha_iter_dev, const float* dparams521, float gp_weight,
+                            float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, void* stream);
 /* replaces the loss + backward of CWGANGPTrainer.train_generator, train.py:285-298.
  * out_dev: 264 floats = grad[258] of g_loss w.r.t. theta_G (local sum, scaled for the global batch), stats[3] =
  * g_loss, adv_loss, rec_loss partial sums, 3 pad.  fake_out_dev (may be NULL) receives G(noisy). */
@@ -259,6 +265,10 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
  * python floats the optimizer holds (1-beta is formed in double before narrowing, as ATen does). */
 int ofdmgan_adam(float* p_dev, float* m_dev, float* v_dev, const float* g_dev, int n, double lr, double beta1,
                  double beta2, double eps, int step, float grad_scale, void* stream);
+
+/* ofdmgan_adam with the step count in device memory: uses t = *step_dev + 1 for the bias corrections and stores t back.  n <= 1024. */
+int ofdmgan_adam_ctr(float* p_dev, float* m_dev, float* v_dev, const float* g_dev, int n, double lr, double beta1,
+                     double beta2, double eps, int32_t* step_dev, float grad_scale, void* stream);
 
 /* ---- data-parallel exchange fused with the optimiser ---------------------------------------------------- */
 /* replaces, for one-process-per-GPU replicas on one node, the pair  all_reduce(grad buffer) ; optimizer.step()  that ends

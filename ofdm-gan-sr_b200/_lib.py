@@ -55,6 +55,9 @@ _SIGNATURES = {
     "ofdmgan_gen_bwd_f32": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_f, c_p]),
     "ofdmgan_gen_fwd_q": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, ctypes.c_int, c_p, c_p]),
     "ofdmgan_disc_fwd_q": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, ctypes.c_int, c_p]),
+    "ofdmgan_critic_step_ctr": (ctypes.c_int, [c_p, c_p, c_p, c_u64, c_u64, c_p, c_p, ctypes.c_float, ctypes.c_float, c_i64, c_i64, c_p, c_p]),
+    "ofdmgan_adam_ctr": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_double, c_p, ctypes.c_float, c_p]),
     "ofdmgan_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_p]),
     "ofdmgan_comm_connect": (ctypes.c_int, [c_p, c_p]),
     "ofdmgan_comm_destroy": (ctypes.c_int, [c_p]),
@@ -100,7 +103,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 5:
+        if L.ofdmgan_abi_version() != 6:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

@@ -14,6 +14,7 @@ struct CriticArgs {
     PhiloxKeys keys;
     uint64_t sample0;
     uint32_t alpha_iter;
+    const int32_t* alpha_iter_dev;   // nullable: device-resident counter read instead of alpha_iter (graph-replayable steps)
     int64_t B;
     int slot;
     float slope;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(OG_THREADS, CRITIC_PER_SM) k_critic2(const __g
                 } else {
                     const uint64_t smp = a.sample0 + (uint64_t)b;
                     uint32_t x[4];
-                    philox4x32_10(a.keys, (uint32_t)smp, (uint32_t)(smp >> 32), a.alpha_iter, 1u, x);
+                    philox4x32_10(a.keys, (uint32_t)smp, (uint32_t)(smp >> 32), a.alpha_iter_dev ? (uint32_t)*a.alpha_iter_dev : a.alpha_iter, 1u, x);
                     alpha = u_half(x[0]);
                 }
             }
@@ -153,7 +154,8 @@ extern "C" {
 
 static int launch_critic(bool score, const float* real, const float* fake, const float* cond, const float* alpha, uint64_t seed,
                          uint64_t sample0, uint32_t alpha_iter, const float* dparams521, float gp_scale, float slope, int64_t B,
-                         bool want_grads, float* norms, cudaStream_t s, int* slot_out, int* grid_out, void** partials_out) {
+                         bool want_grads, float* norms, cudaStream_t s, int* slot_out, int* grid_out, void** partials_out,
+                         const int32_t* alpha_iter_dev = nullptr) {
     int slot, rc;
     CallGuard guard(s);
     if ((rc = guard.rc)) return rc;
@@ -165,7 +167,7 @@ static int launch_critic(bool score, const float* real, const float* fake, const
     CriticArgs a{};
     a.real = real; a.cond = cond; a.fake = fake; a.alpha = alpha;
     a.keys = philox_keys(seed);
-    a.sample0 = sample0; a.alpha_iter = alpha_iter;
+    a.sample0 = sample0; a.alpha_iter = alpha_iter; a.alpha_iter_dev = alpha_iter_dev;
     a.B = B; a.slot = slot; a.slope = slope; a.gp_scale = gp_scale;
     a.want_grads = want_grads ? 1 : 0;
     a.partials = (float*)partials;
@@ -191,9 +193,9 @@ int ofdmgan_gradient_penalty(const float* real_dev, const float* fake_dev, const
     return (int)cudaGetLastError();
 }
 
-int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* alpha_dev, uint64_t seed,
-                        uint64_t sample0, uint32_t alpha_iter, const float* dparams521, float gp_weight, float leaky_slope,
-                        int64_t B_local, int64_t B_global, float* out_dev, void* stream) {
+static int critic_step_impl(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* alpha_dev, uint64_t seed,
+                            uint64_t sample0, uint32_t alpha_iter, const int32_t* alpha_iter_dev, const float* dparams521,
+                            float gp_weight, float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!dparams521 || !out_dev || B_local < 0 || B_global < 1 || B_global < B_local) return OFDMGAN_E_ARG;
     if (B_local > 0 && (!clean_dev || !noisy_dev || !fake_dev || !aligned16(clean_dev) || !aligned16(noisy_dev) || !aligned16(fake_dev)))
@@ -205,10 +207,25 @@ int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const fl
     int slot, grid, rc;
     void* partials;
     if ((rc = launch_critic(true, clean_dev, fake_dev, noisy_dev, alpha_dev, seed, sample0, alpha_iter, dparams521, gp_weight,
-                            leaky_slope, B_local, true, nullptr, s, &slot, &grid, &partials))) return rc;
+                            leaky_slope, B_local, true, nullptr, s, &slot, &grid, &partials, alpha_iter_dev))) return rc;
     k_finalize_critic2<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev,
                                               out_dev + OFDMGAN_D_NPARAMS, 0);
     return (int)cudaGetLastError();
+}
+
+int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* alpha_dev, uint64_t seed,
+                        uint64_t sample0, uint32_t alpha_iter, const float* dparams521, float gp_weight, float leaky_slope,
+                        int64_t B_local, int64_t B_global, float* out_dev, void* stream) {
+    return critic_step_impl(clean_dev, noisy_dev, fake_dev, alpha_dev, seed, sample0, alpha_iter, nullptr, dparams521, gp_weight,
+                            leaky_slope, B_local, B_global, out_dev, stream);
+}
+
+int ofdmgan_critic_step_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed, uint64_t sample0,
+                            const int32_t* alpha_iter_dev, const float* dparams521, float gp_weight, float leaky_slope,
+                            int64_t B_local, int64_t B_global, float* out_dev, void* stream) {
+    if (!alpha_iter_dev) return OFDMGAN_E_ARG;
+    return critic_step_impl(clean_dev, noisy_dev, fake_dev, nullptr, seed, sample0, 0u, alpha_iter_dev, dparams521, gp_weight,
+                            leaky_slope, B_local, B_global, out_dev, stream);
 }
 
 }  // extern "C"

@@ -204,6 +204,18 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __re
     adam_one(p[i], m[i], v[i], __fmul_rn(g[i], grad_scale), c);
 }
 
+// step count read from / advanced in device memory: one block, n <= 1024
+__global__ void __launch_bounds__(1024) k_adam_ctr(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                   const float* __restrict__ g, int n, double lr, double b1, double b2, double eps,
+                                                   int32_t* __restrict__ step_dev, float grad_scale) {
+    const int t = *step_dev + 1;
+    const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);
+    const int i = threadIdx.x;
+    if (i < n) adam_one(p[i], m[i], v[i], __fmul_rn(g[i], grad_scale), c);
+    __syncthreads();
+    if (i == 0) *step_dev = t;
+}
+
 }  // namespace og
 
 using namespace og;
@@ -278,6 +290,14 @@ int ofdmgan_adam(float* p_dev, float* m_dev, float* v_dev, const float* g_dev, i
     if (n == 0) return 0;
     k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p_dev, m_dev, v_dev, g_dev, n, adam_coef(lr, beta1, beta2, eps, step),
                                                                grad_scale);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_adam_ctr(float* p_dev, float* m_dev, float* v_dev, const float* g_dev, int n, double lr, double beta1, double beta2, double eps,
+                     int32_t* step_dev, float grad_scale, void* stream) {
+    if (!p_dev || !m_dev || !v_dev || !g_dev || !step_dev || n < 0 || n > 1024) return OFDMGAN_E_ARG;
+    if (n == 0) return 0;
+    k_adam_ctr<<<1, 1024, 0, (cudaStream_t)stream>>>(p_dev, m_dev, v_dev, g_dev, n, lr, beta1, beta2, eps, step_dev, grad_scale);
     return (int)cudaGetLastError();
 }
 

@@ -60,6 +60,16 @@ static inline AdamCoef adam_coef(double lr, double beta1, double beta2, double e
     return AdamCoef{(float)(lr / bc1), (float)sqrt(bc2), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps};
 }
 #ifdef __CUDACC__
+// the same coefficients from a step count that lives on the device (graph-replayable optimiser steps): beta^t by repeated squaring
+__device__ __forceinline__ double ipow_dev(double b, int t) {
+    double r = 1.0;
+    while (t > 0) { if (t & 1) r *= b; b *= b; t >>= 1; }
+    return r;
+}
+__device__ __forceinline__ AdamCoef adam_coef_dev(double lr, double beta1, double beta2, double eps, int step) {
+    const double bc1 = 1.0 - ipow_dev(beta1, step), bc2 = 1.0 - ipow_dev(beta2, step);
+    return AdamCoef{(float)(lr / bc1), (float)sqrt(bc2), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps};
+}
 __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float gi, const AdamCoef& c) {
     float mi = m, vi = v;
     mi = c.w < 0.5f ? __fadd_rn(mi, __fmul_rn(c.w, __fsub_rn(gi, mi)))

@@ -416,9 +416,20 @@ def gradient_penalty(real, fake, cond, dparams, alpha=None, seed=0, sample0=0, a
 
 
 def critic_step(clean, noisy, fake, dparams, alpha=None, seed=0, sample0=0, alpha_iter=0, gp_weight=10.0, slope=0.2,
-                b_global=None, out=None):
-    """-> out[528] = grad[521] (local sum / B_global), stats[5] (d_loss, wasserstein, gp, d_real, d_fake), 2 pad."""
+                b_global=None, out=None, alpha_iter_dev=None):
+    """-> out[528] = grad[521] (local sum / B_global), stats[5] (d_loss, wasserstein, gp, d_real, d_fake), 2 pad.
+    alpha_iter_dev (int32 CUDA tensor, 1 element): take the Philox alpha counter from device memory (graph-replayable)."""
     clean, noisy, fake = frames(clean), frames(noisy), frames(fake)
+    if alpha_iter_dev is not None:
+        if alpha is not None:
+            raise OfdmGanError("alpha_iter_dev draws alpha from Philox; an injected alpha cannot be combined with it")
+        if out is None:
+            out = torch.empty(CRITIC_OUT, dtype=torch.float32, device=clean.device)
+        B = clean.shape[0]
+        keep, dp = _params(dparams, D_NPARAMS, "dparams")
+        check(_lib.lib().ofdmgan_critic_step_ctr(dptr(clean), dptr(noisy), dptr(fake), seed, sample0, dptr(alpha_iter_dev), dp, gp_weight,
+                                                 slope, B, B if b_global is None else b_global, dptr(out), stream_ptr(clean.device)))
+        return out
     if alpha is not None:
         alpha = alpha.to(torch.float32).contiguous().view(-1)
     if out is None:
@@ -445,9 +456,14 @@ def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, s
     return out
 
 
-def adam(p, m, v, g, lr, beta1, beta2, eps, step, grad_scale=1.0):
-    """In-place fused Adam on flat fp32 CUDA vectors (torch.optim.Adam semantics, train.py:114-127)."""
+def adam(p, m, v, g, lr, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None):
+    """In-place fused Adam on flat fp32 CUDA vectors (torch.optim.Adam semantics, train.py:114-127).
+    step_dev (int32 CUDA tensor, 1 element): the step count lives on the device - t = step_dev + 1 is used and stored back."""
     n = p.numel()
+    if step_dev is not None:
+        check(_lib.lib().ofdmgan_adam_ctr(dptr(p), dptr(m), dptr(v), dptr(g), n, lr, beta1, beta2, eps, dptr(step_dev), grad_scale,
+                                          stream_ptr(p.device)))
+        return
     check(_lib.lib().ofdmgan_adam(dptr(p), dptr(m), dptr(v), dptr(g), n, lr, beta1, beta2, eps, step, grad_scale,
                                   stream_ptr(p.device)))
 

@@ -21,7 +21,7 @@ class CWGANGPStep:
     """
 
     def __init__(self, gparams, dparams, lr_g=2e-4, lr_d=2e-4, betas=(0.0, 0.9), eps=1e-8, n_critic=5, gp_weight=10.0,
-                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops, exchange="auto"):
+                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops, exchange="auto", graph=False):
         """`backend` is the kernel namespace (default: libofdmgan through `ops`).  It exists so the host-side logic
         of this class (sharding, all-reduce, optimiser bookkeeping) can be exercised by the CPU test-suite with a
         stand-in; the product never passes anything but `ops`."""
@@ -46,6 +46,11 @@ class CWGANGPStep:
         self._dout = torch.zeros(max(n_critic, 1), CRITIC_OUT, dtype=torch.float32, device=self.device)
         self._gout = torch.zeros(GEN_OUT, dtype=torch.float32, device=self.device)
         self._fake = None
+        # graph=True (single GPU): the 27 launches of an iteration are captured once per batch shape and replayed as one CUDA
+        # graph; the step counters the kernels need (Philox alpha counter, Adam bias-correction step) then live on the device
+        self.use_graph = bool(graph) and backend is ops and not self.distributed
+        self._ctr = torch.zeros(2, dtype=torch.int32, device=self.device) if self.use_graph else None   # [critic steps, generator steps]
+        self._graph, self._static, self._calls_with_shape = None, None, 0
         # gradient exchange: "peer" = all-reduce fused with Adam over NVLink peer memory (one launch, ops.PeerComm),
         # "nccl" = dist.all_reduce then the Adam kernel, "auto" = peer when the ranks can map each other's memory
         if exchange not in ("auto", "peer", "nccl"):
@@ -106,6 +111,38 @@ class CWGANGPStep:
             self.comm.close()
             self.comm = None
 
+    def _iteration_ctr(self, clean, noisy):
+        """The same iteration as step() with every per-step scalar read from device memory: no argument changes between calls."""
+        B = clean.shape[0]
+        self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
+        for c in range(self.n_critic):
+            out = self._dout[c]
+            self.k.critic_step(clean, noisy, self._fake, self.d, seed=self.seed, sample0=0, gp_weight=self.gp_weight, slope=self.slope,
+                               b_global=B, out=out, alpha_iter_dev=self._ctr[0:1])
+            self.k.adam(self.d, self.d_m, self.d_v, out, self.lr_d, self.betas[0], self.betas[1], self.eps, 0, step_dev=self._ctr[0:1])
+        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=B, out=self._gout)
+        self.k.adam(self.g, self.g_m, self.g_v, self._gout, self.lr_g, self.betas[0], self.betas[1], self.eps, 0, step_dev=self._ctr[1:2])
+
+    def _step_graph(self, clean, noisy):
+        shape = tuple(clean.shape)
+        if self._static is None or tuple(self._static[0].shape) != shape:
+            self._static = (torch.empty_like(clean), torch.empty_like(noisy))
+            self._graph, self._calls_with_shape = None, 0
+        self._static[0].copy_(clean)
+        self._static[1].copy_(noisy)
+        self._calls_with_shape += 1
+        if self._calls_with_shape == 1:
+            self._iteration_ctr(*self._static)                   # first call with this shape: eager (also sizes the library's scratch)
+        else:
+            if self._graph is None:                               # second call: capture (capturing does not execute), then replay
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._iteration_ctr(*self._static)
+                self._graph = g
+            self._graph.replay()
+        self.d_steps += self.n_critic
+        self.g_steps += 1
+
     def step(self, clean, noisy, alphas=None):
         """One trainer iteration on this rank's shard of the batch (train.py:327-344).
 
@@ -113,6 +150,10 @@ class CWGANGPStep:
         compute_gradient_penalty for parity runs; by default alpha comes from Philox(seed, global sample index,
         critic-step counter), so the global batch does not depend on the number of ranks.
         """
+        if self.use_graph:
+            if alphas is not None:
+                raise OfdmGanError("graph=True draws alpha from Philox; injected alphas need graph=False")
+            return self._step_graph(clean, noisy)
         B = clean.shape[0]
         Bg = B * self.world
         self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)

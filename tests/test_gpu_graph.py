@@ -1,0 +1,67 @@
+"""GPU: the trainer iteration replayed as one CUDA graph (device-resident step counters) equals the eager iteration."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import ofdm_gan_sr_b200 as pkg
+    from ofdm_gan_sr_b200.train_step import CWGANGPStep
+    assert torch.cuda.is_available()
+    gp = (np.random.default_rng(7).standard_normal(258) * 0.3).astype(np.float32)
+    dp = (np.random.default_rng(8).standard_normal(521) * 0.2).astype(np.float32)
+    return pkg.ops, CWGANGPStep, gp, dp
+
+
+def _batches(ops, B, n, seed=3):
+    cfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
+    return [ops.chan_sim(cfg, B, seed=seed, frame0=i * B)[:2] for i in range(n)]
+
+
+def test_graph_replay_equals_eager(setup):
+    ops, Step, gp, dp = setup
+    data = _batches(ops, 4096, 6)
+    eager, graph = Step(gp, dp), Step(gp, dp, graph=True)
+    for clean, noisy in data:
+        eager.step(clean, noisy)
+        graph.step(clean, noisy)
+    assert graph._graph is not None and graph.d_steps == eager.d_steps == 30 and graph.g_steps == 6
+    assert graph._ctr.tolist() == [30, 6]                      # the device counters advanced with every replay
+    for a, b in ((graph.g, eager.g), (graph.d, eager.d), (graph.g_m, eager.g_m), (graph.d_v, eager.d_v)):
+        # same alphas, same kernels; Adam's bias correction comes from beta^t by squaring on the device vs pow() on the host
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+    se, sg = eager.stats(), graph.stats()
+    for k in ("d_loss", "gradient_penalty", "g_loss", "rec_loss"):
+        assert abs(se[k] - sg[k]) <= 1e-5 * max(1.0, abs(se[k]))
+
+
+def test_graph_recaptures_on_shape_change_and_rejects_injected_alpha(setup):
+    ops, Step, gp, dp = setup
+    t = Step(gp, dp, graph=True)
+    ref = Step(gp, dp)
+    for B in (1024, 1024, 1024, 2048, 2048, 2048, 1024, 1024):
+        clean, noisy = _batches(ops, B, 1, seed=B)[0]
+        t.step(clean, noisy)
+        ref.step(clean, noisy)
+    assert float((t.d - ref.d).abs().max()) <= 1e-6 * float(ref.d.abs().max())
+    with pytest.raises(Exception):
+        t.step(clean, noisy, alphas=torch.rand(5, 1024, device="cuda"))
+
+
+def test_adam_ctr_matches_host_stepped_adam(setup):
+    ops = setup[0]
+    rng = np.random.default_rng(0)
+    p0 = torch.as_tensor(rng.standard_normal(521).astype(np.float32)).cuda()
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pb, mb, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for t in range(1, 41):
+        g = torch.as_tensor(rng.standard_normal(521).astype(np.float32)).cuda()
+        ops.adam(pa, ma, va, g, 2e-4, 0.5, 0.9, 1e-8, t)
+        ops.adam(pb, mb, vb, g, 2e-4, 0.5, 0.9, 1e-8, 0, step_dev=ctr)
+    assert int(ctr) == 40
+    assert float((pa - pb).abs().max()) <= 1e-6 * float(pa.abs().max())
+    assert torch.equal(ma, mb) and torch.equal(va, vb)         # the moments do not depend on the bias corrections
