@@ -454,9 +454,9 @@ def main():
         Bt = TRAIN_FRAMES_PER_GPU
         tcfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
         clean, noisy, _ = ops.chan_sim(tcfg, Bt, seed=0, frame0=rank * Bt, device=dev)
-        # one GPU: the iteration is replayed as one CUDA graph (device-resident step counters); several GPUs: eager launches with the
-        # peer-memory exchange
-        trainer = CWGANGPStep(gp_h, dp_h, device=dev, graph=(world == 1))
+        # the iteration is replayed as one CUDA graph (device-resident step counters; with several GPUs the peer-memory exchange
+        # kernel is a node of that graph)
+        trainer = CWGANGPStep(gp_h, dp_h, device=dev, graph=True)
         for _ in range(3):
             trainer.step(clean, noisy)
         barrier()

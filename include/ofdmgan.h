@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 6
+#define OFDMGAN_ABI_VERSION 7
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -285,6 +285,11 @@ int ofdmgan_comm_destroy(ofdmgan_comm* comm);
 int ofdmgan_comm_check(ofdmgan_comm* comm, void* stream);   /* synchronises; OFDMGAN_E_COMM if a wait ever timed out */
 int ofdmgan_allreduce_adam(ofdmgan_comm* comm, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params,
                            double lr, double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
+
+/* the same with Adam's step count in device memory (t = *step_dev + 1, stored back): graph-replayable, like ofdmgan_adam_ctr */
+int ofdmgan_allreduce_adam_ctr(ofdmgan_comm* comm, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params,
+                               double lr, double beta1, double beta2, double eps, int32_t* step_dev, float grad_scale,
+                               void* stream);
 
 /* ---- measurement helper -------------------------------------------------------------------------------- */
 /* FP32 FFMA issue-rate microbenchmark (denominator of the fp32 roofline): runs `iters`

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "ofdmgan_comm_check": (ctypes.c_int, [c_p, c_p]),
     "ofdmgan_allreduce_adam": (ctypes.c_int, [c_p, c_p, ctypes.c_int, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                               ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_float, c_p]),
+    "ofdmgan_allreduce_adam_ctr": (ctypes.c_int, [c_p, c_p, ctypes.c_int, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                  ctypes.c_double, ctypes.c_double, c_p, ctypes.c_float, c_p]),
     "ofdmgan_quantize_q88": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_dequantize_q88": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_chan_sim": (ctypes.c_int, [c_p, c_p, c_u64, c_u64, c_p, c_p, c_p, c_i64, c_p]),
@@ -103,7 +105,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 6:
+        if L.ofdmgan_abi_version() != 7:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

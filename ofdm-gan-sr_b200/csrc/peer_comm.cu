@@ -26,6 +26,7 @@ constexpr long long PC_SPIN_LIMIT = 4000000000ll;                // ~2 s of SM c
 struct PeerBlock {                                               // one per rank, device memory
     float slot[2][PC_MAX_WORLD][PC_MAX_N];
     unsigned int flag[2][PC_MAX_WORLD];
+    unsigned int seq;                                            // calls completed by the owning rank (device-resident: graph replays advance it)
     int error;                                                   // sticky: set when a wait timed out
 };
 
@@ -45,11 +46,16 @@ __device__ __forceinline__ float ld_sys(const float* a) {
     return v;
 }
 
-__global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int rank, int world, unsigned int seq, float* __restrict__ g,
+// step_dev == nullptr: Adam coefficients from the host (coef); else t = *step_dev + 1 is used and stored back (ofdmgan_adam_ctr)
+__global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int rank, int world, float* __restrict__ g,
                                                          int n, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                         int n_params, AdamCoef coef, float grad_scale) {
-    const int par = seq & 1u, tid = threadIdx.x;
+                                                         int n_params, AdamCoef coef, double lr, double b1, double b2, double eps,
+                                                         int32_t* __restrict__ step_dev, float grad_scale) {
     PeerBlock* mine = peers.p[rank];
+    const unsigned int seq = mine->seq + 1u;                     // written only by this rank's previous launch (stream order)
+    const int par = seq & 1u, tid = threadIdx.x;
+    int t_adam = 0;
+    if (step_dev) { t_adam = *step_dev + 1; coef = adam_coef_dev(lr, b1, b2, eps, t_adam); }
     __shared__ int timed_out;
     if (tid == 0) timed_out = 0;
     // 1. scatter this rank's message into every peer's block (own block included)
@@ -69,6 +75,7 @@ __global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int ran
         }
     }
     __syncthreads();
+    if (tid == 0) { mine->seq = seq; if (step_dev) *step_dev = t_adam; }
     if (timed_out) return;
     // 3. fixed-order sum, statistics and gradients back to the caller, Adam on the parameters
     for (int i = tid; i < n; i += blockDim.x) {
@@ -85,7 +92,6 @@ using namespace og;
 
 struct ofdmgan_comm {
     int rank, world, device;
-    unsigned int seq;
     PeerBlock* local;
     PeerPtrs peers;
     bool connected;
@@ -97,7 +103,7 @@ int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handl
     if (!out || !ipc_handle64 || world < 1 || world > PC_MAX_WORLD || rank < 0 || rank >= world) return OFDMGAN_E_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     ofdmgan_comm* c = new ofdmgan_comm();
-    c->rank = rank; c->world = world; c->seq = 0; c->connected = false;
+    c->rank = rank; c->world = world; c->connected = false;
     OG_CHECK(cudaGetDevice(&c->device));
     OG_CHECK(cudaMalloc((void**)&c->local, sizeof(PeerBlock)));
     OG_CHECK(cudaMemset(c->local, 0, sizeof(PeerBlock)));
@@ -144,14 +150,25 @@ int ofdmgan_comm_check(ofdmgan_comm* c, void* stream) {
     return err ? OFDMGAN_E_COMM : 0;
 }
 
+static int allreduce_adam_impl(ofdmgan_comm* c, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params, double lr,
+                               double beta1, double beta2, double eps, int step, int32_t* step_dev, float grad_scale, void* stream) {
+    if (!c || !c->connected || !g_dev || n < 1 || n > PC_MAX_N || n_params < 0 || n_params > n) return OFDMGAN_E_ARG;
+    if (n_params > 0 && (!p_dev || !m_dev || !v_dev || (!step_dev && step < 1))) return OFDMGAN_E_ARG;
+    k_allreduce_adam<<<1, 1024, 0, (cudaStream_t)stream>>>(c->peers, c->rank, c->world, g_dev, n, p_dev, m_dev, v_dev, n_params,
+                                                           adam_coef(lr, beta1, beta2, eps, step > 0 ? step : 1), lr, beta1, beta2, eps,
+                                                           n_params > 0 ? step_dev : nullptr, grad_scale);
+    return (int)cudaGetLastError();
+}
+
 int ofdmgan_allreduce_adam(ofdmgan_comm* c, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params, double lr,
                            double beta1, double beta2, double eps, int step, float grad_scale, void* stream) {
-    if (!c || !c->connected || !g_dev || n < 1 || n > PC_MAX_N || n_params < 0 || n_params > n) return OFDMGAN_E_ARG;
-    if (n_params > 0 && (!p_dev || !m_dev || !v_dev || step < 1)) return OFDMGAN_E_ARG;
-    c->seq += 1;
-    k_allreduce_adam<<<1, 1024, 0, (cudaStream_t)stream>>>(c->peers, c->rank, c->world, c->seq, g_dev, n, p_dev, m_dev, v_dev, n_params,
-                                                           adam_coef(lr, beta1, beta2, eps, n_params > 0 ? step : 1), grad_scale);
-    return (int)cudaGetLastError();
+    return allreduce_adam_impl(c, g_dev, n, p_dev, m_dev, v_dev, n_params, lr, beta1, beta2, eps, step, nullptr, grad_scale, stream);
+}
+
+int ofdmgan_allreduce_adam_ctr(ofdmgan_comm* c, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params, double lr,
+                               double beta1, double beta2, double eps, int32_t* step_dev, float grad_scale, void* stream) {
+    if (!step_dev) return OFDMGAN_E_ARG;
+    return allreduce_adam_impl(c, g_dev, n, p_dev, m_dev, v_dev, n_params, lr, beta1, beta2, eps, 0, step_dev, grad_scale, stream);
 }
 
 }  // extern "C"

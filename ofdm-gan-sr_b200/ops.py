@@ -489,9 +489,14 @@ class PeerComm:
         dist.barrier(group)                                      # nobody sends before everybody has mapped everybody
         self.group = group
 
-    def allreduce_adam(self, g, p=None, m=None, v=None, lr=0.0, beta1=0.0, beta2=0.0, eps=0.0, step=1, grad_scale=1.0):
-        """g <- sum over ranks of g (fixed rank order), then Adam on p / m / v with the first p.numel() entries of the sum."""
+    def allreduce_adam(self, g, p=None, m=None, v=None, lr=0.0, beta1=0.0, beta2=0.0, eps=0.0, step=1, grad_scale=1.0, step_dev=None):
+        """g <- sum over ranks of g (fixed rank order), then Adam on p / m / v with the first p.numel() entries of the sum.
+        step_dev (int32 CUDA tensor, 1 element): Adam's step count lives on the device (graph-replayable)."""
         n_params = 0 if p is None else p.numel()
+        if step_dev is not None:
+            check(_lib.lib().ofdmgan_allreduce_adam_ctr(self._h, dptr(g), g.numel(), dptr(p), dptr(m), dptr(v), n_params, lr, beta1, beta2,
+                                                        eps, dptr(step_dev), grad_scale, stream_ptr(g.device)))
+            return
         check(_lib.lib().ofdmgan_allreduce_adam(self._h, dptr(g), g.numel(), dptr(p), dptr(m), dptr(v), n_params, lr, beta1, beta2, eps,
                                                 step, grad_scale, stream_ptr(g.device)))
 

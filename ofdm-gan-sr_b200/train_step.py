@@ -46,9 +46,10 @@ class CWGANGPStep:
         self._dout = torch.zeros(max(n_critic, 1), CRITIC_OUT, dtype=torch.float32, device=self.device)
         self._gout = torch.zeros(GEN_OUT, dtype=torch.float32, device=self.device)
         self._fake = None
-        # graph=True (single GPU): the 27 launches of an iteration are captured once per batch shape and replayed as one CUDA
-        # graph; the step counters the kernels need (Philox alpha counter, Adam bias-correction step) then live on the device
-        self.use_graph = bool(graph) and backend is ops and not self.distributed
+        # graph=True: the 27 launches of an iteration are captured once per batch shape and replayed as one CUDA graph; the step
+        # counters the kernels need (Philox alpha counter, Adam bias-correction step, the peer exchange's sequence number) then live
+        # on the device.  With several ranks it needs the peer-memory exchange (a captured graph cannot hold the NCCL fallback here).
+        self.use_graph = bool(graph) and backend is ops
         self._ctr = torch.zeros(2, dtype=torch.int32, device=self.device) if self.use_graph else None   # [critic steps, generator steps]
         self._graph, self._static, self._calls_with_shape = None, None, 0
         # gradient exchange: "peer" = all-reduce fused with Adam over NVLink peer memory (one launch, ops.PeerComm),
@@ -68,6 +69,8 @@ class CWGANGPStep:
             if int(ok.item()) == 0 and self.comm is not None:
                 self.comm.close()
                 self.comm = None
+        if self.distributed and self.comm is None:
+            self.use_graph = False                               # NCCL exchange: eager launches
 
     def _flat(self, t, n):
         if isinstance(t, torch.nn.Module):
@@ -114,14 +117,22 @@ class CWGANGPStep:
     def _iteration_ctr(self, clean, noisy):
         """The same iteration as step() with every per-step scalar read from device memory: no argument changes between calls."""
         B = clean.shape[0]
+        Bg = B * self.world
+
+        def update(buf, p, m, v, lr, ctr):
+            if self.comm is not None:
+                self.comm.allreduce_adam(buf, p, m, v, lr, self.betas[0], self.betas[1], self.eps, step_dev=ctr)
+            else:
+                self.k.adam(p, m, v, buf, lr, self.betas[0], self.betas[1], self.eps, 0, step_dev=ctr)
+
         self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
         for c in range(self.n_critic):
             out = self._dout[c]
-            self.k.critic_step(clean, noisy, self._fake, self.d, seed=self.seed, sample0=0, gp_weight=self.gp_weight, slope=self.slope,
-                               b_global=B, out=out, alpha_iter_dev=self._ctr[0:1])
-            self.k.adam(self.d, self.d_m, self.d_v, out, self.lr_d, self.betas[0], self.betas[1], self.eps, 0, step_dev=self._ctr[0:1])
-        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=B, out=self._gout)
-        self.k.adam(self.g, self.g_m, self.g_v, self._gout, self.lr_g, self.betas[0], self.betas[1], self.eps, 0, step_dev=self._ctr[1:2])
+            self.k.critic_step(clean, noisy, self._fake, self.d, seed=self.seed, sample0=self.rank * B, gp_weight=self.gp_weight,
+                               slope=self.slope, b_global=Bg, out=out, alpha_iter_dev=self._ctr[0:1])
+            update(out, self.d, self.d_m, self.d_v, self.lr_d, self._ctr[0:1])
+        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
+        update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self._ctr[1:2])
 
     def _step_graph(self, clean, noisy):
         shape = tuple(clean.shape)

@@ -49,9 +49,9 @@ clean, noisy = clean_all[rank * B:(rank + 1) * B].contiguous(), noisy_all[rank *
 gp = (np.random.default_rng(7).standard_normal(258) * 0.3).astype(np.float32)
 dp = (np.random.default_rng(8).standard_normal(521) * 0.2).astype(np.float32)
 runs = {}
-for mode in ("peer", "nccl"):
-    t = CWGANGPStep(gp, dp, device=dev, exchange=mode)
-    assert (t.comm is not None) == (mode == "peer")
+for mode in ("peer", "nccl", "peer+graph"):
+    t = CWGANGPStep(gp, dp, device=dev, exchange=mode.split("+")[0], graph=mode.endswith("graph"))
+    assert (t.comm is not None) == mode.startswith("peer") and t.use_graph == mode.endswith("graph")
     for _ in range(4):
         t.step(clean, noisy)
     runs[mode] = (t.g.clone(), t.d.clone(), t.stats())
@@ -67,6 +67,8 @@ for name, (g, d, st) in runs.items():
     assert abs(st["d_loss"] - solo.stats()["d_loss"]) < 1e-4 * max(1.0, abs(solo.stats()["d_loss"]))
 err = float((runs["peer"][0] - runs["nccl"][0]).abs().max())
 assert err < 1e-6, err                                                   # same sums up to the order NCCL happens to use
+err = float((runs["peer+graph"][1] - runs["peer"][1]).abs().max()) / float(runs["peer"][1].abs().max())
+assert err < 1e-6, err                                                   # replayed graph == eager launches
 dist.barrier()
 if rank == 0:
     print("multi-gpu worker ok: world", world)
