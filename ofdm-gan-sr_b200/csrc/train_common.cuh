@@ -34,9 +34,17 @@ __device__ __forceinline__ void cta_store_partials(const GradAcc<NG>& acc, float
 __device__ __forceinline__ void reduce_group_rows(const float* __restrict__ partials, int nblocks, int slots, int grp, double* red /*[32][32]*/,
                                                   double* total /*[32]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double s = 0.0;
-    for (int b = warp; b < nblocks; b += 32) s += (double)partials[(size_t)b * slots + grp * 32 + lane];
-    red[warp * 32 + lane] = s;
+    // four independent chains per warp keep four row loads in flight (one chain was a ~19-deep load-add dependency per block)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const float* col = partials + grp * 32 + lane;
+    int b = warp;
+    for (; b + 96 < nblocks; b += 128) {
+        const float v0 = col[(size_t)b * slots], v1 = col[(size_t)(b + 32) * slots], v2 = col[(size_t)(b + 64) * slots],
+                    v3 = col[(size_t)(b + 96) * slots];
+        s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+    }
+    for (; b < nblocks; b += 32) s0 += (double)col[(size_t)b * slots];
+    red[warp * 32 + lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (warp == 0) {
         double a = 0.0;
