@@ -30,6 +30,7 @@ def main(argv=None):
     ap.add_argument("--lr", type=float, default=2e-4)
     ap.add_argument("--log_every", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--graph", action="store_true", help="replay each iteration as one CUDA graph")
     args = ap.parse_args(argv)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -41,7 +42,7 @@ def main(argv=None):
     ds = SyntheticOFDMDataset(n_samples=args.batch * world * args.steps, snr_range=(0, 30), nonlinear=args.nonlinear,
                               pa_saturation=args.pa_saturation, seed=args.seed)
     loader = create_dataloader(ds, batch_size=args.batch, rank=rank, world_size=world)
-    step = CWGANGPStep(G, D, lr_g=args.lr, lr_d=args.lr, seed=args.seed)
+    step = CWGANGPStep(G, D, lr_g=args.lr, lr_d=args.lr, seed=args.seed, graph=args.graph)
     history, t0 = [], time.time()
     for i, batch in enumerate(loader):
         step.step(batch["clean"], batch["noisy"])

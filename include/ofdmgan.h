@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 7
+#define OFDMGAN_ABI_VERSION 8
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -153,6 +153,13 @@ int ofdmgan_gen_fwd_q(const int16_t* x_dev, const int8_t* wrom_host, const int16
  * between states: only conv2 channel 15 reaches the pool). */
 int ofdmgan_disc_fwd_q(const int16_t* cand_dev, const int16_t* cond_dev, const int8_t* wrom_host,
                        const int16_t* brom_host, int16_t* score_dev, int64_t B, int mode, void* stream);
+/* replace compute_scale / quantize_tensor / dequantize_tensor, utils/quantization.py:73-161, on device tensors laid out
+ * [C][inner] with one scale per leading index (C = 1: per tensor): scale = max(amax|x|, 1e-8) / (2^(n-1) - 1);
+ * q = clamp(round_half_even(x / scale), -2^(n-1), 2^(n-1) - 1) as float; x = q * scale. */
+int ofdmgan_compute_scale(const float* x_dev, int64_t C, int64_t inner, int n_bits, float* scale_dev, void* stream);
+int ofdmgan_quantize_tensor(const float* x_dev, int64_t C, int64_t inner, const float* scale_dev, int n_bits, float* q_dev,
+                            void* stream);
+int ofdmgan_dequantize_tensor(const float* q_dev, int64_t C, int64_t inner, const float* scale_dev, float* x_dev, void* stream);
 /* float -> Q8.8 by truncation toward zero, (x*256).astype(int16): proof/verification.py:297-298 */
 int ofdmgan_quantize_q88(const float* x_dev, int16_t* q_dev, int64_t n, void* stream);
 int ofdmgan_dequantize_q88(const int16_t* q_dev, float* x_dev, int64_t n, void* stream);

@@ -66,6 +66,9 @@ _SIGNATURES = {
                                               ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_float, c_p]),
     "ofdmgan_allreduce_adam_ctr": (ctypes.c_int, [c_p, c_p, ctypes.c_int, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                                   ctypes.c_double, ctypes.c_double, c_p, ctypes.c_float, c_p]),
+    "ofdmgan_compute_scale": (ctypes.c_int, [c_p, c_i64, c_i64, ctypes.c_int, c_p, c_p]),
+    "ofdmgan_quantize_tensor": (ctypes.c_int, [c_p, c_i64, c_i64, c_p, ctypes.c_int, c_p, c_p]),
+    "ofdmgan_dequantize_tensor": (ctypes.c_int, [c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "ofdmgan_quantize_q88": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_dequantize_q88": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
     "ofdmgan_chan_sim": (ctypes.c_int, [c_p, c_p, c_u64, c_u64, c_p, c_p, c_p, c_i64, c_p]),
@@ -105,7 +108,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 7:
+        if L.ofdmgan_abi_version() != 8:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

@@ -73,6 +73,31 @@ __global__ void k_quantize_q88(const float* __restrict__ x, int16_t* __restrict_
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         q[i] = (int16_t)(int)(x[i] * 256.0f);                 // C cast: truncation toward zero (proof/verification.py:297)
 }
+// utils/quantization.py:73-161 on tensors laid out [C][inner] (C = 1: per tensor).  IEEE division and round-half-even, like
+// torch.clamp(amax, min=1e-8) / qmax  and  torch.clamp(torch.round(x / scale), lo, hi).
+__global__ void __launch_bounds__(256) k_compute_scale(const float* __restrict__ x, int64_t inner, float qmax, float* __restrict__ scale) {
+    __shared__ float red[256];
+    const float* row = x + (int64_t)blockIdx.x * inner;
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < inner; i += 256) m = fmaxf(m, fabsf(row[i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scale[blockIdx.x] = __fdiv_rn(fmaxf(red[0], 1e-8f), qmax);
+}
+__global__ void k_quantize_tensor(const float* __restrict__ x, int64_t n, int64_t inner, const float* __restrict__ scale, float lo, float hi,
+                                  float* __restrict__ q) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        q[i] = fminf(fmaxf(rintf(__fdiv_rn(x[i], scale[i / inner])), lo), hi);
+}
+__global__ void k_dequantize_tensor(const float* __restrict__ q, int64_t n, int64_t inner, const float* __restrict__ scale,
+                                    float* __restrict__ x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = __fmul_rn(q[i], scale[i / inner]);
+}
 __global__ void k_dequantize_q88(const int16_t* __restrict__ q, float* __restrict__ x, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         x[i] = (float)q[i] * (1.0f / 256.0f);
@@ -259,6 +284,27 @@ int ofdmgan_quantize_q88(const float* x_dev, int16_t* q_dev, int64_t n, void* st
     if (!x_dev || !q_dev || n < 0) return OFDMGAN_E_ARG;
     if (n == 0) return 0;
     k_quantize_q88<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x_dev, q_dev, n);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_compute_scale(const float* x_dev, int64_t C, int64_t inner, int n_bits, float* scale_dev, void* stream) {
+    if (!x_dev || !scale_dev || C < 1 || C > 65535 || inner < 1 || n_bits < 2 || n_bits > 24) return OFDMGAN_E_ARG;
+    k_compute_scale<<<(int)C, 256, 0, (cudaStream_t)stream>>>(x_dev, inner, (float)((1 << (n_bits - 1)) - 1), scale_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_quantize_tensor(const float* x_dev, int64_t C, int64_t inner, const float* scale_dev, int n_bits, float* q_dev, void* stream) {
+    if (!x_dev || !scale_dev || !q_dev || C < 1 || inner < 1 || n_bits < 2 || n_bits > 24) return OFDMGAN_E_ARG;
+    const int64_t n = C * inner;
+    k_quantize_tensor<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x_dev, n, inner, scale_dev, -(float)(1 << (n_bits - 1)),
+                                                                            (float)((1 << (n_bits - 1)) - 1), q_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_dequantize_tensor(const float* q_dev, int64_t C, int64_t inner, const float* scale_dev, float* x_dev, void* stream) {
+    if (!x_dev || !scale_dev || !q_dev || C < 1 || inner < 1) return OFDMGAN_E_ARG;
+    const int64_t n = C * inner;
+    k_dequantize_tensor<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(q_dev, n, inner, scale_dev, x_dev);
     return (int)cudaGetLastError();
 }
 

@@ -136,6 +136,28 @@ def disc_fwd_q(cand_q88, cond_q88, wrom, brom, mode=GEN_Q_SPEC):
     return score
 
 
+def compute_scale(x2d, n_bits):
+    """x2d: [C, inner] float32 CUDA -> [C] scales (utils/quantization.py:73-112)."""
+    x2d = x2d.to(torch.float32).contiguous()
+    scale = torch.empty(x2d.shape[0], dtype=torch.float32, device=x2d.device)
+    check(_lib.lib().ofdmgan_compute_scale(dptr(x2d), x2d.shape[0], x2d.shape[1], n_bits, dptr(scale), stream_ptr(x2d.device)))
+    return scale
+
+
+def quantize_tensor(x2d, scale, n_bits):
+    x2d, scale = x2d.to(torch.float32).contiguous(), scale.to(torch.float32).contiguous().view(-1)
+    q = torch.empty_like(x2d)
+    check(_lib.lib().ofdmgan_quantize_tensor(dptr(x2d), x2d.shape[0], x2d.shape[1], dptr(scale), n_bits, dptr(q), stream_ptr(x2d.device)))
+    return q
+
+
+def dequantize_tensor(q2d, scale):
+    q2d, scale = q2d.to(torch.float32).contiguous(), scale.to(torch.float32).contiguous().view(-1)
+    x = torch.empty_like(q2d)
+    check(_lib.lib().ofdmgan_dequantize_tensor(dptr(q2d), q2d.shape[0], q2d.shape[1], dptr(scale), dptr(x), stream_ptr(q2d.device)))
+    return x
+
+
 def quantize_q88(x):
     if not x.is_cuda:
         raise OfdmGanError("quantize_q88 needs a CUDA tensor")

@@ -1,8 +1,10 @@
 """Weight / activation quantisation with the reference's interface (utils/quantization.py:44-161) plus the Q1.7 / Q8.8
 ROM export that feeds the integer generator kernel (rtl/ofdmGAN/weight_rom.v layout).
 
-These functions touch a few hundred weights once per export: they are host-side tensor arithmetic, not part of the
-per-frame hot path.  The per-frame integer arithmetic lives in libofdmgan (ofdmgan_gen_fwd_q, ofdmgan_quantize_q88).
+compute_scale / quantize_tensor / dequantize_tensor run in libofdmgan (ofdmgan_compute_scale, ofdmgan_quantize_tensor,
+ofdmgan_dequantize_tensor) for CUDA tensors.  The file exporters at the bottom write a few hundred bytes from module state
+that train.py keeps on the host at that point (train.py:530-531): host-side file output, the same tensor expressions as
+upstream.  The per-frame integer arithmetic lives in ofdmgan_gen_fwd_q / ofdmgan_disc_fwd_q / ofdmgan_quantize_q88.
 """
 import binascii
 import json
@@ -29,6 +31,13 @@ class QuantizationConfig:
 def compute_scale(tensor: torch.Tensor, n_bits: int, per_channel: bool = False, channel_dim: int = 0) -> torch.Tensor:
     """scale = max(|x|, 1e-8) / (2^(n-1) - 1), per tensor or per channel (utils/quantization.py:73-112)."""
     qmax = 2 ** (n_bits - 1) - 1
+    if tensor.is_cuda:
+        if per_channel:
+            t = tensor.movedim(channel_dim, 0)
+            shape = [1] * tensor.dim()
+            shape[channel_dim] = tensor.shape[channel_dim]
+            return ops.compute_scale(t.reshape(t.shape[0], -1), n_bits).view(shape)
+        return ops.compute_scale(tensor.reshape(1, -1), n_bits).view(())
     if per_channel:
         dims = [d for d in range(tensor.dim()) if d != channel_dim]
         amax = tensor.abs().amax(dim=dims, keepdim=True)
@@ -39,11 +48,29 @@ def compute_scale(tensor: torch.Tensor, n_bits: int, per_channel: bool = False, 
 
 def quantize_tensor(tensor: torch.Tensor, scale: torch.Tensor, n_bits: int) -> torch.Tensor:
     """clamp(round_half_even(x / scale), -2^(n-1), 2^(n-1)-1), returned as float (utils/quantization.py:115-141)."""
+    if tensor.is_cuda:
+        return _per_channel_call(ops.quantize_tensor, tensor, scale, n_bits)
     return torch.clamp(torch.round(tensor / scale), -(2 ** (n_bits - 1)), 2 ** (n_bits - 1) - 1)
 
 
 def dequantize_tensor(quantized: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    if quantized.is_cuda:
+        return _per_channel_call(ops.dequantize_tensor, quantized, scale)
     return quantized * scale
+
+
+def _per_channel_call(fn, tensor, scale, *extra):
+    """Run a [C, inner] kernel for a scale that is one number or a keepdim per-channel tensor (what compute_scale returns)."""
+    scale = torch.as_tensor(scale, dtype=torch.float32, device=tensor.device)
+    if scale.numel() == 1:
+        return fn(tensor.reshape(1, -1), scale.reshape(1), *extra).view(tensor.shape)
+    dims = [d for d in range(scale.dim()) if scale.shape[d] != 1]
+    if scale.dim() != tensor.dim() or len(dims) != 1 or scale.shape[dims[0]] != tensor.shape[dims[0]]:
+        raise ops.OfdmGanError("scale must be a scalar or a keepdim per-channel tensor (the shapes compute_scale returns)")
+    d = dims[0]
+    t = tensor.movedim(d, 0)
+    out = fn(t.reshape(t.shape[0], -1), scale.reshape(-1), *extra)
+    return out.view(t.shape).movedim(0, d).contiguous()
 
 
 class FakeQuantize(nn.Module):

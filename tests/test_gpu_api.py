@@ -196,7 +196,7 @@ def test_fused_trainer_step_vs_torch_eager(pkg):
         g_loss.backward()
         oG.step()
         st = tr.stats()
-        assert abs(st["d_loss"] - float(d_loss)) <= 2e-5 * max(1, abs(float(d_loss)))
+        assert abs(st["d_loss"] - float(d_loss.detach())) <= 2e-5 * max(1, abs(float(d_loss.detach())))
         assert abs(st["g_loss"] - float(g_loss)) <= 2e-5 * max(1, abs(float(g_loss)))
     tr.store_to(G, D)
     for (n, p), (_, q) in zip(list(G.named_parameters()) + list(D.named_parameters()),
@@ -280,3 +280,33 @@ def test_q_rom_export_and_integer_inference(pkg):
     # the clean-dataflow integer model tracks the float model it was exported from (1x1 output conv, clip instead of tanh
     # and a 0.3125 LeakyReLU make it an approximation, not a bit-level twin)
     assert pkg.utils.q88_to_float(xq).sub(x).abs().max() <= 1 / 256
+
+
+def test_quantize_helpers_on_the_device_match_reference(ref_channel):
+    """compute_scale / quantize_tensor / dequantize_tensor (utils/quantization.py:73-161) as libofdmgan kernels, bit-exact against the
+    values recorded from the reference, for per-tensor and per-channel scales and for a channel dimension that is not the first."""
+    import ofdm_gan_sr_b200.utils as utils
+    r = ref_channel
+    t = torch.as_tensor(r["qt_in"]).cuda()
+    assert np.array_equal(utils.quantize_tensor(t, torch.tensor(1.0 / 128), 8).cpu().numpy(), r["qt_q17"])
+    scale = utils.compute_scale(t, 8)
+    assert scale.is_cuda and scale.dim() == 0 and float(scale) == float(r["qt_scale"])
+    q = utils.quantize_tensor(t, scale, 8)
+    assert np.array_equal(q.cpu().numpy(), r["qt_q8"])
+    assert np.array_equal(utils.dequantize_tensor(q, scale).cpu().numpy(), r["qt_deq"])
+    w = torch.as_tensor(r["qt_w"]).cuda()
+    ws = utils.compute_scale(w, 8, per_channel=True, channel_dim=0)
+    assert ws.shape == r["qt_w_scale"].shape and np.array_equal(ws.cpu().numpy(), r["qt_w_scale"])
+    assert np.array_equal(utils.quantize_tensor(w, ws, 8).cpu().numpy(), r["qt_w_q"])
+    # another channel dimension, large tensor: the same numbers as the host expression
+    x = torch.randn(6, 40, 33, device="cuda") * 3
+    for dim in (0, 1, 2):
+        s_dev = utils.compute_scale(x, 6, per_channel=True, channel_dim=dim)
+        s_host = utils.compute_scale(x.cpu(), 6, per_channel=True, channel_dim=dim)
+        assert torch.equal(s_dev.cpu(), s_host)
+        q_dev, q_host = utils.quantize_tensor(x, s_dev, 6), utils.quantize_tensor(x.cpu(), s_host, 6)
+        assert torch.equal(q_dev.cpu(), q_host)
+        assert torch.equal(utils.dequantize_tensor(q_dev, s_dev).cpu(), utils.dequantize_tensor(q_host, s_host))
+    fq = utils.FakeQuantize(8, per_channel=False).cuda().train()
+    y = fq(t.clone().requires_grad_(True))
+    assert torch.allclose(y.detach().cpu(), torch.as_tensor(r["qt_deq"]), atol=1e-7)
