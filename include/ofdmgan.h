@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 8
+#define OFDMGAN_ABI_VERSION 9
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -186,6 +186,10 @@ int ofdmgan_philox_blocks(uint64_t seed, uint64_t ctr0, uint32_t c2, uint32_t c3
  * constellation index = bits MSB first; QAM16/64 point = (levels[idx % sqrtM] + j levels[idx / sqrtM]) / norm (np.meshgrid order);
  * hard decisions pick the nearest point, ties to the lowest index. */
 int ofdmgan_qam_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, int bits_per_symbol, void* stream);
+/* np.unpackbits / np.packbits (MSB first): the pixel-byte <-> bit step of ImageOFDMConverter, utils/ofdm_utils.py:910,986.
+ * bits are one 0/1 value per byte, 8 * n_bytes of them. */
+int ofdmgan_unpackbits(const uint8_t* bytes_dev, int64_t n_bytes, uint8_t* bits_dev, void* stream);
+int ofdmgan_packbits(const uint8_t* bits_dev, int64_t n_bytes, uint8_t* bytes_dev, void* stream);
 int ofdmgan_qam_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_symbols, int bits_per_symbol, void* stream);
 /* replaces QAMModulator('QPSK').modulate, utils/ofdm_utils.py:163-193: bits_dev[2n] (0/1 bytes, MSB first) -> sym_dev[n] */
 int ofdmgan_qpsk_modulate(const uint8_t* bits_dev, float* sym_dev, int64_t n_symbols, void* stream);

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "ofdmgan_chan_draws": (ctypes.c_int, [c_p, c_u64, c_u64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p]),
     "ofdmgan_philox_blocks": (ctypes.c_int, [c_u64, c_u64, ctypes.c_uint32, ctypes.c_uint32, c_p, c_i64, c_p]),
     "ofdmgan_chan_fade_draws": (ctypes.c_int, [c_p, c_u64, c_u64, c_p, c_i64, c_p]),
+    "ofdmgan_unpackbits": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),
+    "ofdmgan_packbits": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),
     "ofdmgan_qam_modulate": (ctypes.c_int, [c_p, c_p, c_i64, ctypes.c_int, c_p]),
     "ofdmgan_qam_demodulate": (ctypes.c_int, [c_p, c_p, c_i64, ctypes.c_int, c_p]),
     "ofdmgan_qpsk_modulate": (ctypes.c_int, [c_p, c_p, c_i64, c_p]),
@@ -108,7 +110,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 8:
+        if L.ofdmgan_abi_version() != 9:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

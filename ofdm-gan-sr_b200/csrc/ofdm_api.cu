@@ -101,6 +101,19 @@ __device__ __forceinline__ void fft_any(float (&re)[N], float (&im)[N]) {
     }
 }
 
+__global__ void k_unpackbits(const uint8_t* __restrict__ bytes, int64_t n_bits, uint8_t* __restrict__ bits) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_bits; i += (int64_t)gridDim.x * blockDim.x)
+        bits[i] = (bytes[i >> 3] >> (7 - (int)(i & 7))) & 1u;
+}
+__global__ void k_packbits(const uint8_t* __restrict__ bits, int64_t n_bytes, uint8_t* __restrict__ bytes) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_bytes; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) v = (v << 1) | (bits[i * 8 + b] != 0 ? 1u : 0u);
+        bytes[i] = (uint8_t)v;
+    }
+}
+
 __device__ __forceinline__ bool is_pilot(int k, int spacing) { return spacing > 0 && (k % spacing) == 0; }
 
 // :281-329.  One OFDM symbol per thread.
@@ -178,6 +191,23 @@ int ofdmgan_qpsk_demodulate(const float* sym_dev, uint8_t* bits_dev, int64_t n_s
     if (n_symbols == 0) return 0;
     if (!bits_dev || !sym_dev || (reinterpret_cast<uintptr_t>(bits_dev) & 1u) || (reinterpret_cast<uintptr_t>(sym_dev) & 7u)) return OFDMGAN_E_ARG;
     k_qpsk_demod<<<grid_for(n_symbols, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(sym_dev), bits_dev, n_symbols);
+    return (int)cudaGetLastError();
+}
+
+// np.unpackbits / np.packbits (MSB first), the byte <-> bit step of ImageOFDMConverter (utils/ofdm_utils.py:910, :986)
+int ofdmgan_unpackbits(const uint8_t* bytes_dev, int64_t n_bytes, uint8_t* bits_dev, void* stream) {
+    if (n_bytes < 0) return OFDMGAN_E_ARG;
+    if (n_bytes == 0) return 0;
+    if (!bytes_dev || !bits_dev) return OFDMGAN_E_ARG;
+    k_unpackbits<<<grid_for(n_bytes * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(bytes_dev, n_bytes * 8, bits_dev);
+    return (int)cudaGetLastError();
+}
+
+int ofdmgan_packbits(const uint8_t* bits_dev, int64_t n_bytes, uint8_t* bytes_dev, void* stream) {
+    if (n_bytes < 0) return OFDMGAN_E_ARG;
+    if (n_bytes == 0) return 0;
+    if (!bytes_dev || !bits_dev) return OFDMGAN_E_ARG;
+    k_packbits<<<grid_for(n_bytes, 256, 8), 256, 0, (cudaStream_t)stream>>>(bits_dev, n_bytes, bytes_dev);
     return (int)cudaGetLastError();
 }
 

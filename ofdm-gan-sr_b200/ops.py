@@ -341,6 +341,26 @@ def _c64(t, device=None):
     return t.to(device=device if device is not None else t.device, dtype=torch.complex64).contiguous()
 
 
+def unpackbits(bytes_):
+    """uint8 CUDA tensor -> uint8 0/1 tensor, 8 per byte, MSB first (np.unpackbits)."""
+    b = bytes_.to(torch.uint8).contiguous().view(-1)
+    if not b.is_cuda:
+        raise OfdmGanError("expected a CUDA tensor: libofdmgan has no CPU path")
+    bits = torch.empty(b.numel() * 8, dtype=torch.uint8, device=b.device)
+    check(_lib.lib().ofdmgan_unpackbits(dptr(b), b.numel(), dptr(bits), stream_ptr(b.device)))
+    return bits
+
+
+def packbits(bits):
+    """0/1 uint8 CUDA tensor (a multiple of 8 long) -> bytes, MSB first (np.packbits)."""
+    b = bits.to(torch.uint8).contiguous().view(-1)
+    if not b.is_cuda or b.numel() % 8:
+        raise OfdmGanError("packbits needs a CUDA tensor whose length is a multiple of 8")
+    out = torch.empty(b.numel() // 8, dtype=torch.uint8, device=b.device)
+    check(_lib.lib().ofdmgan_packbits(dptr(b), out.numel(), dptr(out), stream_ptr(b.device)))
+    return out
+
+
 def qam_modulate(bits, bits_per_symbol):
     """bits: uint8 CUDA tensor of 0/1 (MSB first) -> complex64 symbols; bits_per_symbol 2 (QPSK), 4 (QAM16) or 6 (QAM64)."""
     if not bits.is_cuda:

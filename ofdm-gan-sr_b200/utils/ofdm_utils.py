@@ -238,8 +238,7 @@ class ImageOFDMConverter:
 
     def _signal(self, pixels_dev: torch.Tensor) -> torch.Tensor:
         """uint8 pixels (CUDA, flat) -> complex64 OFDM signal padded / truncated to frame_length"""
-        shifts = torch.arange(7, -1, -1, device=pixels_dev.device, dtype=torch.uint8)
-        bits = ((pixels_dev[:, None] >> shifts) & 1).reshape(-1)                 # np.unpackbits: MSB first
+        bits = ops.unpackbits(pixels_dev)                                        # np.unpackbits: MSB first
         sig = self.ofdm.modulate(self.qam.modulate(bits))
         out = torch.zeros(self.frame_length, dtype=torch.complex64, device=sig.device)
         n = min(self.frame_length, sig.numel())
@@ -291,8 +290,7 @@ class ImageOFDMConverter:
             bits = bits[:need]
         else:
             bits = torch.cat([bits, torch.zeros(need - bits.numel(), dtype=torch.uint8, device=bits.device)])
-        weights = (1 << torch.arange(7, -1, -1, device=bits.device, dtype=torch.int32))
-        pixels = (bits.view(-1, 8).to(torch.int32) * weights).sum(dim=1).to(torch.uint8)      # np.packbits
+        pixels = ops.packbits(bits)                                              # np.packbits
         return pixels.cpu().numpy().reshape(original_shape)
 
     def to_tensor(self, iq_signal: np.ndarray) -> torch.Tensor:
