@@ -205,7 +205,7 @@ def run_reference(args, rank, saved_stdout):
     import oracle
     gp, _ = seed_params()
     cfg = oracle.make_cfg(**WORKLOAD)
-    cores = os.cpu_count()
+    cores = oracle.set_threads()                               # torchrun exports OMP_NUM_THREADS=1: take the whole host back
     t0 = time.perf_counter()
     oracle.sim_gen_metrics(cfg, 0, 1 << 17, gparams=gp, seed=1)
     rate = (1 << 17) / (time.perf_counter() - t0)
@@ -546,6 +546,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         import oracle                                            # checker / CPU baseline leg only
         ocfg = oracle.make_cfg(**WORKLOAD)
+        cpu_threads = oracle.set_threads()
         t0 = time.perf_counter()
         oracle.sim_gen_metrics(ocfg, 0, 1 << 17, gparams=gp_h, seed=1)
         rate = (1 << 17) / (time.perf_counter() - t0)
@@ -553,7 +554,7 @@ def main():
         t0 = time.perf_counter()
         om = oracle.sim_gen_metrics(ocfg, 0, sample, gparams=gp_h, seed=1)
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": sample / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+        cpu_baseline = {"value": sample / dt, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
                         "sample": f"{sample} frames of the same workload, oracle/channel.c + fp32_models.c with OpenMP on all host cores"}
         # the same sample through the GPU path must tell the same story (parity spot check inside the bench)
         gm = ops.sim_gen_metrics(cfg, sample, gparams=gp_d, seed=1).cpu().numpy()

@@ -148,6 +148,13 @@ def disc_fwd_q(cand, cond, wrom, brom, mode):
     return score
 
 
+def set_threads(n=None):
+    """Give the C restatement n OpenMP threads (default: every core this process may run on).  torchrun exports OMP_NUM_THREADS=1
+    to its workers; the CPU baseline legs of bench.py call this so that they still use the whole host.  Returns the count used."""
+    n = int(n or len(os.sched_getaffinity(0)))
+    return int(lib().oracle_set_threads(n))
+
+
 def digest_i16(y):
     y = np.ascontiguousarray(y, dtype=np.int16)
     s, x = ctypes.c_uint64(0), ctypes.c_uint64(0)

@@ -407,3 +407,12 @@ int oracle_equalize(const float* noisy, const float* clean, const float* snr_db,
     for (int64_t b = 0; b < B; ++b) oracle_equalize_frame(noisy + 32 * b, clean + 32 * b, snr_db ? (double)snr_db[b] : 20.0, method, est + 32 * b);
     return 0;
 }
+
+/* Thread count of this library's OpenMP regions (bench.py's CPU-baseline legs: torchrun exports OMP_NUM_THREADS=1 to its workers).
+ * Lives here so that it reaches whichever OpenMP runtime this shared object is bound to. */
+#ifdef _OPENMP
+#include <omp.h>
+int oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int oracle_set_threads(int n) { (void)n; return 1; }
+#endif
