@@ -520,13 +520,19 @@ def main():
         barrier()
         t0 = time.perf_counter()
         prefetch(0)
+        ticket = None
         for i in range(K):
             if i + 1 < K:
                 prefetch(i + 1)
             torch.cuda.current_stream().wait_event(ready[i % 2])
             trainer.step(*bufs[i % 2])
             freed[i % 2].record()
-            trainer.stats()
+            nxt = trainer.request_stats()                        # D2H of this step's losses into pinned memory, asynchronous
+            if ticket is not None:
+                trainer.collect_stats(ticket)                    # the previous step's losses are read while this step runs
+            ticket = nxt
+        last_stats = trainer.collect_stats(ticket)
+        assert np.isfinite(last_stats["d_loss"])
         barrier()
         e2e_train = Bt * world * K / max_over_ranks(time.perf_counter() - t0)
         also["train"] = {"samples_per_s": Bt * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": Bt, "n_critic": 5,

@@ -179,13 +179,35 @@ class CWGANGPStep:
         self.g_steps += 1
         self._reduce_and_update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self.g_steps)
 
+    def _packed_stats(self):
+        d = self._dout[:, D_NPARAMS:D_NPARAMS + 5]
+        g = self._gout[G_NPARAMS:G_NPARAMS + 3]
+        return torch.cat([d.reshape(-1), g])
+
+    def request_stats(self):
+        """Start the device->host copy of this step's statistics into pinned memory without waiting for it: a training loop logs
+        the previous step's numbers (`collect_stats`) while the GPU runs the next one, instead of draining the stream every step."""
+        if getattr(self, "_pin", None) is None:
+            self._pin = [torch.empty(self.n_critic * 5 + 3, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._pin_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._pin_i = 0
+        i = self._pin_i = 1 - self._pin_i
+        self._pin[i].copy_(self._packed_stats(), non_blocking=True)
+        self._pin_ev[i].record()
+        return i
+
+    def collect_stats(self, ticket):
+        """The statistics requested under `ticket` (waits only for that copy)."""
+        self._pin_ev[ticket].synchronize()
+        return self._unpack(self._pin[ticket].clone())
+
     def stats(self):
         """The scalars train.py:255-261,301-305 log, from the last step: one device->host copy."""
         if self.comm is not None:
             self.comm.check()
-        d = self._dout[:, D_NPARAMS:D_NPARAMS + 5]
-        g = self._gout[G_NPARAMS:G_NPARAMS + 3]
-        packed = torch.cat([d.reshape(-1), g]).cpu()
+        return self._unpack(self._packed_stats().cpu())
+
+    def _unpack(self, packed):
         last = packed[(self.n_critic - 1) * 5:self.n_critic * 5] if self.n_critic else torch.zeros(5)
         gs = packed[self.n_critic * 5:]
         return {"d_loss": float(last[0]), "wasserstein_distance": float(last[1]), "gradient_penalty": float(last[2]),

@@ -65,3 +65,16 @@ def test_adam_ctr_matches_host_stepped_adam(setup):
     assert int(ctr) == 40
     assert float((pa - pb).abs().max()) <= 1e-6 * float(pa.abs().max())
     assert torch.equal(ma, mb) and torch.equal(va, vb)         # the moments do not depend on the bias corrections
+
+
+def test_asynchronous_stats_equal_synchronous(setup):
+    ops, Step, gp, dp = setup
+    t = Step(gp, dp)
+    tickets = []
+    want = []
+    for clean, noisy in _batches(ops, 2048, 3):
+        t.step(clean, noisy)
+        tickets.append(t.request_stats())
+        want.append(t.stats())
+        got = t.collect_stats(tickets[-1])
+        assert got == want[-1]
