@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 9
+#define OFDMGAN_ABI_VERSION 10
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -264,6 +264,16 @@ int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const fl
 int ofdmgan_critic_step_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed,
                             uint64_t sample0, const int32_t* alpha_iter_dev, const float* dparams521, float gp_weight,
                             float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, void* stream);
+/* Single-GPU form of one WHOLE critic iteration of train.py:201-261 (loss, backward, optimizer_D.step()): the kernel of
+ * ofdmgan_critic_step_ctr, then ONE tail launch that reduces the gradients, applies Adam to dparams521_dev / m_dev / v_dev in
+ * place (step count t = *step_dev + 1, stored back; *step_dev before the call is also the Philox alpha counter) and refreshes
+ * the kernel's weight image.  out_dev as for ofdmgan_critic_step.  image_is_current != 0: the previous call on this stream
+ * was this function on the same parameters (its tail already installed their image), so the image refresh at entry is skipped;
+ * pass 0 whenever anything else may have written the parameters. */
+int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed,
+                             uint64_t sample0, int32_t* step_dev, float* dparams521_dev, float* m_dev, float* v_dev, double lr,
+                             double beta1, double beta2, double eps, float gp_weight, float leaky_slope, int64_t B,
+                             float* out_dev, int image_is_current, void* stream);
 /* replaces the loss + backward of CWGANGPTrainer.train_generator, train.py:285-298.
  * out_dev: 264 floats = grad[258] of g_loss w.r.t. theta_G (local sum, scaled for the global batch), stats[3] =
  * g_loss, adv_loss, rec_loss partial sums, 3 pad.  fake_out_dev (may be NULL) receives G(noisy). */

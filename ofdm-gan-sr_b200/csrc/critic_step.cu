@@ -146,6 +146,55 @@ __global__ void __launch_bounds__(1024) k_finalize_critic2(const float* __restri
     }
 }
 
+// Single-GPU tail of a critic iteration: the fixed-order reduction of k_finalize_critic2, and - in the block that finishes last -
+// Adam on the 521 parameters (step count in device memory, as k_adam_ctr) and the refresh of the weight-image staging buffer.
+// One launch instead of finalize + Adam + prep_d_image.
+__global__ void __launch_bounds__(1024) k_critic_tail(const float* __restrict__ partials, int nblocks, double inv_b, double gp_weight,
+                                                      float* __restrict__ out, float* __restrict__ p, float* __restrict__ m,
+                                                      float* __restrict__ v, double lr, double b1, double b2, double eps,
+                                                      int32_t* __restrict__ step_dev, unsigned int* __restrict__ arrivals,
+                                                      float* __restrict__ image) {
+    __shared__ double red[32 * 32], total[32];
+    __shared__ unsigned int ticket;
+    __shared__ float pnew[OFDMGAN_D_NPARAMS];
+    const int grp = blockIdx.x;
+    reduce_group_rows(partials, nblocks, CS_SLOTS, grp, red, total);
+    if (threadIdx.x < 32) {
+        const int i = cs_param_of(grp, threadIdx.x);
+        if (i >= 0) out[i] = (float)(total[threadIdx.x] * inv_b);
+    }
+    if (grp == 1 && threadIdx.x == 0) {
+        float* stats = out + OFDMGAN_D_NPARAMS;
+        const double dr = total[CS_SREAL - 32] * inv_b, df = total[CS_SFAKE - 32] * inv_b, gp = total[CS_SGP - 32] * inv_b;
+        stats[0] = (float)(df - dr + gp_weight * gp);
+        stats[1] = (float)(dr - df);
+        stats[2] = (float)gp;
+        stats[3] = (float)dr;
+        stats[4] = (float)df;
+        stats[5] = 0.f;
+        stats[6] = 0.f;
+    }
+    __threadfence();                                             // this block's gradients are visible before it takes its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(arrivals, 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+    // last block: every group's gradients are in `out`
+    if (threadIdx.x == 0) *arrivals = 0u;
+    const int t = *step_dev + 1;
+    const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);
+    const int i = threadIdx.x;
+    if (i < OFDMGAN_D_NPARAMS) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_one(pi, mi, vi, __ldcg(out + i), c);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        pnew[i] = pi;
+    }
+    __syncthreads();
+    if (i == 0) *step_dev = t;
+    for (int j = i; j < OG_D_IMG; j += blockDim.x) image[j] = d_img_entry(pnew, j);
+}
+
 }  // namespace og
 
 using namespace og;
@@ -226,6 +275,49 @@ int ofdmgan_critic_step_ctr(const float* clean_dev, const float* noisy_dev, cons
     if (!alpha_iter_dev) return OFDMGAN_E_ARG;
     return critic_step_impl(clean_dev, noisy_dev, fake_dev, nullptr, seed, sample0, 0u, alpha_iter_dev, dparams521, gp_weight,
                             leaky_slope, B_local, B_global, out_dev, stream);
+}
+
+int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed, uint64_t sample0,
+                             int32_t* step_dev, float* dparams521_dev, float* m_dev, float* v_dev, double lr, double beta1, double beta2,
+                             double eps, float gp_weight, float leaky_slope, int64_t B, float* out_dev, int image_is_current,
+                             void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!clean_dev || !noisy_dev || !fake_dev || !step_dev || !dparams521_dev || !m_dev || !v_dev || !out_dev || B < 1) return OFDMGAN_E_ARG;
+    if (!aligned16(clean_dev) || !aligned16(noisy_dev) || !aligned16(fake_dev)) return OFDMGAN_E_ARG;
+    int rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    const int slot = 0;
+    // image_is_current: the previous call on this stream was this function on the same parameters, so the constant bank already
+    // holds the image of dparams521_dev (the tail below refreshed and committed it)
+    if (!image_is_current && (rc = upload_d(dparams521_dev, slot, s))) return rc;
+    const int grid = grid_for(B * 3, OG_THREADS, CRITIC_PER_SM);
+    void *partials = nullptr, *arrivals = nullptr;
+    if ((rc = scratch_for_slot(slot, (size_t)grid * CS_SLOTS * sizeof(float), 6, &partials))) return rc;
+    if ((rc = scratch_for_slot(slot, 256, 8, &arrivals))) return rc;
+    static bool zeroed[64] = {false};
+    int dev = 0;
+    OG_CHECK(cudaGetDevice(&dev));
+    if (!zeroed[dev]) {                                          // the tail leaves the counter at zero; only the very first use needs this
+        OG_CHECK(cudaMemsetAsync(arrivals, 0, 256, s));
+        zeroed[dev] = true;
+    }
+    float* image = nullptr;
+    if ((rc = d_image_staging(slot, &image))) return rc;
+    CriticArgs a{};
+    a.real = clean_dev; a.cond = noisy_dev; a.fake = fake_dev; a.alpha = nullptr;
+    a.keys = philox_keys(seed);
+    a.sample0 = sample0; a.alpha_iter = 0u; a.alpha_iter_dev = step_dev;
+    a.B = B; a.slot = slot; a.slope = leaky_slope; a.gp_scale = gp_weight;
+    a.want_grads = 1;
+    a.partials = (float*)partials;
+    a.norms = nullptr;
+    k_critic2<true><<<grid, OG_THREADS, 0, s>>>(a);
+    OG_CHECK(cudaGetLastError());
+    k_critic_tail<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B, (double)gp_weight, out_dev, dparams521_dev, m_dev,
+                                         v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, image);
+    OG_CHECK(cudaGetLastError());
+    return commit_d_image(slot, s);
 }
 
 }  // extern "C"

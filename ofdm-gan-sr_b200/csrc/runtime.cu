@@ -8,8 +8,8 @@ namespace og {
 
 static std::mutex g_mu;
 static DeviceInfo g_dev[64];
-static void* g_scratch[64][OG_NSLOT][8];
-static size_t g_scratch_bytes[64][OG_NSLOT][8];
+static void* g_scratch[64][OG_NSLOT][12];
+static size_t g_scratch_bytes[64][OG_NSLOT][12];
 
 const DeviceInfo& device_info(int* err) {
     static DeviceInfo none;
@@ -80,7 +80,7 @@ CallGuard::~CallGuard() { g_call_mu.unlock(); }
 int scratch_for_slot(int slot, size_t bytes, int which, void** ptr) {
     int d = -1;
     OG_CHECK(cudaGetDevice(&d));
-    if (d < 0 || d >= 64 || slot < 0 || slot >= OG_NSLOT || which < 0 || which >= 8) return OFDMGAN_E_ARG;
+    if (d < 0 || d >= 64 || slot < 0 || slot >= OG_NSLOT || which < 0 || which >= 12) return OFDMGAN_E_ARG;
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_scratch_bytes[d][slot][which] < bytes) {
         // growth only happens on the first calls (sizes are bounded by the grid); never inside stream capture

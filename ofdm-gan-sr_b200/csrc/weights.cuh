@@ -82,20 +82,24 @@ static __global__ void prep_g_image(const float* __restrict__ p, float* __restri
     img[i] = g_img_base(p, base + ((2 * o2 + h) * IC + ic) * K + k);
 }
 
-static __global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
-    const int i = threadIdx.x + blockIdx.x * blockDim.x;
-    if (i >= OG_D_IMG) return;
-    if (i < DI2_C1) { img[i] = i < OFDMGAN_D_NPARAMS ? p[i] : 0.f; return; }
+// entry i of the D image from the raw parameters
+__device__ __forceinline__ float d_img_entry(const float* __restrict__ p, int i) {
+    if (i < DI2_C1) return i < OFDMGAN_D_NPARAMS ? p[i] : 0.f;
     if (i < DI2_C2) {                                            // ((o2*4 + ic)*3 + k)*2 + h <- conv1[2*o2+h][ic][k]
         const int e = i - DI2_C1, h = e & 1, r = e >> 1, k = r % 3, ic = (r / 3) % 4, o2 = r / 12;
-        img[i] = p[DP_C1_W + ((2 * o2 + h) * 4 + ic) * 3 + k];
-    } else if (i < DI2_C2T) {                                    // ((o2*8 + ic)*3 + k)*2 + h <- conv2[2*o2+h][ic][k]
-        const int e = i - DI2_C2, h = e & 1, r = e >> 1, k = r % 3, ic = (r / 3) % 8, o2 = r / 24;
-        img[i] = p[DP_C2_W + ((2 * o2 + h) * 8 + ic) * 3 + k];
-    } else {                                                     // ((oc*4 + i2)*3 + k)*2 + h <- conv2[oc][2*i2+h][k]
-        const int e = i - DI2_C2T, h = e & 1, r = e >> 1, k = r % 3, i2 = (r / 3) % 4, oc = r / 12;
-        img[i] = p[DP_C2_W + (oc * 8 + 2 * i2 + h) * 3 + k];
+        return p[DP_C1_W + ((2 * o2 + h) * 4 + ic) * 3 + k];
     }
+    if (i < DI2_C2T) {                                           // ((o2*8 + ic)*3 + k)*2 + h <- conv2[2*o2+h][ic][k]
+        const int e = i - DI2_C2, h = e & 1, r = e >> 1, k = r % 3, ic = (r / 3) % 8, o2 = r / 24;
+        return p[DP_C2_W + ((2 * o2 + h) * 8 + ic) * 3 + k];
+    }
+    const int e = i - DI2_C2T, h = e & 1, r = e >> 1, k = r % 3, i2 = (r / 3) % 4, oc = r / 12;   // ((oc*4 + i2)*3 + k)*2 + h <- conv2[oc][2*i2+h][k]
+    return p[DP_C2_W + (oc * 8 + 2 * i2 + h) * 3 + k];
+}
+
+static __global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i < OG_D_IMG) img[i] = d_img_entry(p, i);
 }
 
 // params258 may be a host or a device pointer
@@ -110,6 +114,22 @@ static int upload_g(const float* params258, int slot, cudaStream_t s) {
     OG_CHECK(cudaGetLastError());
     OG_CHECK(cudaMemcpyToSymbolAsync(c_g, img, OG_G_IMG * sizeof(float), 0,
                                      cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// the staging buffer of the D image (device), for kernels that refresh the image themselves
+static int d_image_staging(int slot, float** img) {
+    void* p = nullptr;
+    int rc = scratch_for_slot(slot, OG_D_IMG * sizeof(float), 3, &p);
+    *img = (float*)p;
+    return rc;
+}
+// copy an already prepared staging image into the constant bank
+static int commit_d_image(int slot, cudaStream_t s) {
+    float* img = nullptr;
+    int rc = d_image_staging(slot, &img);
+    if (rc) return rc;
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_d, img, OG_D_IMG * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

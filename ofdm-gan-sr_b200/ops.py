@@ -484,6 +484,19 @@ def critic_step(clean, noisy, fake, dparams, alpha=None, seed=0, sample0=0, alph
     return out
 
 
+def critic_train(clean, noisy, fake, dparams, m, v, step_dev, lr, beta1, beta2, eps, seed=0, sample0=0, gp_weight=10.0, slope=0.2, out=None,
+                 image_is_current=False):
+    """One whole critic iteration on one GPU (loss, backward, Adam in place on dparams / m / v, weight-image refresh): two launches.
+    step_dev: int32 CUDA tensor (1 element) = optimiser steps taken so far; doubles as the Philox alpha counter."""
+    clean, noisy, fake = frames(clean), frames(noisy), frames(fake)
+    if out is None:
+        out = torch.empty(CRITIC_OUT, dtype=torch.float32, device=clean.device)
+    check(_lib.lib().ofdmgan_critic_train_ctr(dptr(clean), dptr(noisy), dptr(fake), seed, sample0, dptr(step_dev), dptr(dparams), dptr(m),
+                                              dptr(v), lr, beta1, beta2, eps, gp_weight, slope, clean.shape[0], dptr(out),
+                                              1 if image_is_current else 0, stream_ptr(clean.device)))
+    return out
+
+
 def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, slope=0.2, b_global=None, out=None,
              fake_out=None):
     """-> out[264] = grad[258] (local sum / B_global), stats[3] (g_loss, adv, rec), 3 pad."""

@@ -78,3 +78,24 @@ def test_asynchronous_stats_equal_synchronous(setup):
         want.append(t.stats())
         got = t.collect_stats(tickets[-1])
         assert got == want[-1]
+
+
+def test_fused_critic_iteration_is_bitwise_the_unfused_one(setup):
+    """ofdmgan_critic_train_ctr (kernel + one tail launch) == ofdmgan_critic_step_ctr + ofdmgan_adam_ctr, bit for bit, over several
+    iterations, with and without the image_is_current shortcut."""
+    ops, _, gp, dp = setup
+    clean, noisy = _batches(ops, 3000, 1)[0]
+    fake = ops.gen_fwd_f32(noisy, gp)
+    dev = clean.device
+    d0 = torch.as_tensor(dp).to(dev)
+    a = dict(d=d0.clone(), m=torch.zeros_like(d0), v=torch.zeros_like(d0), ctr=torch.zeros(1, dtype=torch.int32, device=dev))
+    b = dict(d=d0.clone(), m=torch.zeros_like(d0), v=torch.zeros_like(d0), ctr=torch.zeros(1, dtype=torch.int32, device=dev))
+    for it in range(6):
+        oa = ops.critic_step(clean, noisy, fake, a["d"], seed=11, gp_weight=10.0, alpha_iter_dev=a["ctr"])
+        ops.adam(a["d"], a["m"], a["v"], oa, 2e-4, 0.0, 0.9, 1e-8, 0, step_dev=a["ctr"])
+        ob = ops.critic_train(clean, noisy, fake, b["d"], b["m"], b["v"], b["ctr"], 2e-4, 0.0, 0.9, 1e-8, seed=11, gp_weight=10.0,
+                              image_is_current=it % 3 != 0)
+        assert torch.equal(oa, ob), it
+        for k in ("d", "m", "v", "ctr"):
+            assert torch.equal(a[k], b[k]), (it, k)
+    assert int(b["ctr"]) == 6
