@@ -92,6 +92,7 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 fma2_rd(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 // a pair of adjacent floats of a constant image (8-byte aligned index)
 __device__ __forceinline__ f32x2 ldc2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }
 

@@ -16,7 +16,8 @@ constexpr int DQ_RAW = 0;        // ROM[256 .. 753]   index = address - 256 (con
 constexpr int DQ_BIAS = 512;     // bias ROM[32 .. 56] index = address - 32  (conv1 0, conv2 8, dense 24)
 constexpr int DQ2_C1 = 544;      // conv1 channel pairs  [((o2*4 + ic)*3 + k)*2 + h]
 constexpr int DQ2_C2 = 640;      // conv2 channel pairs  [((o2*8 + ic)*3 + k)*2 + h]
-constexpr int OG_DQ_IMG = 1024;
+constexpr int DQ_BIASM = 1024;   // 1.5*2^23 + bias (exact): accumulator start values, same indexing as DQ_BIAS
+constexpr int OG_DQ_IMG = 1056;
 static __constant__ __align__(16) float c_dq[OG_DQ_IMG];
 
 static int upload_dq(const int8_t* wrom_host, const int16_t* brom_host, cudaStream_t s) {
@@ -24,6 +25,7 @@ static int upload_dq(const int8_t* wrom_host, const int16_t* brom_host, cudaStre
     for (int i = 0; i < OG_DQ_IMG; ++i) img[i] = 0.f;
     for (int a = 256; a < 754; ++a) img[DQ_RAW + a - 256] = (float)wrom_host[a] * (1.0f / 128.0f);
     for (int a = 32; a <= 56; ++a) img[DQ_BIAS + a - 32] = (float)brom_host[a];
+    for (int a = 32; a <= 56; ++a) img[DQ_BIASM + a - 32] = 12582912.0f + (float)brom_host[a];
     auto pairs = [&](int dst, int wa, int OC, int IC) {
         for (int o2 = 0; o2 < OC / 2; ++o2)
             for (int ic = 0; ic < IC; ++ic)
@@ -48,7 +50,7 @@ __device__ __forceinline__ float critic_q_spec(const float* __restrict__ Q, cons
     for (int o2 = 0; o2 < 4; ++o2)
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            f32x2 acc = magic2;
+            f32x2 acc = ldc2(Q + DQ_BIASM + 2 * o2);
 #pragma unroll
             for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
@@ -56,17 +58,15 @@ __device__ __forceinline__ float critic_q_spec(const float* __restrict__ Q, cons
                     const int i = 2 * p + k - 1;
                     if (i >= 0) acc = fxacc2(x[ic][i], ldc2(Q + DQ2_C1 + ((o2 * 4 + ic) * 3 + k) * 2), acc);
                 }
-            float lo, hi;
-            upk2(acc, lo, hi);
-            c1[2 * o2][p] = fx_finish(lo, Q[DQ_BIAS + 2 * o2], true);
-            c1[2 * o2 + 1][p] = fx_finish(hi, Q[DQ_BIAS + 2 * o2 + 1], true);
+            fx_finish2(acc, true, c1[2 * o2][p], c1[2 * o2 + 1][p]);
         }
     float dense = FX_MAGIC;
     // rolled over the channel pair: the 48 weights of a pair are loaded inside the iteration that uses them
 #pragma unroll 1
     for (int o2 = 0; o2 < 8; ++o2) {
         const float* W2 = Q + DQ2_C2 + o2 * 8 * 3 * 2;
-        f32x2 acc[4] = {magic2, magic2, magic2, magic2};
+        const f32x2 b2 = ldc2(Q + DQ_BIASM + 8 + 2 * o2);
+        f32x2 acc[4] = {b2, b2, b2, b2};
 #pragma unroll
         for (int ic = 0; ic < 8; ++ic)
 #pragma unroll
@@ -79,13 +79,12 @@ __device__ __forceinline__ float critic_q_spec(const float* __restrict__ Q, cons
                 }
             }
         float pool_lo = 0.f, pool_hi = 0.f;
-        const float b_lo = Q[DQ_BIAS + 8 + 2 * o2], b_hi = Q[DQ_BIAS + 8 + 2 * o2 + 1];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             float lo, hi;
-            upk2(acc[p], lo, hi);
-            pool_lo += fx_finish(lo, b_lo, true);
-            pool_hi += fx_finish(hi, b_hi, true);
+            fx_finish2(acc[p], true, lo, hi);
+            pool_lo += lo;
+            pool_hi += hi;
         }
         dense = fxacc(fx_wrap16(pool_lo), Q[DQ_RAW + 480 + 2 * o2], dense);
         dense = fxacc(fx_wrap16(pool_hi), Q[DQ_RAW + 480 + 2 * o2 + 1], dense);

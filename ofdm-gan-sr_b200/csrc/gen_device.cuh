@@ -129,6 +129,23 @@ __device__ __forceinline__ float fx_clip(float v) { return v > 256.f ? 255.f : (
 // Two output channels per FFMA2.RM: acc2 = fma.rm.f32x2((a, a), (w[oc], w[oc+1]), acc2) with the weight pair read from the
 // interleaved half of the Q image.
 __device__ __forceinline__ f32x2 fxacc2(float a, f32x2 w2, f32x2 acc2) { return fma2_rd(pk2(a, a), w2, acc2); }
+// Finish a channel pair whose accumulator started at MAGIC + bias (exact): leave the magic domain, saturate, LeakyReLU - the
+// subtracts and the two floor-FMAs of the activation packed (6 instead of 9 instructions per value).
+__device__ __forceinline__ void fx_finish2(f32x2 acc, bool act, float& lo, float& hi) {
+    const f32x2 nmagic2 = pk2(-FX_MAGIC, -FX_MAGIC);
+    upk2(add2(acc, nmagic2), lo, hi);
+    lo = fx_sat16(lo);
+    hi = fx_sat16(hi);
+    if (act) {
+        const f32x2 r2 = pk2(lo, hi);
+        f32x2 t2 = fma2_rd(r2, pk2(0.25f, 0.25f), pk2(FX_MAGIC, FX_MAGIC));
+        t2 = fma2_rd(r2, pk2(0.0625f, 0.0625f), t2);
+        float tl, th;
+        upk2(add2(t2, nmagic2), tl, th);
+        lo = lo < 0.f ? tl : lo;
+        hi = hi < 0.f ? th : hi;
+    }
+}
 
 __device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, const float (&x)[2][16], float (&y)[2][16]) {
     float a1[4][8], a2[8][4], sk[4][8];
@@ -137,7 +154,7 @@ __device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, cons
     for (int o2 = 0; o2 < 2; ++o2)
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            f32x2 acc = magic2;
+            f32x2 acc = ldc2(Q + QI_BIASM + 0 + 2 * o2);
 #pragma unroll
             for (int ic = 0; ic < 2; ++ic)
 #pragma unroll
@@ -145,16 +162,13 @@ __device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, cons
                     const int i = 2 * p + k - 1;
                     if (i >= 0) acc = fxacc2(x[ic][i], ldc2(Q + QI2_ENC + ((o2 * 2 + ic) * 3 + k) * 2), acc);
                 }
-            float lo, hi;
-            upk2(acc, lo, hi);
-            a1[2 * o2][p] = fx_finish(lo, Q[QI_BIAS + 0 + 2 * o2], true);
-            a1[2 * o2 + 1][p] = fx_finish(hi, Q[QI_BIAS + 0 + 2 * o2 + 1], true);
+            fx_finish2(acc, true, a1[2 * o2][p], a1[2 * o2 + 1][p]);
         }
 #pragma unroll
     for (int o2 = 0; o2 < 4; ++o2)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            f32x2 acc = magic2;
+            f32x2 acc = ldc2(Q + QI_BIASM + 4 + 2 * o2);
 #pragma unroll
             for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
@@ -162,17 +176,14 @@ __device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, cons
                     const int i = 2 * p + k - 1;
                     if (i >= 0) acc = fxacc2(a1[ic][i], ldc2(Q + QI2_BN + ((o2 * 4 + ic) * 3 + k) * 2), acc);
                 }
-            float lo, hi;
-            upk2(acc, lo, hi);
-            a2[2 * o2][p] = fx_finish(lo, Q[QI_BIAS + 4 + 2 * o2], true);
-            a2[2 * o2 + 1][p] = fx_finish(hi, Q[QI_BIAS + 4 + 2 * o2 + 1], true);
+            fx_finish2(acc, true, a2[2 * o2][p], a2[2 * o2 + 1][p]);
         }
     // per-tap floor does not commute with weight folding: evaluate the 3 taps on the upsampled signal
 #pragma unroll
     for (int o2 = 0; o2 < 2; ++o2)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            f32x2 acc = magic2;
+            f32x2 acc = ldc2(Q + QI_BIASM + 12 + 2 * o2);
 #pragma unroll
             for (int ic = 0; ic < 8; ++ic)
 #pragma unroll
@@ -181,18 +192,18 @@ __device__ __forceinline__ void gen_fwd_q_spec(const float* __restrict__ Q, cons
                     if (i >= 0 && i < 8) acc = fxacc2(a2[ic][i >> 1], ldc2(Q + QI2_DEC + ((o2 * 8 + ic) * 3 + k) * 2), acc);
                 }
             float lo, hi;
-            upk2(acc, lo, hi);
-            sk[2 * o2][q] = fx_sat16(fx_finish(lo, Q[QI_BIAS + 12 + 2 * o2], true) + a1[2 * o2][q]);
-            sk[2 * o2 + 1][q] = fx_sat16(fx_finish(hi, Q[QI_BIAS + 12 + 2 * o2 + 1], true) + a1[2 * o2 + 1][q]);
+            fx_finish2(acc, true, lo, hi);
+            sk[2 * o2][q] = fx_sat16(lo + a1[2 * o2][q]);
+            sk[2 * o2 + 1][q] = fx_sat16(hi + a1[2 * o2 + 1][q]);
         }
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-        f32x2 acc = magic2;
+        f32x2 acc = ldc2(Q + QI_BIASM + 16);
 #pragma unroll
         for (int ic = 0; ic < 4; ++ic) acc = fxacc2(sk[ic][p], ldc2(Q + QI2_OUT + ic * 2), acc);
         float lo, hi;
-        upk2(acc, lo, hi);
-        const float v0 = fx_clip(fx_finish(lo, Q[QI_BIAS + 16], false)), v1 = fx_clip(fx_finish(hi, Q[QI_BIAS + 17], false));
+        fx_finish2(acc, false, lo, hi);
+        const float v0 = fx_clip(lo), v1 = fx_clip(hi);
         y[0][2 * p] = v0; y[0][2 * p + 1] = v0;
         y[1][2 * p] = v1; y[1][2 * p + 1] = v1;
     }

@@ -42,6 +42,7 @@ constexpr int DI2_C1 = 528, DI2_C2 = 624, DI2_C2T = 1008;                 // 96 
 constexpr int OG_D_IMG = 1392;
 constexpr int OG_Q_IMG = 512;
 constexpr int QI_BIAS = 232;
+constexpr int QI_BIASM = 480;    // [18] 1.5*2^23 + bias: accumulator start values of the packed spec path (pairs stay adjacent)
 // second half of the Q image: the same weights with the two output channels of a pair interleaved, [oc/2][ic][k][2], so one
 // 64-bit uniform load feeds a packed FFMA2 (two output channels per instruction)
 constexpr int QI2_ENC = 256, QI2_BN = 280, QI2_DEC = 376, QI2_OUT = 472;     // 24 + 96 + 96 + 8 floats
@@ -153,6 +154,7 @@ static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot,
     for (int i = 0; i < OG_Q_IMG; ++i) img[i] = 0.f;
     for (int i = 0; i < 226; ++i) img[i] = (float)wrom_host[i] * (1.0f / 128.0f);
     for (int i = 0; i < 18; ++i) img[QI_BIAS + i] = (float)brom_host[i];
+    for (int i = 0; i < 18; ++i) img[QI_BIASM + i] = 12582912.0f + (float)brom_host[i];      // exact: |bias| < 2^15, ulp = 1
     auto pairs = [&](int dst, int wa, int OC, int IC, int K) {
         for (int o2 = 0; o2 < OC / 2; ++o2)
             for (int ic = 0; ic < IC; ++ic)
