@@ -69,6 +69,18 @@ err = float((runs["peer"][0] - runs["nccl"][0]).abs().max())
 assert err < 1e-6, err                                                   # same sums up to the order NCCL happens to use
 err = float((runs["peer+graph"][1] - runs["peer"][1]).abs().max()) / float(runs["peer"][1].abs().max())
 assert err < 1e-6, err                                                   # replayed graph == eager launches
+# ---- 3. the sweep: frame-sharded over the ranks == the whole range on one GPU (counts exact, sums to rounding)
+from ofdm_gan_sr_b200.sweep import run_benchmark, run_sweep  # noqa: E402
+cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=1000)
+total = 7 * 1000 * 37 + 13                                               # ragged on purpose
+sharded = run_sweep(cfg, total, gparams=gp, seed=9, device=dev)          # all ranks, all-reduced
+whole = ops.sim_gen_metrics(cfg, total, gparams=gp, seed=9, device=dev).cpu().numpy()
+assert np.array_equal(sharded[:, :, 0], whole[:, :, 0]) and sharded[:, :2, 0].sum() == 2 * total
+assert np.allclose(sharded[:, :2, 1:5], whole[:, :2, 1:5], rtol=5e-6, atol=0)      # fp32 per-thread partial sums regroup
+res = run_benchmark(gp, n_trials=5000, nonlinear=True, pa_saturation=0.8, device=dev, seed=4)
+every = [None] * world
+dist.all_gather_object(every, {m: {s: v["evm"] for s, v in res[m].items()} for m in res})
+assert all(e == every[0] for e in every)                                 # every rank holds the same table
 dist.barrier()
 if rank == 0:
     print("multi-gpu worker ok: world", world)
