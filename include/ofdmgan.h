@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 10
+#define OFDMGAN_ABI_VERSION 11
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -264,16 +264,18 @@ int ofdmgan_critic_step(const float* clean_dev, const float* noisy_dev, const fl
 int ofdmgan_critic_step_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed,
                             uint64_t sample0, const int32_t* alpha_iter_dev, const float* dparams521, float gp_weight,
                             float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, void* stream);
-/* Single-GPU form of one WHOLE critic iteration of train.py:201-261 (loss, backward, optimizer_D.step()): the kernel of
- * ofdmgan_critic_step_ctr, then ONE tail launch that reduces the gradients, applies Adam to dparams521_dev / m_dev / v_dev in
- * place (step count t = *step_dev + 1, stored back; *step_dev before the call is also the Philox alpha counter) and refreshes
- * the kernel's weight image.  out_dev as for ofdmgan_critic_step.  image_is_current != 0: the previous call on this stream
- * was this function on the same parameters (its tail already installed their image), so the image refresh at entry is skipped;
- * pass 0 whenever anything else may have written the parameters. */
+/* One WHOLE critic iteration of train.py:201-261 (loss, backward, optimizer_D.step()) in two launches: the kernel of
+ * ofdmgan_critic_step_ctr, then ONE tail launch that reduces the gradients, sums them over the data-parallel ranks through `comm`
+ * (NULL: single GPU), applies Adam to dparams521_dev / m_dev / v_dev in place (step count t = *step_dev + 1, stored back;
+ * *step_dev before the call is also the Philox alpha counter) and refreshes the kernel's weight image.  out_dev as for
+ * ofdmgan_critic_step (global sums when comm is given).  image_is_current != 0: the previous call on this stream was this
+ * function on the same parameters (its tail already installed their image), so the image refresh at entry is skipped; pass 0
+ * whenever anything else may have written the parameters. */
+typedef struct ofdmgan_comm ofdmgan_comm;
 int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed,
                              uint64_t sample0, int32_t* step_dev, float* dparams521_dev, float* m_dev, float* v_dev, double lr,
-                             double beta1, double beta2, double eps, float gp_weight, float leaky_slope, int64_t B,
-                             float* out_dev, int image_is_current, void* stream);
+                             double beta1, double beta2, double eps, float gp_weight, float leaky_slope, int64_t B_local,
+                             int64_t B_global, float* out_dev, int image_is_current, ofdmgan_comm* comm, void* stream);
 /* replaces the loss + backward of CWGANGPTrainer.train_generator, train.py:285-298.
  * out_dev: 264 floats = grad[258] of g_loss w.r.t. theta_G (local sum, scaled for the global batch), stats[3] =
  * g_loss, adv_loss, rec_loss partial sums, 3 pad.  fake_out_dev (may be NULL) receives G(noisy). */
@@ -299,7 +301,6 @@ int ofdmgan_adam_ctr(float* p_dev, float* m_dev, float* v_dev, const float* g_de
  * Setup: every rank calls ofdmgan_comm_create (allocates its exchange block, returns a 64-byte CUDA IPC handle), the host
  * side all-gathers the handles (torch.distributed), every rank calls ofdmgan_comm_connect with the world x 64 bytes.
  * All ranks must issue the same sequence of ofdmgan_allreduce_adam calls.  n <= 1024. */
-typedef struct ofdmgan_comm ofdmgan_comm;
 int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handle64);
 int ofdmgan_comm_connect(ofdmgan_comm* comm, const void* all_handles);
 int ofdmgan_comm_destroy(ofdmgan_comm* comm);

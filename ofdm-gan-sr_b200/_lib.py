@@ -57,7 +57,7 @@ _SIGNATURES = {
     "ofdmgan_disc_fwd_q": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, ctypes.c_int, c_p]),
     "ofdmgan_critic_step_ctr": (ctypes.c_int, [c_p, c_p, c_p, c_u64, c_u64, c_p, c_p, ctypes.c_float, ctypes.c_float, c_i64, c_i64, c_p, c_p]),
     "ofdmgan_critic_train_ctr": (ctypes.c_int, [c_p, c_p, c_p, c_u64, c_u64, c_p, c_p, c_p, c_p, ctypes.c_double, ctypes.c_double,
-                                                ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, c_i64, c_p, ctypes.c_int, c_p]),
+                                                ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, c_i64, c_i64, c_p, ctypes.c_int, c_p, c_p]),
     "ofdmgan_adam_ctr": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_double, c_p, ctypes.c_float, c_p]),
     "ofdmgan_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_p]),
@@ -112,7 +112,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 10:
+        if L.ofdmgan_abi_version() != 11:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

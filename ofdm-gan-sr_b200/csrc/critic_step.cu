@@ -3,6 +3,7 @@
 // backward for the penalty) and the five logged statistics.   ofdmgan_critic_step / ofdmgan_gradient_penalty
 #include "train_common.cuh"
 #include "critic_stream.cuh"
+#include "peer_comm.cuh"
 
 namespace og {
 
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(1024) k_critic_tail(const float* __restrict__ 
                                                       float* __restrict__ out, float* __restrict__ p, float* __restrict__ m,
                                                       float* __restrict__ v, double lr, double b1, double b2, double eps,
                                                       int32_t* __restrict__ step_dev, unsigned int* __restrict__ arrivals,
-                                                      float* __restrict__ image) {
+                                                      float* __restrict__ image, PeerPtrs peers, int rank, int world) {
     __shared__ double red[32 * 32], total[32];
     __shared__ unsigned int ticket;
     __shared__ float pnew[OFDMGAN_D_NPARAMS];
@@ -181,12 +182,20 @@ __global__ void __launch_bounds__(1024) k_critic_tail(const float* __restrict__ 
     if (ticket != gridDim.x - 1) return;
     // last block: every group's gradients are in `out`
     if (threadIdx.x == 0) *arrivals = 0u;
+    if (world > 1) {                                             // data parallel: sum the 528 floats over the ranks through peer memory
+        __shared__ int timed_out;
+        PeerBlock* mine = peers.p[rank];
+        const unsigned int seq = mine->seq + 1u;
+        const bool ok = peer_allreduce_block(peers, rank, world, seq, out, OFDMGAN_CRITIC_OUT, &timed_out);
+        if (threadIdx.x == 0) mine->seq = seq;
+        if (!ok) return;
+    }
     const int t = *step_dev + 1;
     const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);
     const int i = threadIdx.x;
     if (i < OFDMGAN_D_NPARAMS) {
         float pi = p[i], mi = m[i], vi = v[i];
-        adam_one(pi, mi, vi, __ldcg(out + i), c);
+        adam_one(pi, mi, vi, __ldcg(out + i), c);               // (__fmul_rn(g, 1) of k_adam_ctr is the identity)
         p[i] = pi; m[i] = mi; v[i] = vi;
         pnew[i] = pi;
     }
@@ -279,10 +288,14 @@ int ofdmgan_critic_step_ctr(const float* clean_dev, const float* noisy_dev, cons
 
 int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, uint64_t seed, uint64_t sample0,
                              int32_t* step_dev, float* dparams521_dev, float* m_dev, float* v_dev, double lr, double beta1, double beta2,
-                             double eps, float gp_weight, float leaky_slope, int64_t B, float* out_dev, int image_is_current,
-                             void* stream) {
+                             double eps, float gp_weight, float leaky_slope, int64_t B, int64_t B_global, float* out_dev,
+                             int image_is_current, ofdmgan_comm* comm, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    if (!clean_dev || !noisy_dev || !fake_dev || !step_dev || !dparams521_dev || !m_dev || !v_dev || !out_dev || B < 1) return OFDMGAN_E_ARG;
+    if (!clean_dev || !noisy_dev || !fake_dev || !step_dev || !dparams521_dev || !m_dev || !v_dev || !out_dev || B < 1 || B_global < B)
+        return OFDMGAN_E_ARG;
+    PeerPtrs peers{};
+    int rank = 0, world = 1;
+    if (comm && !comm_view(comm, &peers, &rank, &world)) return OFDMGAN_E_ARG;
     if (!aligned16(clean_dev) || !aligned16(noisy_dev) || !aligned16(fake_dev)) return OFDMGAN_E_ARG;
     int rc;
     CallGuard guard(s);
@@ -314,8 +327,8 @@ int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, con
     a.norms = nullptr;
     k_critic2<true><<<grid, OG_THREADS, 0, s>>>(a);
     OG_CHECK(cudaGetLastError());
-    k_critic_tail<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B, (double)gp_weight, out_dev, dparams521_dev, m_dev,
-                                         v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, image);
+    k_critic_tail<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev, dparams521_dev,
+                                         m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, image, peers, rank, world);
     OG_CHECK(cudaGetLastError());
     return commit_d_image(slot, s);
 }

@@ -2,49 +2,21 @@
 //
 // The training step of train.py:201-305 ends each of its 5 + 1 optimiser steps with a sum of a 528- / 264-float buffer over
 // the data-parallel ranks followed by Adam on 521 / 258 parameters.  At 2 KB the collective is pure latency (NCCL: ~25 us per
-// call at 8 ranks, a fifth of the step).  Here one 1024-thread CTA per rank does all of it in one launch:
-//   1. every rank stores its buffer straight into slot [parity][rank] of EVERY peer's exchange block (P2P stores over
-//      NVLink), fences, then publishes a sequence number in each peer's flag word;
-//   2. waits until all `world` flags of its own block show that sequence number;
-//   3. sums the `world` slots in rank order - the same order on every rank, so replicas stay bit-identical - writes the total
-//      back to the caller's buffer (loss statistics ride along) and applies Adam to the parameters.
-// Two slot sets alternate by sequence parity: a rank can start step s+1 while a peer still reads step s, and cannot reach step
-// s+2 before that peer has sent its step s+1 contribution, i.e. after it finished reading step s.
+// call at 8 ranks, a fifth of the step).  Here one 1024-thread CTA per rank does all of it in one launch (peer_comm.cuh):
+//   1. every rank stores its buffer straight into slot [parity][rank] of EVERY peer's exchange block (P2P stores over NVLink), each
+//      word tagged with the call's sequence number;
+//   2. reads the `world` slots of its own block, polling each word until its tag is current, and sums them in rank order - the same
+//      order on every rank, so replicas stay bit-identical - writes the total back to the caller's buffer (loss statistics ride
+//      along) and applies Adam to the parameters.
 // Exchange blocks are cudaMalloc'ed by the library and shared between the one-process-per-GPU ranks through CUDA IPC handles
-// that the host side swaps over torch.distributed.
+// that the host side swaps over torch.distributed.  The same block-wide exchange is the middle of the critic tail kernel
+// (critic_step.cu, ofdmgan_critic_train_ctr).
 #include <cstring>
 
-#include "common.cuh"
+#include "peer_comm.cuh"
 #include "train_common.cuh"
 
 namespace og {
-
-constexpr int PC_MAX_WORLD = 16;
-constexpr int PC_MAX_N = 1024;                                   // floats per message (critic 528, generator 264)
-constexpr long long PC_SPIN_LIMIT = 4000000000ll;                // ~2 s of SM clocks: a peer that never arrives is an error, not a hang
-
-struct PeerBlock {                                               // one per rank, device memory
-    float slot[2][PC_MAX_WORLD][PC_MAX_N];
-    unsigned int flag[2][PC_MAX_WORLD];
-    unsigned int seq;                                            // calls completed by the owning rank (device-resident: graph replays advance it)
-    int error;                                                   // sticky: set when a wait timed out
-};
-
-struct PeerPtrs { PeerBlock* p[PC_MAX_WORLD]; };
-
-__device__ __forceinline__ void st_release_sys(unsigned int* a, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* a) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_sys(const float* a) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(a) : "memory");
-    return v;
-}
 
 // step_dev == nullptr: Adam coefficients from the host (coef); else t = *step_dev + 1 is used and stored back (ofdmgan_adam_ctr)
 __global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int rank, int world, float* __restrict__ g,
@@ -53,37 +25,14 @@ __global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int ran
                                                          int32_t* __restrict__ step_dev, float grad_scale) {
     PeerBlock* mine = peers.p[rank];
     const unsigned int seq = mine->seq + 1u;                     // written only by this rank's previous launch (stream order)
-    const int par = seq & 1u, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     int t_adam = 0;
     if (step_dev) { t_adam = *step_dev + 1; coef = adam_coef_dev(lr, b1, b2, eps, t_adam); }
     __shared__ int timed_out;
-    if (tid == 0) timed_out = 0;
-    // 1. scatter this rank's message into every peer's block (own block included)
-    for (int i = tid; i < n; i += blockDim.x) {
-        const float x = g[i];
-        for (int r = 0; r < world; ++r) peers.p[r]->slot[par][rank][i] = x;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) st_release_sys(&peers.p[tid]->flag[par][rank], seq);
-    // 2. wait for every rank's message
-    if (tid < world) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(&mine->flag[par][tid]) != seq) {
-            if (clock64() - t0 > PC_SPIN_LIMIT) { timed_out = 1; mine->error = 1; break; }
-            __nanosleep(40);
-        }
-    }
-    __syncthreads();
+    const bool ok = peer_allreduce_block(peers, rank, world, seq, g, n, &timed_out);
     if (tid == 0) { mine->seq = seq; if (step_dev) *step_dev = t_adam; }
-    if (timed_out) return;
-    // 3. fixed-order sum, statistics and gradients back to the caller, Adam on the parameters
-    for (int i = tid; i < n; i += blockDim.x) {
-        float s = 0.f;
-        for (int r = 0; r < world; ++r) s += ld_sys(&mine->slot[par][r][i]);
-        g[i] = s;
-        if (i < n_params) adam_one(p[i], m[i], v[i], __fmul_rn(s, grad_scale), coef);
-    }
+    if (!ok) return;
+    for (int i = tid; i < n_params; i += blockDim.x) adam_one(p[i], m[i], v[i], __fmul_rn(g[i], grad_scale), coef);
 }
 
 }  // namespace og
@@ -96,6 +45,14 @@ struct ofdmgan_comm {
     PeerPtrs peers;
     bool connected;
 };
+
+namespace og {
+bool comm_view(const ofdmgan_comm* c, PeerPtrs* peers, int* rank, int* world) {
+    if (!c || !c->connected) return false;
+    *peers = c->peers; *rank = c->rank; *world = c->world;
+    return true;
+}
+}  // namespace og
 
 extern "C" {
 

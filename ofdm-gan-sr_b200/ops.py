@@ -485,15 +485,18 @@ def critic_step(clean, noisy, fake, dparams, alpha=None, seed=0, sample0=0, alph
 
 
 def critic_train(clean, noisy, fake, dparams, m, v, step_dev, lr, beta1, beta2, eps, seed=0, sample0=0, gp_weight=10.0, slope=0.2, out=None,
-                 image_is_current=False):
-    """One whole critic iteration on one GPU (loss, backward, Adam in place on dparams / m / v, weight-image refresh): two launches.
-    step_dev: int32 CUDA tensor (1 element) = optimiser steps taken so far; doubles as the Philox alpha counter."""
+                 image_is_current=False, comm=None, b_global=None):
+    """One whole critic iteration (loss, backward, gradient sum over the ranks of `comm` if given, Adam in place on dparams / m / v,
+    weight-image refresh): two launches.  step_dev: int32 CUDA tensor (1 element) = optimiser steps taken so far; doubles as the
+    Philox alpha counter."""
     clean, noisy, fake = frames(clean), frames(noisy), frames(fake)
     if out is None:
         out = torch.empty(CRITIC_OUT, dtype=torch.float32, device=clean.device)
     check(_lib.lib().ofdmgan_critic_train_ctr(dptr(clean), dptr(noisy), dptr(fake), seed, sample0, dptr(step_dev), dptr(dparams), dptr(m),
-                                              dptr(v), lr, beta1, beta2, eps, gp_weight, slope, clean.shape[0], dptr(out),
-                                              1 if image_is_current else 0, stream_ptr(clean.device)))
+                                              dptr(v), lr, beta1, beta2, eps, gp_weight, slope, clean.shape[0],
+                                              clean.shape[0] if b_global is None else b_global, dptr(out),
+                                              1 if image_is_current else 0, comm._h if comm is not None else None,
+                                              stream_ptr(clean.device)))
     return out
 
 

@@ -128,12 +128,12 @@ class CWGANGPStep:
         self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
         for c in range(self.n_critic):
             out = self._dout[c]
-            if self.comm is None and hasattr(self.k, "critic_train"):
-                # one GPU: loss + backward, then ONE tail launch (gradient reduction, Adam, weight-image refresh); from the second
-                # iteration on the image installed by the previous tail is still current
+            if hasattr(self.k, "critic_train"):
+                # loss + backward, then ONE tail launch (gradient reduction, the sum over the ranks through peer memory, Adam,
+                # weight-image refresh); from the second iteration on the image installed by the previous tail is still current
                 self.k.critic_train(clean, noisy, self._fake, self.d, self.d_m, self.d_v, self._ctr[0:1], self.lr_d, self.betas[0],
-                                    self.betas[1], self.eps, seed=self.seed, sample0=0, gp_weight=self.gp_weight, slope=self.slope,
-                                    out=out, image_is_current=c > 0)
+                                    self.betas[1], self.eps, seed=self.seed, sample0=self.rank * B, gp_weight=self.gp_weight,
+                                    slope=self.slope, out=out, image_is_current=c > 0, comm=self.comm, b_global=Bg)
                 continue
             self.k.critic_step(clean, noisy, self._fake, self.d, seed=self.seed, sample0=self.rank * B, gp_weight=self.gp_weight,
                                slope=self.slope, b_global=Bg, out=out, alpha_iter_dev=self._ctr[0:1])
@@ -224,6 +224,6 @@ class CWGANGPStep:
     # kernels launched by one step() (for bench.py's gpu_launches): G fwd 2 (weight image + kernel), per critic iteration
     # 4 (image, k_critic, finalize, adam), generator step 6 (2 images, k_gen_step, finalize, adam)... see DESIGN.md
     def launches_per_step(self):
-        if self.use_graph and self.comm is None:                 # fused critic iterations: kernel + tail, one image refresh per step
+        if self.use_graph:                                       # fused critic iterations: kernel + tail, one image refresh per step
             return 2 + (2 * self.n_critic + 1) + 5
         return 2 + self.n_critic * 4 + 5                         # (the fused exchange kernel takes the Adam kernel's place)
