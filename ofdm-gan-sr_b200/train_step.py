@@ -128,7 +128,7 @@ class CWGANGPStep:
         self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
         for c in range(self.n_critic):
             out = self._dout[c]
-            if hasattr(self.k, "critic_train"):
+            if hasattr(self.k, "critic_train") and B > 0:        # (an empty shard takes the unfused calls: same exchange sequence)
                 # loss + backward, then ONE tail launch (gradient reduction, the sum over the ranks through peer memory, Adam,
                 # weight-image refresh); from the second iteration on the image installed by the previous tail is still current
                 self.k.critic_train(clean, noisy, self._fake, self.d, self.d_m, self.d_v, self._ctr[0:1], self.lr_d, self.betas[0],
