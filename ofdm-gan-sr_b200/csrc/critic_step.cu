@@ -29,7 +29,10 @@ struct CriticArgs {
 // Work item = (term, 128-sample tile) with term in {penalty, -D(real), +D(fake)}: three times the parallelism of one
 // thread doing all three terms of its sample, which matters at 65,536 samples per GPU (443 samples per SM).  The
 // heaviest term (penalty) is scheduled first.  <= 128 registers: 4 CTAs (16 warps) per SM, see critic_stream.cuh.
-constexpr int CRITIC_PER_SM = 4;
+#ifndef OG_CRITIC_PER_SM
+#define OG_CRITIC_PER_SM 4
+#endif
+constexpr int CRITIC_PER_SM = OG_CRITIC_PER_SM;
 
 template <bool SCORE>
 __global__ void __launch_bounds__(OG_THREADS, CRITIC_PER_SM) k_critic2(const __grid_constant__ CriticArgs a) {
