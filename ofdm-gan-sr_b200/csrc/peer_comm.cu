@@ -60,16 +60,22 @@ int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handl
     if (!out || !ipc_handle64 || world < 1 || world > PC_MAX_WORLD || rank < 0 || rank >= world) return OFDMGAN_E_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     ofdmgan_comm* c = new ofdmgan_comm();
-    c->rank = rank; c->world = world; c->connected = false;
-    OG_CHECK(cudaGetDevice(&c->device));
-    OG_CHECK(cudaMalloc((void**)&c->local, sizeof(PeerBlock)));
-    OG_CHECK(cudaMemset(c->local, 0, sizeof(PeerBlock)));
-    cudaIpcMemHandle_t h;
-    OG_CHECK(cudaIpcGetMemHandle(&h, c->local));
-    memcpy(ipc_handle64, &h, 64);
+    c->rank = rank; c->world = world; c->connected = false; c->local = nullptr;
     for (int r = 0; r < PC_MAX_WORLD; ++r) c->peers.p[r] = nullptr;
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaGetDevice(&c->device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->local, sizeof(PeerBlock));
+    if (e == cudaSuccess) e = cudaMemset(c->local, 0, sizeof(PeerBlock));
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();          // the zeroed block must be in place before any peer writes to it
+    if (e != cudaSuccess) {                                      // nothing is handed out on failure
+        if (c->local) cudaFree(c->local);
+        delete c;
+        (void)cudaGetLastError();
+        return (int)e;
+    }
+    memcpy(ipc_handle64, &h, 64);
     c->peers.p[rank] = c->local;
-    OG_CHECK(cudaDeviceSynchronize());                           // the zeroed block must be in place before any peer writes to it
     *out = c;
     return 0;
 }
