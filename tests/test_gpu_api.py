@@ -197,7 +197,7 @@ def test_fused_trainer_step_vs_torch_eager(pkg):
         oG.step()
         st = tr.stats()
         assert abs(st["d_loss"] - float(d_loss.detach())) <= 2e-5 * max(1, abs(float(d_loss.detach())))
-        assert abs(st["g_loss"] - float(g_loss)) <= 2e-5 * max(1, abs(float(g_loss)))
+        assert abs(st["g_loss"] - float(g_loss.detach())) <= 2e-5 * max(1, abs(float(g_loss.detach())))
     tr.store_to(G, D)
     for (n, p), (_, q) in zip(list(G.named_parameters()) + list(D.named_parameters()),
                               list(TG.named_parameters()) + list(TD.named_parameters())):
