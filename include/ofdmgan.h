@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 11
+#define OFDMGAN_ABI_VERSION 12
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -220,6 +220,11 @@ int ofdmgan_sim_gen_metrics(const ofdmgan_chan_cfg* cfg_host, int gen_kind, cons
 int ofdmgan_sim_gen_metrics_host(const ofdmgan_chan_cfg* cfg_host, int gen_kind, const float* gparams258_host,
                                  const int8_t* wrom_host, const int16_t* brom_host, float leaky_slope,
                                  uint64_t seed, uint64_t frame0, int64_t B, double* metrics_host, void* stream);
+/* Which simulator kernel a configuration runs on: 1 = the lean headline kernel (csrc/sim_lean.cu: Gaussian source, AWGN channel,
+ * Rapp / IQ / phase noise, fp32 generator or none), 0 = the general kernel (every other option of ofdmgan_chan_cfg).  gen_kind -1 =
+ * simulate only.  has_tx_or_fade != 0: the call injects time-domain frames or fading draws.  The environment variable
+ * OFDMGAN_SIM_IMPL=general forces 0 (A/B runs, cross-check tests).  Pure host function. */
+int ofdmgan_sim_impl_for(const ofdmgan_chan_cfg* cfg_host, int gen_kind, int has_tx_or_fade);
 /* metric rows for frames that already exist in HBM (benchmark_comparison.py:137-146,205-214).
  * est/ref: [B][2][16] f32 device; bin_dev: [B] int32 SNR bin per frame or NULL (all bin 0). */
 int ofdmgan_frame_metrics(const float* est_dev, const float* ref_dev, const int32_t* bin_dev, int method, int n_snr,

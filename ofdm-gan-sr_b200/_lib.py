@@ -87,6 +87,7 @@ _SIGNATURES = {
     "ofdmgan_ofdm_demodulate": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f, c_f, c_p, c_p, c_p]),
     "ofdmgan_sim_gen_metrics": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_p, c_p, c_f, c_u64, c_u64, c_i64, c_p, c_p]),
     "ofdmgan_sim_gen_metrics_host": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_p, c_p, c_f, c_u64, c_u64, c_i64, c_p, c_p]),
+    "ofdmgan_sim_impl_for": (ctypes.c_int, [c_p, ctypes.c_int, ctypes.c_int]),
     "ofdmgan_equalize": (ctypes.c_int, [c_p, c_p, c_p, ctypes.c_int, c_p, c_i64, c_p]),
     "ofdmgan_frame_metrics": (ctypes.c_int, [c_p, c_p, c_p, ctypes.c_int, ctypes.c_int, c_i64, c_p, c_p]),
     "ofdmgan_disc_fwd_f32": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_p]),
@@ -112,7 +113,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 11:
+        if L.ofdmgan_abi_version() != 12:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

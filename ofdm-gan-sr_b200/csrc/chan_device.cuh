@@ -53,6 +53,8 @@ struct SimCall {
 };
 int sim_launch_gauss(const SimCall& c);    // sim_gauss.cu
 int sim_launch_qpsk(const SimCall& c);     // sim_qpsk.cu
+int sim_launch_lean(const SimCall& c);     // sim_lean.cu: the headline kernel
+bool sim_lean_eligible(const SimCall& c);
 
 // ---- radix-2 DIT inverse FFT, fully unrolled, unscaled: x[n] = sum_k X[k] e^{+j 2 pi k n / N} -------------
 // twiddles e^{+j 2 pi k / 16}, k = 0..7, as constant-folded selects (a constexpr table indexed after unrolling is
@@ -105,12 +107,28 @@ __device__ __forceinline__ void fft_inplace(float (&re)[N], float (&im)[N]) {
 }
 
 // ---- draws ------------------------------------------------------------------------------------------------
-// Philox block layout per frame (purpose 0): 0-7 symbol normals, 8-11 phase increments, 12 {snr uniform, payload
-// bits}, 13-20 noise normals.  See oracle/channel.c header.
-__device__ __forceinline__ void draw_normals(const SimArgs& a, uint64_t frame, uint32_t blk, float (&n)[4], float var = 1.0f) {
-    uint32_t x[4];
-    philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), blk, 0u, x);
-    normals_from_block(x, n, var);
+// Philox block layout per frame (purpose 0), three Box-Muller pairs per block (common.cuh): blocks 0-5 the 16 symbol pairs
+// (normals 0-15 Re, 16-31 Im), 8-10 the 8 phase-increment pairs, 12 {snr uniform, payload bits, LOS phase}, 13-18 the 16 noise
+// pairs (Re then Im), 21 / 22 two fading pairs each.  See oracle/channel.c header.
+// the section of NP pairs that starts at block blk0, as 2 NP normals of variance var
+template <int NP>
+__device__ __forceinline__ void draw_section(const SimArgs& a, uint64_t frame, uint32_t blk0, float (&n)[2 * NP], float var = 1.0f) {
+#pragma unroll
+    for (int b = 0; b < (NP + 2) / 3; ++b) {
+        uint32_t x[4];
+        philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), blk0 + b, 0u, x);
+        constexpr int last = NP - 3 * ((NP + 2) / 3 - 1);         // pairs in the last block
+        const float k = OG_BM_K * var;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (3 * b + q >= NP) break;
+            float r, c, s;
+            bm_polar(x, q, k, r, c, s);
+            n[2 * (3 * b + q)] = r * c;
+            n[2 * (3 * b + q) + 1] = r * s;
+        }
+        (void)last;
+    }
 }
 
 __device__ __forceinline__ int snr_bin_of(const ofdmgan_chan_cfg& c, uint64_t frame) {
@@ -147,17 +165,10 @@ __device__ __forceinline__ void tx_frame(const SimArgs& a, int64_t b, uint64_t f
 #pragma unroll
             for (int k = 0; k < 16; ++k) { cr[k] = a.sym[b * 32 + k] * sc; ci[k] = a.sym[b * 32 + 16 + k] * sc; }
         } else {
-            const float var = sc * sc;
+            float n[32];
+            draw_section<16>(a, frame, 0u, n, sc * sc);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float n[4];
-                draw_normals(a, frame, j, n, var);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) cr[4 * j + t] = n[t];
-                draw_normals(a, frame, 4 + j, n, var);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) ci[4 * j + t] = n[t];
-            }
+            for (int k = 0; k < 16; ++k) { cr[k] = n[k]; ci[k] = n[16 + k]; }
         }
         fft_inplace<16, +1>(cr, ci);
         return;
@@ -190,8 +201,8 @@ __device__ __forceinline__ void fade_draws(const SimArgs& a, int64_t b, uint64_t
         return;
     }
     float n0[4], n1[4];
-    draw_normals(a, frame, 21u, n0);
-    draw_normals(a, frame, 22u, n1);
+    draw_section<2>(a, frame, 21u, n0);
+    draw_section<2>(a, frame, 22u, n1);
     if (a.cfg.channel_type == OFDMGAN_CHAN_RICIAN) {
         uint32_t x12[4];
         philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
@@ -310,20 +321,19 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
         for (int i = 0; i < 16; ++i) ni[i] = c.iq_gain * (c.iq_cos * ni[i] + c.iq_sin * nr[i]);
     }
     if (c.impair & OFDMGAN_IMPAIR_PN) {
-        float th = 0.f;
+        float th = 0.f, n16[16];
+        if (a.pn) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) n16[t] = a.pn[b * 16 + t];
+        } else {
+            draw_section<8>(a, frame, 8u, n16);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float n[4];
-            if (a.pn) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) n[t] = a.pn[b * 16 + 4 * j + t];
-            } else {
-                draw_normals(a, frame, 8 + j, n);
-            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int i = 4 * j + t;
-                th = fmaf(c.pn_sigma, n[t], th);
+                th = fmaf(c.pn_sigma, n16[i], th);
                 const float red = fmaf(-6.283185307179586f, rintf(th * 0.15915494309189535f), th);
                 const float s = fast_sin(red), co = fast_cos(red);
                 const float xr = nr[i], xi = ni[i];
@@ -340,21 +350,17 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
     P *= 0.0625f;
     // sigma = sqrt(P / 10^(snr/10) / 2)
     const float sd = fast_sqrt(0.5f * P * fast_ex2(-0.33219280948873623f * snr_db));
+    float n32[32];
+    if (a.noise) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float n[4], m[4];
-        if (a.noise) {
+        for (int t = 0; t < 32; ++t) n32[t] = a.noise[b * 32 + t];
+    } else {
+        draw_section<16>(a, frame, 13u, n32);
+    }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { n[t] = a.noise[b * 32 + 4 * j + t]; m[t] = a.noise[b * 32 + 16 + 4 * j + t]; }
-        } else {
-            draw_normals(a, frame, 13 + j, n);
-            draw_normals(a, frame, 17 + j, m);
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            nr[4 * j + t] = fmaf(sd, n[t], nr[4 * j + t]);
-            ni[4 * j + t] = fmaf(sd, m[t], ni[4 * j + t]);
-        }
+    for (int k = 0; k < 16; ++k) {
+        nr[k] = fmaf(sd, n32[k], nr[k]);
+        ni[k] = fmaf(sd, n32[16 + k], ni[k]);
     }
 }
 

@@ -93,6 +93,7 @@ __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 fma2_rd(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 // a pair of adjacent floats of a constant image (8-byte aligned index)
 __device__ __forceinline__ f32x2 ldc2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }
 
@@ -104,18 +105,47 @@ __device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ft
 __device__ __forceinline__ float fast_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// Box-Muller on the word pairs (x0,x1), (x2,x3): 4 normals per Philox block.
-//   r = sqrt(-2 ln u1) = sqrt(-2 ln2 * lg2 u1), u1 in (0,1) so the radicand is > 0; angle 2 pi u2 in [0, 2 pi)
-//   `var` scales the variance (the caller folds any output scale s as var = s^2: the multiply disappears into the
-//   constant under the square root); the angle is (x >> 8) * (2 pi 2^-24), one multiply.
-__device__ __forceinline__ void normals_from_block(const uint32_t (&x)[4], float (&n)[4], float var = 1.0f) {
-    const float k = -1.3862943611198906f * var;
+// ---- normals: Box-Muller, THREE pairs per Philox block -----------------------------------------------------------------
+// A pair needs a radius uniform u1 (its resolution sets the tail: 23 bits reach 5.8 sigma) and an angle; 16 angle bits (65,536
+// directions) are plenty, so one 128-bit block feeds three pairs instead of two - a quarter fewer Philox blocks per frame,
+// and the 32 x 32 -> 64 multiplies of Philox are the most expensive instructions of the fused kernel (4 cycles of the FMA-heavy
+// pipe each).  Pair `slot` of block (x0, x1, x2, x3):
+//     radius bits m = x[slot] & 0x7FFFFF,          u1 = (m + 0.5) * 2^-23 in (0,1)
+//     angle bits  a = x3 & 0xFFFF | x3 >> 16 | (x0 >> 24) | (x1 >> 24) << 8   for slot 0 | 1 | 2,   theta = 2 pi a / 65536
+//     normals (r cos theta, r sin theta), r = sqrt(-2 ln u1 * var) = sqrt(k * lg2 u1), k = -2 ln2 * var
+// (any output scale s enters as var = s^2 under the square root: free).  No integer-to-float conversion anywhere: the radius bits
+// are OR-ed into the mantissa of [1,2) (one LOP3) and shifted down by an exact subtraction; the angle bits are byte-permuted
+// into the mantissa of 2^23 (value 2^23 + a exactly) and ONE fma forms a * (2 pi / 65536) with a single rounding.
+// A "section" of the stream is NP consecutive pairs starting at block blk0: pair p lives in block blk0 + p / 3, slot p % 3.
+// Definition shared with oracle/channel.c (section_normals).
+#define OG_BM_K (-1.3862943611198906f)                     /* -2 ln 2 */
+// (x & m) | c as ONE LOP3 (the compiler splits it in two when both constants are immediates)
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t m, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(m), "r"(c));
+    return r;
+}
+// polar pieces of pair `slot` (compile-time after unrolling) so that callers can fold the product into an FMA
+__device__ __forceinline__ void bm_polar(const uint32_t (&x)[4], int slot, float k, float& r, float& c, float& s) {
+    const float u1 = __uint_as_float(and_or(x[slot], 0x007FFFFFu, 0x3F800000u)) - (1.0f - 5.9604644775390625e-08f);
+    r = fast_sqrt(k * fast_lg2(u1));
+    const uint32_t tb = slot == 0   ? __byte_perm(x[3], 0x4B000000u, 0x7610)
+                        : slot == 1 ? __byte_perm(x[3], 0x4B000000u, 0x7632)
+                                    : __byte_perm(__byte_perm(x[0], x[1], 0x3373), 0x4B000000u, 0x7610);
+    const float th = fmaf(__uint_as_float(tb), 9.587379924285257e-05f, -804.247719318987f);   // (2^23 + a) 2 pi 2^-16 - 2^23 2 pi 2^-16
+    c = fast_cos(th);
+    s = fast_sin(th);
+}
+// the first NP (<= 3) pairs of one block as 2 NP normals of variance `var`
+template <int NP>
+__device__ __forceinline__ void normals_from_block(const uint32_t (&x)[4], float (&n)[2 * NP], float var = 1.0f) {
+    const float k = OG_BM_K * var;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const float r = fast_sqrt(k * fast_lg2(u_open(x[2 * h])));
-        const float th = (float)(x[2 * h + 1] >> 8) * 3.7450702829239286e-07f;
-        n[2 * h] = r * fast_cos(th);
-        n[2 * h + 1] = r * fast_sin(th);
+    for (int q = 0; q < NP; ++q) {
+        float r, c, s;
+        bm_polar(x, q, k, r, c, s);
+        n[2 * q] = r * c;
+        n[2 * q + 1] = r * s;
     }
 }
 

@@ -171,10 +171,10 @@ __global__ void k_chan_draws(const __grid_constant__ SimArgs a, float* sym, uint
     const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const uint64_t frame = a.frame0 + (uint64_t)b;
-    float n[4];
-    if (sym) for (int j = 0; j < 8; ++j) { draw_normals(a, frame, j, n); for (int t = 0; t < 4; ++t) sym[b * 32 + 4 * j + t] = n[t]; }
-    if (pn) for (int j = 0; j < 4; ++j) { draw_normals(a, frame, 8 + j, n); for (int t = 0; t < 4; ++t) pn[b * 16 + 4 * j + t] = n[t]; }
-    if (noise) for (int j = 0; j < 8; ++j) { draw_normals(a, frame, 13 + j, n); for (int t = 0; t < 4; ++t) noise[b * 32 + 4 * j + t] = n[t]; }
+    float n[32];
+    if (sym) { draw_section<16>(a, frame, 0u, n); for (int t = 0; t < 32; ++t) sym[b * 32 + t] = n[t]; }
+    if (pn) { float m[16]; draw_section<8>(a, frame, 8u, m); for (int t = 0; t < 16; ++t) pn[b * 16 + t] = m[t]; }
+    if (noise) { draw_section<16>(a, frame, 13u, n); for (int t = 0; t < 32; ++t) noise[b * 32 + t] = n[t]; }
     if (bits || snr_db) {
         uint32_t x[4];
         philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x);
@@ -315,7 +315,15 @@ int ofdmgan_dequantize_q88(const int16_t* q_dev, float* x_dev, int64_t n, void* 
     return (int)cudaGetLastError();
 }
 
-static int sim_dispatch(const SimCall& c) { return c.src == SRC_GAUSS ? sim_launch_gauss(c) : sim_launch_qpsk(c); }
+// OFDMGAN_SIM_IMPL=general keeps every call on the general one-thread-per-frame kernel (A/B runs, cross-check tests)
+static bool sim_lean_enabled() {
+    const char* e = getenv("OFDMGAN_SIM_IMPL");
+    return !(e && e[0] == 'g');
+}
+static int sim_dispatch(const SimCall& c) {
+    if (sim_lean_enabled() && sim_lean_eligible(c)) return sim_launch_lean(c);
+    return c.src == SRC_GAUSS ? sim_launch_gauss(c) : sim_launch_qpsk(c);
+}
 
 int ofdmgan_chan_sim(const ofdmgan_chan_cfg* cfg_host, const ofdmgan_chan_rand* rand_host, uint64_t seed, uint64_t frame0,
                      float* clean_dev, float* noisy_dev, float* snr_dev, int64_t B, void* stream) {
@@ -342,6 +350,18 @@ int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t
     a.B = B;
     k_chan_draws<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, sym_dev, bits_dev, pn_dev, snr_db_dev, noise_dev);
     return (int)cudaGetLastError();
+}
+
+int ofdmgan_sim_impl_for(const ofdmgan_chan_cfg* cfg_host, int gen_kind, int has_tx_or_fade) {
+    if (!cfg_host) return OFDMGAN_E_ARG;
+    SimCall c{};
+    c.cfg = cfg_host;
+    c.B = 1;
+    c.gen_kind = gen_kind;
+    c.src = cfg_host->symbol_source == OFDMGAN_SYM_GAUSSIAN ? SRC_GAUSS : SRC_COUNT;
+    ofdmgan_chan_rand r{};
+    if (has_tx_or_fade) { r.tx = reinterpret_cast<const float*>(1); c.rand = &r; }
+    return sim_lean_enabled() && sim_lean_eligible(c) ? 1 : 0;
 }
 
 int ofdmgan_chan_fade_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t frame0, float* fade_dev, int64_t B, void* stream) {

@@ -29,7 +29,11 @@ constexpr int GI_OUT_F = 264;    // [2][4][4] folded
 constexpr int GI_OUT_B = 296;    // [2]
 // pair-interleaved copies of the four weight blocks, [oc/2][ic][k][2]: one 64-bit uniform load feeds a packed FFMA2
 constexpr int GI2_ENC = 304, GI2_BN = 328, GI2_DEC = 424, GI2_OUT = 552;   // 24 + 96 + 128 + 32 floats
-constexpr int OG_G_IMG = 584;
+// out_conv once more, folded taps (pair-interleaved) and bias multiplied by 2 log2(e): tanh(v) = 1 - 2 / (1 + 2^(v 2 log2 e)) then
+// needs no multiply in the fused simulator (sim_ws.cu)
+constexpr int GI2_OUT_T = 584, GI_OUT_BT = 616;                            // 32 + 2 floats
+constexpr float G_TANH_SCALE = 2.8853900817779268f;
+constexpr int OG_G_IMG = 624;
 // raw parameter offsets (torch order, include/ofdmgan.h)
 constexpr int GP_ENC_W = 0, GP_ENC_B = 24, GP_BN_W = 28, GP_BN_B = 124, GP_DEC_W = 132, GP_DEC_B = 228, GP_OUT_W = 232,
               GP_OUT_B = 256;
@@ -70,9 +74,12 @@ __device__ __forceinline__ float g_img_base(const float* __restrict__ p, int i) 
 }
 
 static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
-    const int i = threadIdx.x;
+    int i = threadIdx.x;
     if (i < GI2_ENC) { img[i] = g_img_base(p, i); return; }
     if (i >= OG_G_IMG) return;
+    if (i >= GI_OUT_BT) { img[i] = i < GI_OUT_BT + 2 ? p[GP_OUT_B + (i - GI_OUT_BT)] * G_TANH_SCALE : 0.f; return; }
+    const float post = i >= GI2_OUT_T ? G_TANH_SCALE : 1.0f;
+    if (i >= GI2_OUT_T) i -= GI2_OUT_T - GI2_OUT;
     // pair-interleaved copies: entry ((o2*IC + ic)*K + k)*2 + h  <-  base[((2*o2+h)*IC + ic)*K + k]
     int e, base, IC, K;
     if (i < GI2_BN) { e = i - GI2_ENC; base = GI_ENC_W; IC = 2; K = 3; }
@@ -80,7 +87,7 @@ static __global__ void prep_g_image(const float* __restrict__ p, float* __restri
     else if (i < GI2_OUT) { e = i - GI2_DEC; base = GI_DEC_F; IC = 8; K = 4; }
     else { e = i - GI2_OUT; base = GI_OUT_F; IC = 4; K = 4; }
     const int h = e & 1, r = e >> 1, k = r % K, ic = (r / K) % IC, o2 = r / (K * IC);
-    img[i] = g_img_base(p, base + ((2 * o2 + h) * IC + ic) * K + k);
+    img[threadIdx.x] = g_img_base(p, base + ((2 * o2 + h) * IC + ic) * K + k) * post;
 }
 
 // entry i of the D image from the raw parameters

@@ -19,10 +19,12 @@
  *
  * RNG (defined by this project, not by the reference, whose draws come from NumPy's global MT19937):
  *   Philox4x32-10, key = seed, counter = (frame lo, frame hi, block, purpose).  purpose 0 = channel:
- *   blocks 0-7 symbol normals (4 each; 0-15 Re, 16-31 Im), 8-11 phase-noise increments, 12 = {snr uniform,
- *   payload bits, -, -}, 13-20 noise normals.  purpose 1 = gradient-penalty alpha (block = critic iteration).
- *   uniform u1 = ((x>>9)+0.5)*2^-23, u2 = (x>>8)*2^-24 ; Box-Muller r = sqrt(-2 ln u1), (r cos 2pi u2, r sin 2pi u2)
- *   from the word pairs (x0,x1) and (x2,x3).
+ *   Normals come in Box-Muller pairs, THREE per block: pair `slot` uses radius bits x[slot] & 0x7FFFFF (u1 = (m+0.5)*2^-23) and the
+ *   16 angle bits x3 & 0xFFFF | x3 >> 16 | (x0>>24) | (x1>>24)<<8 (theta = 2 pi a / 65536); (r cos theta, r sin theta), r = sqrt(-2 ln u1).
+ *   A section of n pairs starting at block b0 puts pair p in block b0 + p/3, slot p%3.  Sections: blocks 0-5 the 16 symbol pairs
+ *   (normals 0-15 Re, 16-31 Im), 8-10 the 8 phase-noise pairs, 12 = {snr uniform, payload bits, LOS phase, -}, 13-18 the 16 noise
+ *   pairs, 21 / 22 two fading pairs each.  purpose 1 = gradient-penalty alpha (block = critic iteration).
+ *   Plain uniforms (snr, alpha, LOS phase): u = (x>>8)*2^-24.
  */
 #include <math.h>
 #include <stdint.h>
@@ -60,23 +62,28 @@ void oracle_philox_blocks(uint64_t seed, uint64_t ctr0, uint32_t c2, uint32_t c3
 static inline double u_open(uint32_t x) { return ((double)(x >> 9) + 0.5) * (1.0 / 8388608.0); }
 static inline double u_half(uint32_t x) { return (double)(x >> 8) * (1.0 / 16777216.0); }
 
-static void normals4(uint64_t seed, uint64_t frame, uint32_t blk, uint32_t purpose, double n[4]) {
-    uint32_t x[4];
-    oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), blk, purpose, x);
-    for (int h = 0; h < 2; ++h) {
-        double r = sqrt(-2.0 * log(u_open(x[2 * h]))), th = 2.0 * M_PI * u_half(x[2 * h + 1]);
-        n[2 * h] = r * cos(th);
-        n[2 * h + 1] = r * sin(th);
+/* 2*npairs normals of the section that starts at block blk0: pair p = block blk0 + p/3, slot p%3 (csrc/common.cuh) */
+static void section_normals(uint64_t seed, uint64_t frame, uint32_t blk0, uint32_t purpose, int npairs, double* out) {
+    uint32_t x[4] = {0, 0, 0, 0};
+    for (int p = 0; p < npairs; ++p) {
+        int slot = p % 3;
+        if (slot == 0)
+            oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), blk0 + (uint32_t)(p / 3),
+                                 purpose, x);
+        uint32_t a16 = slot == 0 ? (x[3] & 0xFFFFu) : slot == 1 ? (x[3] >> 16) : ((x[0] >> 24) | ((x[1] >> 24) << 8));
+        double u1 = ((double)(x[slot] & 0x7FFFFFu) + 0.5) * (1.0 / 8388608.0);
+        double r = sqrt(-2.0 * log(u1)), th = 2.0 * M_PI * (double)a16 * (1.0 / 65536.0);
+        out[2 * p] = r * cos(th);
+        out[2 * p + 1] = r * sin(th);
     }
 }
 
 /* the draws frame `frame` consumes; any output may be NULL */
 void oracle_frame_draws(const ofdmgan_chan_cfg* cfg, uint64_t seed, uint64_t frame, double* sym32, uint32_t* bits,
                         double* pn16, double* snr_db, double* noise32) {
-    double n[4];
-    if (sym32) for (uint32_t j = 0; j < 8; ++j) { normals4(seed, frame, j, 0, n); memcpy(sym32 + 4 * j, n, sizeof n); }
-    if (pn16) for (uint32_t j = 0; j < 4; ++j) { normals4(seed, frame, 8 + j, 0, n); memcpy(pn16 + 4 * j, n, sizeof n); }
-    if (noise32) for (uint32_t j = 0; j < 8; ++j) { normals4(seed, frame, 13 + j, 0, n); memcpy(noise32 + 4 * j, n, sizeof n); }
+    if (sym32) section_normals(seed, frame, 0, 0, 16, sym32);
+    if (pn16) section_normals(seed, frame, 8, 0, 8, pn16);
+    if (noise32) section_normals(seed, frame, 13, 0, 16, noise32);
     if (bits || snr_db) {
         uint32_t x[4];
         oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), 12, 0, x);
@@ -175,7 +182,8 @@ static void impair_and_channel(const ofdmgan_chan_cfg* cfg, const double* pn16, 
     double P = 0;
     for (int i = 0; i < 16; ++i) P += r[i] * r[i] + q[i] * q[i];
     P /= 16.0;
-    double sd = sqrt(P / pow(10.0, snr_db / 10.0) / 2.0);
+    /* OFDMGAN_SNR_NONE: the impairments on their own (NonLinearImpairments.apply_* without ChannelModel.apply) */
+    double sd = cfg->snr_mode == OFDMGAN_SNR_NONE ? 0.0 : sqrt(P / pow(10.0, snr_db / 10.0) / 2.0);
     for (int i = 0; i < 16; ++i) { yr[i] = r[i] + sd * noise32[i]; yi[i] = q[i] + sd * noise32[16 + i]; }
 }
 

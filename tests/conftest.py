@@ -36,13 +36,43 @@ def rtl_critic_vectors():
     return json.load(open(os.path.join(GOLDEN, "rtl_critic_vectors.json")))
 
 
-def assert_close(got, ref, rtol=1e-5, name=""):
-    """|got-ref| <= rtol * max(|ref|, scale) with scale = max|ref| over the tensor: the 1e-5 relative bound of
-    BASELINE.json's north_star, taken relative to the tensor's scale so exact zeros do not demand exactness."""
+PARITY = []          # (name, to-scale error, element-wise error, n significant elements): reported at session end
+
+
+def assert_close(got, ref, rtol=1e-5, name="", elem_rtol=None):
+    """Two readings of "<= 1e-5 relative error" (BASELINE.json north_star):
+      to-scale      |got-ref| / max(|ref|, scale), scale = max|ref| over the tensor - asserted <= rtol; exact zeros do not demand
+                    exactness;
+      element-wise  |got-ref| / |ref| over the entries with |ref| >= 1e-3 * scale - always measured and reported (session summary
+                    and gpurun_out/parity_report.json), asserted <= elem_rtol where a test passes one.
+    Entries far below the tensor's scale (sums with cancellation, saturated tanh tails) carry the absolute error of the large
+    entries, so only the to-scale bound can hold for them; DESIGN.md lists which tensors meet 1e-5 in both readings."""
     got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
-    scale = max(float(np.max(np.abs(ref))), 1e-30)
-    err = np.abs(got - ref) / np.maximum(np.abs(ref), scale)
+    scale = max(float(np.max(np.abs(ref))), 1e-30) if ref.size else 1.0
+    diff = np.abs(got - ref)
+    err = diff / np.maximum(np.abs(ref), scale)
     worst = float(err.max()) if err.size else 0.0
-    assert worst <= rtol, f"{name}: max rel-to-scale err {worst:.3e} > {rtol:.1e} (scale {scale:.3e})"
+    sig = np.abs(ref) >= 1e-3 * scale
+    elem = float((diff[sig] / np.abs(ref[sig])).max()) if sig.any() else 0.0
+    PARITY.append((name, worst, elem, int(sig.sum())))
+    assert worst <= rtol, f"{name}: max rel-to-scale err {worst:.3e} > {rtol:.1e} (scale {scale:.3e}; element-wise {elem:.3e})"
+    if elem_rtol is not None:
+        assert elem <= elem_rtol, f"{name}: max element-wise rel err {elem:.3e} > {elem_rtol:.1e} (to-scale {worst:.3e})"
     return worst
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not PARITY:
+        return
+    import json
+    rows = {}
+    for name, w, e, n in PARITY:                                  # worst case per name
+        r = rows.setdefault(name, [0.0, 0.0, 0])
+        r[0], r[1], r[2] = max(r[0], w), max(r[1], e), r[2] + n
+    both = sum(1 for r in rows.values() if r[1] <= 1e-5)
+    terminalreporter.write_line(f"parity: {len(rows)} tensors compared; {both} meet 1e-5 element-wise as well as to-scale")
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump({k: {"to_scale": v[0], "element_wise": v[1], "n_significant": v[2]} for k, v in sorted(rows.items())}, f, indent=1)

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_abi_version_and_error_strings(pkg):
     L = pkg._lib.lib()
-    assert L.ofdmgan_abi_version() == 11
+    assert L.ofdmgan_abi_version() == 12
     assert L.ofdmgan_error_string(0) == b"ok"
     assert b"invalid argument" in L.ofdmgan_error_string(-1)
     assert b"streams" in L.ofdmgan_error_string(-2)

