@@ -132,6 +132,28 @@ __device__ __forceinline__ void ifft16(float (&re)[16], float (&im)[16]) {
     for (int i = 0; i < 16; ++i) { re[i] = tr[i]; im[i] = ti[i]; }
 }
 
+// The same transform with the symbols still in Box-Muller's polar pieces (Re X[k] = normal k, Im X[k] = normal 16 + k, normal
+// 2p | 2p+1 = r[p] c[p] | r[p] s[p]): the first stage a +- b forms one product and two FMAs instead of two products and two adds.
+__device__ __forceinline__ void ifft16_polar(const float (&r)[16], const float (&c)[16], const float (&s)[16], float (&re)[16],
+                                             float (&im)[16]) {
+    float tr[16], ti[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k = bitrev(2 * q, 4), pa = k >> 1, pb = pa + 4;        // X[k] and X[k + 8]
+        const float ta = r[pb] * ((k & 1) ? s[pb] : c[pb]);
+        tr[2 * q] = fmaf(r[pa], (k & 1) ? s[pa] : c[pa], ta);
+        tr[2 * q + 1] = fmaf(r[pa], (k & 1) ? s[pa] : c[pa], -ta);
+        const float tb = r[8 + pb] * ((k & 1) ? s[8 + pb] : c[8 + pb]);
+        ti[2 * q] = fmaf(r[8 + pa], (k & 1) ? s[8 + pa] : c[8 + pa], tb);
+        ti[2 * q + 1] = fmaf(r[8 + pa], (k & 1) ? s[8 + pa] : c[8 + pa], -tb);
+    }
+    ifft16_stage<2, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+    ifft16_stage<3, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+    ifft16_stage<4, 0, 1, 2, 3, 4, 5, 6, 7>(tr, ti);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { re[i] = tr[i]; im[i] = ti[i]; }
+}
+
 // ---- generator forward, inference form ---------------------------------------------------------------------------------
 // As gen_fwd_f32_infer (gen_device.cuh) with three more folds: the input scale (the normalisation of the received frame) is
 // applied to enc1's accumulators, LeakyReLU's multiply is packed over the channel pair, and the output convolution uses taps
@@ -198,10 +220,8 @@ __device__ __forceinline__ void gen_fwd_f32_scaled(const float* __restrict__ W, 
             float e0, e1, o0, o1;
             lrelu2(e, sl2, e0, e1);
             lrelu2(o, sl2, o0, o1);
-            sk[2 * o2][2 * p] = e0 + a1[2 * o2][2 * p];
-            sk[2 * o2 + 1][2 * p] = e1 + a1[2 * o2 + 1][2 * p];
-            sk[2 * o2][2 * p + 1] = o0 + a1[2 * o2][2 * p + 1];
-            sk[2 * o2 + 1][2 * p + 1] = o1 + a1[2 * o2 + 1][2 * p + 1];
+            upk2(add2(pk2(e0, e1), pk2(a1[2 * o2][2 * p], a1[2 * o2 + 1][2 * p])), sk[2 * o2][2 * p], sk[2 * o2 + 1][2 * p]);
+            upk2(add2(pk2(o0, o1), pk2(a1[2 * o2][2 * p + 1], a1[2 * o2 + 1][2 * p + 1])), sk[2 * o2][2 * p + 1], sk[2 * o2 + 1][2 * p + 1]);
         }
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -264,8 +284,12 @@ __device__ __forceinline__ LnScal ln_scalars(const ofdmgan_chan_cfg& c) {
 }
 
 // ---- one frame per thread -------------------------------------------------------------------------------------------------
-// INJ: the caller may inject host-generated draws (parity runs)
-template <int GEN, bool INJ>
+// INJ: the caller may inject host-generated draws (parity runs).  OUT: frames go to HBM (the dataset path).
+// CHAIN: which stages are compiled in.  0: whatever the configuration says, as uniform branches; 1: the linear chain (AWGN only:
+// SyntheticOFDMDataset's default); 2: the reference's non-linear chain (Rapp with p = 3, IQ imbalance, phase noise with sigma <=
+// 0.2, AWGN: --nonlinear).  The specialised instantiations are straight-line code: no branch joins, no register shuffling.
+enum { CHAIN_ANY = 0, CHAIN_LINEAR = 1, CHAIN_NONLINEAR = 2 };
+template <int GEN, bool INJ, bool OUT, int CHAIN>
 __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constant__ SimArgs a) {
     extern __shared__ float4 sm[];
     double* table = reinterpret_cast<double*>(sm + LN_W * 32 * 8);    // [n_snr][LN_TBL_NM][NC]
@@ -278,6 +302,9 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
         __syncthreads();
     }
     const LnScal sc = ln_scalars(a.cfg);
+    const bool pa_on = CHAIN == CHAIN_ANY ? sc.pa_on : CHAIN == CHAIN_NONLINEAR, p3 = CHAIN == CHAIN_ANY ? sc.p3 : true;
+    const bool pn_on = CHAIN == CHAIN_ANY ? sc.pn_on : CHAIN == CHAIN_NONLINEAR, pn_fast = CHAIN == CHAIN_ANY ? sc.pn_fast : true;
+    const bool awgn = CHAIN == CHAIN_ANY ? sc.awgn : true;
     const LnChunk ch = ln_chunk(a.B, blockIdx.x, gridDim.x, warp);
     const float* const inj_sym = INJ ? a.sym : nullptr;
     const float* const inj_pn = INJ ? a.pn : nullptr;
@@ -312,7 +339,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
         float snr_db;
         if (sc.grid_mode) {
             snr_db = fmaf(a.cfg.snr_step, (float)fbin, a.cfg.snr_lo);
-        } else if (!sc.awgn) {
+        } else if (!awgn) {
             snr_db = __int_as_float(0x7f800000);                     // +inf: reported as "no noise"
         } else if (inj_snr) {
             snr_db = inj_snr[bb];
@@ -330,13 +357,9 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
         } else {
             float r[16], c[16], s[16];
             section_polar<16>(a.keys, pf, 0u, sc.k_sym, r, c, s);
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                zr[2 * p] = r[p] * c[p]; zr[2 * p + 1] = r[p] * s[p];
-                zi[2 * p] = r[8 + p] * c[8 + p]; zi[2 * p + 1] = r[8 + p] * s[8 + p];
-            }
+            ifft16_polar(r, c, s, zr, zi);
         }
-        ifft16(zr, zi);
+        if (inj_sym) ifft16(zr, zi);
         {
             float f[2][16];
 #pragma unroll
@@ -349,8 +372,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
 
         // ---- Rapp PA (on z: gain = A (1 + |z|^2p)^(-1/2p)) and IQ imbalance; Ez = sum |z|^2
         float nr[16], ni[16], Ez = 0.f;
-        if (sc.pa_on) {
-            if (sc.p3) {
+        if (pa_on) {
+            if (p3) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float t = fmaf(zi[i], zi[i], zr[i] * zr[i]);
@@ -376,12 +399,12 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
             for (int i = 0; i < 16; ++i) {
                 Ez = fmaf(zi[i], zi[i], fmaf(zr[i], zr[i], Ez));
                 nr[i] = zr[i];
-                ni[i] = fmaf(sc.gs, zr[i], sc.gc * zi[i]);
+                ni[i] = CHAIN == CHAIN_LINEAR ? zi[i] : fmaf(sc.gs, zr[i], sc.gc * zi[i]);
             }
         }
 
         // ---- Wiener phase noise: theta_i = theta_{i-1} + sigma n_i, x_i *= e^{j theta_i}
-        if (sc.pn_on) {
+        if (pn_on) {
             auto steps = [&](auto fast) {
                 float th = 0.f, r[8], c[8], s[8];
                 if (!inj_pn) section_polar<8>(a.keys, pf, 8u, sc.k_pn, r, c, s);
@@ -396,11 +419,11 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
                     ni[i] = fmaf(xr, sn, xi * co);
                 }
             };
-            if (sc.pn_fast) steps(std::true_type{}); else steps(std::false_type{});
+            if (pn_fast) steps(std::true_type{}); else steps(std::false_type{});
         }
 
         // ---- AWGN at the measured power: sigma^2 = P / 10^(snr/10) / 2, P = mean |x|^2; the variance goes under Box-Muller's root
-        if (sc.awgn) {
+        if (awgn) {
             float P = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) P = fmaf(nr[i], nr[i], fmaf(ni[i], ni[i], P));
@@ -442,7 +465,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
         }
 
         // ---- frames to HBM when asked for (the dataset path): materialise, stage through the warp's tile, store coalesced
-        if (a.clean || a.noisy) {
+        if (OUT && (a.clean || a.noisy)) {
             float zz[2][16];
             tile_read_f32(park, lane, zz);
             __syncwarp();
@@ -460,7 +483,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
             }
             if (GEN >= 0) tile_write_f32(park, lane, zz);
         }
-        if (a.snr_out && live) a.snr_out[b] = snr_db;
+        if (OUT && a.snr_out && live) a.snr_out[b] = snr_db;
         if (GEN < 0) continue;
 
         // ---- metrics without equalisation: |s_n n - kappa z|^2 = s_n^2 |n - rho z|^2
@@ -526,7 +549,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
     }
 }
 
-template <int GEN, bool INJ>
+template <int GEN, bool INJ, bool OUT, int CHAIN>
 static int sim_lean_launch_one(const SimCall& c) {
     cudaStream_t s = c.stream;
     int rc;
@@ -541,7 +564,7 @@ static int sim_lean_launch_one(const SimCall& c) {
     int64_t want = (ng + LN_W - 1) / LN_W;
     if (want < 1) want = 1;
     const int grid = (int)(want < sms ? want : sms);                 // persistent: one CTA per SM
-    OG_CHECK(cudaFuncSetAttribute(k_sim_lean<GEN, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LN_SMEM));
+    OG_CHECK(cudaFuncSetAttribute(k_sim_lean<GEN, INJ, OUT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LN_SMEM));
     const int n = c.n_snr * NM * NC;
     void* partials = nullptr;
     if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
@@ -556,7 +579,7 @@ static int sim_lean_launch_one(const SimCall& c) {
     a.slope = c.slope;
     a.partials = (double*)partials;
     a.n_snr = c.n_snr;
-    k_sim_lean<GEN, INJ><<<grid, LN_THREADS, LN_SMEM, s>>>(a);
+    k_sim_lean<GEN, INJ, OUT, CHAIN><<<grid, LN_THREADS, LN_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
     if (partials) {
         reduce_partials_launch((const double*)partials, grid, n, c.metrics, s);
@@ -576,10 +599,28 @@ bool sim_lean_eligible(const SimCall& c) {
     if (c.rand && (c.rand->tx || c.rand->fade)) return false;
     return true;
 }
+// the stage set of a configuration (CHAIN_*)
+static int chain_of(const ofdmgan_chan_cfg& c) {
+    if (c.snr_mode == OFDMGAN_SNR_NONE) return CHAIN_ANY;
+    const int nl = OFDMGAN_IMPAIR_PA | OFDMGAN_IMPAIR_IQ | OFDMGAN_IMPAIR_PN;
+    if ((c.impair & nl) == 0) return CHAIN_LINEAR;
+    if ((c.impair & nl) == nl && c.pa_smoothness == 3.0f && c.pn_sigma <= 0.2f) return CHAIN_NONLINEAR;
+    return CHAIN_ANY;
+}
+template <int GEN, bool OUT>
+static int sim_lean_launch_chain(const SimCall& c, bool inj) {
+    if (inj) return sim_lean_launch_one<GEN, true, OUT, CHAIN_ANY>(c);     // parity runs: one instantiation with every branch
+    switch (chain_of(*c.cfg)) {
+        case CHAIN_LINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_LINEAR>(c);
+        case CHAIN_NONLINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_NONLINEAR>(c);
+        default: return sim_lean_launch_one<GEN, false, OUT, CHAIN_ANY>(c);
+    }
+}
 int sim_launch_lean(const SimCall& c) {
     const bool inj = c.rand && (c.rand->sym || c.rand->pn || c.rand->snr_db || c.rand->noise);
-    if (c.gen_kind == -1) return inj ? sim_lean_launch_one<-1, true>(c) : sim_lean_launch_one<-1, false>(c);
-    return inj ? sim_lean_launch_one<OFDMGAN_GEN_F32, true>(c) : sim_lean_launch_one<OFDMGAN_GEN_F32, false>(c);
+    const bool out = c.clean || c.noisy || c.snr;
+    if (c.gen_kind == -1) return sim_lean_launch_chain<-1, true>(c, inj);
+    return out ? sim_lean_launch_chain<OFDMGAN_GEN_F32, true>(c, inj) : sim_lean_launch_chain<OFDMGAN_GEN_F32, false>(c, inj);
 }
 
 }  // namespace og
