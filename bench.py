@@ -323,6 +323,41 @@ def main():
     n_frames_seen = float(table[:, :2, 0].sum().item())
     assert n_frames_seen == 2.0 * F * world, "metric table does not account for every frame"
 
+    # ---- sustained: the same step back to back for >= 2 s, clocks and power sampled over the whole stretch (the K-step headline above
+    # lasts tens of milliseconds; this shows what the rate does once the part has warmed up under load)
+    sustained = None
+    if not args.skip_also:
+        n_sus = max(K, int(2.2e3 / ms_step) + 1)
+        sclk = ClockSampler(clocks.uuid)
+        barrier()
+        if rank == 0:
+            sclk.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for s_ in range(n_sus):
+            fused_step(W + K + s_)
+        s1.record()
+        barrier()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        sc = sclk.stop() if rank == 0 else None
+        sustained = {"seconds": sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms / n_sus, "value": F * world * n_sus / (sus_ms * 1e-3),
+                     "unit": "frames/s", "vs_headline": (sus_ms / n_sus) / ms_step, "clocks": sc}
+
+    # ---- multi-GPU parity, outside every timed region: the checks of tests/multi_gpu_checks.py (peer exchange bit-equal to the rank-
+    # ordered sum, replicas identical, peer == NCCL == one GPU on the whole batch to 2e-5, sharded sweep == whole sweep).  A failure
+    # ends the run with a non-zero exit code.
+    parity = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import multi_gpu_checks
+        try:
+            parity = multi_gpu_checks.run_all(dev, rank, world)
+            parity["status"] = "ok"
+        except BaseException as e:                               # noqa: BLE001 - any failure on any rank fails the whole launch
+            sys.stderr.write(f"[rank {rank}] multi-GPU parity FAILED: {type(e).__name__}: {e}\n")
+            sys.stderr.flush()
+            os._exit(1)
+
     # ---- e2e: the host-buffer C-ABI call (weights from host memory in, metric table to host memory out), every step
     def e2e_step(s):
         out = ops.sim_gen_metrics_host(cfg, F, gparams=gp_h, seed=1, frame0=(s * world + rank) * F)
@@ -348,17 +383,22 @@ def main():
     ffma = ops.ffma_peak(8192, device=dev)
     flop_frame = FLOP_SIM + FLOP_GEN
     achieved = F * flop_frame / (float(np.mean(per_step_ms)) * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and F == FRAMES_PER_GPU:                # dram bytes per launch of this kernel at this size, from the ncu capture
+    # dram bytes per launch and issue-slot utilisation cannot be measured outside a profiler: they are PROFILE CONSTANTS, read from
+    # the committed ncu capture of this kernel at this size and labelled as such (profiles/r2_kernel_counters.json)
+    traffic = issue_frac = prof_src = None
+    tpath = os.path.join(ROOT, "profiles", "r2_kernel_counters.json")
+    if os.path.exists(tpath) and F == FRAMES_PER_GPU:
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        issue_frac = tj.get("issue_slots_busy_pct", 0.0) / 100.0 or None
+        prof_src = tj.get("source")
     roofline = {"bound": "fp32", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma, "traffic": traffic,
-                "kernel": "og::k_sim<SRC_GAUSS>", "algorithmic_flop_per_frame": flop_frame, "frames_per_launch": F,
+                "issue_frac": issue_frac, "traffic_and_issue_frac_source": prof_src,
+                "kernel": "og::k_sim_lean<GEN_F32, CHAIN_NONLINEAR>", "algorithmic_flop_per_frame": flop_frame, "frames_per_launch": F,
                 "peak_source": "FFMA issue-rate microbenchmark ofdmgan_ffma_peak, same run (148 SMs x 128 lanes x 2 flop x clock)",
                 "note": "inputs are generated on-chip and outputs reduced on-chip: HBM traffic per launch is the per-CTA metric "
                         "partials only, so the binding roofline is the FP32/INT issue rate, not HBM (BASELINE.json north_star)",
-                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src}
+                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "sustained": sustained}
 
     also = {}
     launches = K * 3                                             # prep_g_image + k_sim + k_reduce_partials per step
@@ -569,17 +609,35 @@ def main():
         assert np.array_equal(gm[:, :2, 0], om[:, :2, 0])
         assert np.allclose(gm[:, :2, 3], om[:, :2, 3], rtol=1e-4), "GPU and CPU sweeps disagree"
 
+    # the UNMODIFIED reference (Python / NumPy / PyTorch CPU) cannot travel to the GPU box (/root/reference does not exist there): its
+    # numbers were taken in the build container by tools/time_reference_here.py and are quoted with their host
+    cpu_unmodified = None
+    upath = os.path.join(ROOT, "profiles", "r1_reference_cpu_container.json")
+    if os.path.exists(upath):
+        cpu_unmodified = {"host": "build container (8 cores), not this box", "source": "profiles/r1_reference_cpu_container.json",
+                          "numbers": json.load(open(upath))}
     if rank == 0:
+        tr = also.get("train") or {}
+        summary = {"frames_per_s": value, "ms_per_step": ms_step, "roofline_frac": achieved / ffma, "e2e_frames_per_s": e2e_value,
+                   "sustained_frames_per_s": sustained and sustained["value"], "train_ms_per_step": tr.get("ms_per_step"),
+                   "train_samples_per_s": tr.get("samples_per_s"), "train_frac_of_ffma_peak": tr.get("fp32_frac_of_ffma_peak"),
+                   "train_ms_per_step_nccl": tr.get("ms_per_step_with_nccl_exchange"),
+                   "multi_gpu_parity": parity["status"] if parity else ("n/a (1 GPU)" if world == 1 else None), "n_gpus": world}
         line = {"metric": "OFDM frames/s: fused channel sim + G inference", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAME, "frames_per_gpu_per_step": F, "parallelism": f"frame-sharded x{world}",
                            "l2": "no HBM inputs: frames are generated on-chip from Philox counters and reduced on-chip",
-                           "weights": "random-init (Xavier-uniform, seed 0)"},
+                           "weights": "random-init (Xavier-uniform, seed 0)",
+                           "train": {"workload": "C3: CWGAN-GP step (n_critic 5, GP weight 10) at 65,536 frames per GPU, data-parallel",
+                                     "ms_per_step": tr.get("ms_per_step"), "samples_per_s": tr.get("samples_per_s"),
+                                     "frac_of_ffma_peak": tr.get("fp32_frac_of_ffma_peak"), "exchange": tr.get("exchange"),
+                                     "ms_per_step_with_nccl_exchange": tr.get("ms_per_step_with_nccl_exchange")},
+                           "multi_gpu_parity": parity},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "ofdmgan_sim_gen_metrics_host (host weights in, host metric table out, synchronous)"},
-                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "also": also,
-                "per_step_ms": per_step_ms}
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "cpu_baseline_unmodified": cpu_unmodified, "per_step_ms": per_step_ms, "also": also, "summary": summary}
         _emit(saved_stdout, line)
     if world > 1:
         dist.destroy_process_group()

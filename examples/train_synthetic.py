@@ -53,6 +53,7 @@ def main(argv=None):
                 print(f"step {i + 1:6d}  rec {st['rec_loss']:.4f}  d_loss {st['d_loss']:+.4f}  gp {st['gradient_penalty']:.4f}  "
                       f"W {st['wasserstein_distance']:+.4f}  {(i + 1) * args.batch * world / (time.time() - t0):.3g} samples/s", flush=True)
     step.store_to(G, D)
+    step.close()                                                 # unmaps the peer exchange blocks (a barrier: every rank calls it)
     res = run_benchmark(G, n_trials=20000, nonlinear=args.nonlinear, pa_saturation=args.pa_saturation, seed=123)
     if rank == 0:
         for snr in res["GAN"]:

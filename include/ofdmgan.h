@@ -39,7 +39,7 @@ extern "C" {
 #define OFDMGAN_E_ARG (-1)                /* null pointer / bad enum / bad size */
 #define OFDMGAN_E_STREAMS (-2)            /* reserved (stream bookkeeping failure) */
 #define OFDMGAN_E_UNSUPPORTED (-3)        /* valid in the reference but not built here (named in DESIGN.md) */
-#define OFDMGAN_E_COMM (-4)               /* a data-parallel peer did not arrive within the wait limit */
+#define OFDMGAN_E_COMM (-4)               /* a data-parallel peer did not arrive within the wait limit (see ofdmgan_comm_create) */
 
 /* Parameter packing = torch parameters()/state_dict order, flattened (models/generator.py:129-164,
  * models/discriminator.py:78-100):
@@ -309,7 +309,11 @@ int ofdmgan_adam_ctr(float* p_dev, float* m_dev, float* v_dev, const float* g_de
 int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handle64);
 int ofdmgan_comm_connect(ofdmgan_comm* comm, const void* all_handles);
 int ofdmgan_comm_destroy(ofdmgan_comm* comm);
-int ofdmgan_comm_check(ofdmgan_comm* comm, void* stream);   /* synchronises; OFDMGAN_E_COMM if a wait ever timed out */
+/* synchronises; non-zero once a wait has run out: a peer that does not arrive within the wait limit (environment variable
+ * OFDMGAN_COMM_TIMEOUT_S at ofdmgan_comm_create, default 120 s) makes the waiting kernel set the communicator's error word and TRAP, so
+ * that launch and every later call on the context fail with a CUDA error - no rank continues on a partial sum, replicas cannot
+ * diverge silently.  Put a barrier after rank-asymmetric work (rank-0 checkpointing, validation) that may exceed the limit. */
+int ofdmgan_comm_check(ofdmgan_comm* comm, void* stream);
 int ofdmgan_allreduce_adam(ofdmgan_comm* comm, float* g_dev, int n, float* p_dev, float* m_dev, float* v_dev, int n_params,
                            double lr, double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
 

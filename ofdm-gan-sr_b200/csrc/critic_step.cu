@@ -186,12 +186,10 @@ __global__ void __launch_bounds__(1024) k_critic_tail(const float* __restrict__ 
     // last block: every group's gradients are in `out`
     if (threadIdx.x == 0) *arrivals = 0u;
     if (world > 1) {                                             // data parallel: sum the 528 floats over the ranks through peer memory
-        __shared__ int timed_out;
         PeerBlock* mine = peers.p[rank];
         const unsigned int seq = mine->seq + 1u;
-        const bool ok = peer_allreduce_block(peers, rank, world, seq, out, OFDMGAN_CRITIC_OUT, &timed_out);
+        peer_allreduce_block(peers, rank, world, seq, out, OFDMGAN_CRITIC_OUT);   // traps if a peer never arrives
         if (threadIdx.x == 0) mine->seq = seq;
-        if (!ok) return;
     }
     const int t = *step_dev + 1;
     const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);

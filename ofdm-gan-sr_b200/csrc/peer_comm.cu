@@ -11,6 +11,7 @@
 // Exchange blocks are cudaMalloc'ed by the library and shared between the one-process-per-GPU ranks through CUDA IPC handles
 // that the host side swaps over torch.distributed.  The same block-wide exchange is the middle of the critic tail kernel
 // (critic_step.cu, ofdmgan_critic_train_ctr).
+#include <cstdlib>
 #include <cstring>
 
 #include "peer_comm.cuh"
@@ -28,10 +29,8 @@ __global__ void __launch_bounds__(1024) k_allreduce_adam(PeerPtrs peers, int ran
     const int tid = threadIdx.x;
     int t_adam = 0;
     if (step_dev) { t_adam = *step_dev + 1; coef = adam_coef_dev(lr, b1, b2, eps, t_adam); }
-    __shared__ int timed_out;
-    const bool ok = peer_allreduce_block(peers, rank, world, seq, g, n, &timed_out);
+    peer_allreduce_block(peers, rank, world, seq, g, n);         // traps if a peer never arrives: nothing below runs on a partial sum
     if (tid == 0) { mine->seq = seq; if (step_dev) *step_dev = t_adam; }
-    if (!ok) return;
     for (int i = tid; i < n_params; i += blockDim.x) adam_one(p[i], m[i], v[i], __fmul_rn(g[i], grad_scale), coef);
 }
 
@@ -64,6 +63,13 @@ int ofdmgan_comm_create(int rank, int world, ofdmgan_comm** out, void* ipc_handl
     for (int r = 0; r < PC_MAX_WORLD; ++r) c->peers.p[r] = nullptr;
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaGetDevice(&c->device);
+    {                                                            // the wait limit in SM clocks
+        double secs = PC_DEFAULT_TIMEOUT_S;
+        if (const char* env = getenv("OFDMGAN_COMM_TIMEOUT_S")) { const double v = atof(env); if (v > 0.0) secs = v; }
+        int khz = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        c->peers.spin_limit = (long long)(secs * 1e3 * (double)(khz > 0 ? khz : 2000000));
+    }
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->local, sizeof(PeerBlock));
     if (e == cudaSuccess) e = cudaMemset(c->local, 0, sizeof(PeerBlock));
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
@@ -104,7 +110,8 @@ int ofdmgan_comm_destroy(ofdmgan_comm* c) {
     return 0;
 }
 
-// 0 while every wait so far completed; OFDMGAN_E_COMM after a peer failed to arrive within the spin limit.  Synchronises the stream.
+// 0 while every wait so far completed.  A wait that ran out traps its kernel, so afterwards this (like every call on the context)
+// returns the CUDA error of the failed launch; OFDMGAN_E_COMM if the error word could still be read.  Synchronises the stream.
 int ofdmgan_comm_check(ofdmgan_comm* c, void* stream) {
     if (!c) return OFDMGAN_E_ARG;
     int err = 0;

@@ -6,6 +6,7 @@ evaluated by one fused launch instead of building and differentiating an autogra
 """
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from .. import ops
 from .._lib import D_NPARAMS, OfdmGanError
@@ -36,6 +37,7 @@ class _CriticFunction(torch.autograd.Function):
         return score.view(-1, 1)
 
     @staticmethod
+    @once_differentiable                     # first-order only: a double backward through this node must fail loudly, not drop terms
     def backward(ctx, g):
         cand, cond, flat = ctx.saved_tensors
         dcand, dcond, dflat = ops.disc_bwd_f32(cand, cond, flat, g.reshape(-1), ctx.slope, need_dcand=ctx.need[0],
@@ -62,6 +64,7 @@ class _GradientPenaltyFunction(torch.autograd.Function):
         return gp.reshape(())
 
     @staticmethod
+    @once_differentiable                     # first-order only: a double backward through this node must fail loudly, not drop terms
     def backward(ctx, g):
         if not ctx.has:
             return (None,) * (5 + len(ctx.shapes))

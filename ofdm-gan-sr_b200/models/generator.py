@@ -8,6 +8,7 @@ from typing import List
 
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from .. import ops
 from .._lib import G_NPARAMS, OfdmGanError
@@ -29,6 +30,7 @@ class _GeneratorFunction(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable                     # first-order only: a double backward through this node must fail loudly, not drop terms
     def backward(ctx, dy):
         x, flat = ctx.saved_tensors
         dx, dflat = ops.gen_bwd_f32(x, flat, dy.contiguous(), ctx.slope, need_dx=ctx.need_dx)

@@ -35,6 +35,7 @@ class CWGANGPStep:
         self.g, self.d = f(gparams, G_NPARAMS), f(dparams, D_NPARAMS)
         z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)
         self.g_m, self.g_v, self.d_m, self.d_v = z(G_NPARAMS), z(G_NPARAMS), z(D_NPARAMS), z(D_NPARAMS)
+        self._graph = None
         self.lr_g, self.lr_d, self.betas, self.eps = lr_g, lr_d, tuple(betas), eps
         self.n_critic, self.gp_weight, self.rec_weight, self.adv_weight = n_critic, gp_weight, rec_weight, adv_weight
         self.slope, self.seed = leaky_slope, seed
@@ -51,7 +52,7 @@ class CWGANGPStep:
         # on the device.  With several ranks it needs the peer-memory exchange (a captured graph cannot hold the NCCL fallback here).
         self.use_graph = bool(graph) and backend is ops
         self._ctr = torch.zeros(2, dtype=torch.int32, device=self.device) if self.use_graph else None   # [critic steps, generator steps]
-        self._graph, self._static, self._calls_with_shape = None, None, 0
+        self._static, self._calls_with_shape = None, 0
         # gradient exchange: "peer" = all-reduce fused with Adam over NVLink peer memory (one launch, ops.PeerComm),
         # "nccl" = dist.all_reduce then the Adam kernel, "auto" = peer when the ranks can map each other's memory
         if exchange not in ("auto", "peer", "nccl"):
@@ -71,6 +72,69 @@ class CWGANGPStep:
                 self.comm = None
         if self.distributed and self.comm is None:
             self.use_graph = False                               # NCCL exchange: eager launches
+
+    # Host scalars are baked into a captured CUDA graph: assigning any of them (e.g. the StepLR halving of train.py:497-514 writing
+    # lr_g / lr_d) drops the captured graph, and the next step() captures a new one with the current values.
+    _GRAPH_SCALARS = ("lr_g", "lr_d", "betas", "eps", "n_critic", "gp_weight", "rec_weight", "adv_weight", "slope", "seed")
+
+    def __setattr__(self, name, value):
+        if name in CWGANGPStep._GRAPH_SCALARS and getattr(self, "_graph", None) is not None and getattr(self, name, None) != value:
+            object.__setattr__(self, "_graph", None)
+            object.__setattr__(self, "_calls_with_shape", 1)      # the library's scratch is sized already: capture on the next call
+        object.__setattr__(self, name, value)
+
+    # ---- checkpointing: everything train.py:411-445 saves for the two optimisers, in torch.optim.Adam's own layout
+    def state_dict(self):
+        """Parameters, Adam moments and step counters (flat fp32 vectors in state_dict order)."""
+        ctr = self._ctr.cpu().tolist() if self._ctr is not None and self.use_graph else None
+        return {"g": self.g.clone(), "d": self.d.clone(), "g_m": self.g_m.clone(), "g_v": self.g_v.clone(), "d_m": self.d_m.clone(),
+                "d_v": self.d_v.clone(), "d_steps": self.d_steps, "g_steps": self.g_steps, "device_counters": ctr,
+                "hyper": {k: getattr(self, k) for k in self._GRAPH_SCALARS}}
+
+    def load_state_dict(self, sd):
+        for k in ("g", "d", "g_m", "g_v", "d_m", "d_v"):
+            getattr(self, k).copy_(torch.as_tensor(sd[k]).to(self.device))
+        self.d_steps, self.g_steps = int(sd["d_steps"]), int(sd["g_steps"])
+        if self._ctr is not None:
+            self._ctr.copy_(torch.tensor([self.d_steps, self.g_steps], dtype=torch.int32))
+        for k, v in sd.get("hyper", {}).items():
+            setattr(self, k, tuple(v) if k == "betas" else v)
+
+    def adam_state_dict(self, which, module):
+        """The state_dict a torch.optim.Adam over `module.parameters()` would hold after the same steps (`which` = "g" | "d"): what
+        train.py:417-418 stores under 'optimizer_G_state_dict' / 'optimizer_D_state_dict'."""
+        m, v, t, lr = (self.g_m, self.g_v, self.g_steps, self.lr_g) if which == "g" else (self.d_m, self.d_v, self.d_steps, self.lr_d)
+        state, off = {}, 0
+        for i, p in enumerate(module.parameters()):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(t)), "exp_avg": m[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": v[off:off + n].view_as(p).clone()}
+            off += n
+        group = {"lr": lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(state)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_adam_state_dict(self, which, sd):
+        """Inverse of adam_state_dict: resume from a checkpoint written by the reference trainer (train.py:434-445)."""
+        m, v = (self.g_m, self.g_v) if which == "g" else (self.d_m, self.d_v)
+        off, t = 0, 0
+        for i in sorted(sd["state"]):
+            st = sd["state"][i]
+            n = st["exp_avg"].numel()
+            m[off:off + n].copy_(st["exp_avg"].reshape(-1).to(self.device))
+            v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1).to(self.device))
+            t = int(st["step"])
+            off += n
+        if off != m.numel():
+            raise OfdmGanError(f"optimizer state holds {off} values, expected {m.numel()}")
+        grp = sd["param_groups"][0]
+        if which == "g":
+            self.g_steps, self.lr_g = t, grp["lr"]
+        else:
+            self.d_steps, self.lr_d = t, grp["lr"]
+        self.betas, self.eps = tuple(grp["betas"]), grp["eps"]
+        if self._ctr is not None:
+            self._ctr.copy_(torch.tensor([self.d_steps, self.g_steps], dtype=torch.int32))
 
     def _flat(self, t, n):
         if isinstance(t, torch.nn.Module):
@@ -128,7 +192,7 @@ class CWGANGPStep:
         self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
         for c in range(self.n_critic):
             out = self._dout[c]
-            if hasattr(self.k, "critic_train") and B > 0:        # (an empty shard takes the unfused calls: same exchange sequence)
+            if hasattr(self.k, "critic_train"):
                 # loss + backward, then ONE tail launch (gradient reduction, the sum over the ranks through peer memory, Adam,
                 # weight-image refresh); from the second iteration on the image installed by the previous tail is still current
                 self.k.critic_train(clean, noisy, self._fake, self.d, self.d_m, self.d_v, self._ctr[0:1], self.lr_d, self.betas[0],
@@ -164,10 +228,13 @@ class CWGANGPStep:
     def step(self, clean, noisy, alphas=None):
         """One trainer iteration on this rank's shard of the batch (train.py:327-344).
 
-        clean, noisy: [B_local,2,16] CUDA tensors.  alphas (optional, [n_critic,B_local]): the torch.rand draws of
+        clean, noisy: [B_local,2,16] CUDA tensors; B_local must be the same on every rank (the global batch is B_local x world).  alphas (optional, [n_critic,B_local]): the torch.rand draws of
         compute_gradient_penalty for parity runs; by default alpha comes from Philox(seed, global sample index,
         critic-step counter), so the global batch does not depend on the number of ranks.
         """
+        if clean.shape[0] < 1:
+            raise OfdmGanError("CWGANGPStep.step: empty local batch - every rank must hold the same, non-empty number of frames "
+                               "(gradients are scaled by 1 / (B_local x world); GPUBatchLoader shards that way)")
         if self.use_graph:
             if alphas is not None:
                 raise OfdmGanError("graph=True draws alpha from Philox; injected alphas need graph=False")

@@ -137,7 +137,9 @@ class GPUBatchLoader:
     """Iterates a SyntheticOFDMDataset in device-resident batches: the replacement for DataLoader(num_workers=0) at
     train.py:660 (the dict it yields is what train.py:327-329 consumes; `.to(device)` is then a no-op).
 
-    rank / world_size shard each global batch by contiguous frame ranges (no exchange needed)."""
+    rank / world_size shard each global batch by contiguous frame ranges (no exchange needed).  Every rank always gets the SAME
+    local batch size - the data-parallel step scales gradients by 1 / (B_local x world): with drop_last=False the ragged last global
+    batch is split evenly and its up to world-1 leftover frames are dropped."""
 
     def __init__(self, dataset: SyntheticOFDMDataset, batch_size: int = 32, drop_last: bool = True, rank: int = 0, world_size: int = 1):
         self.dataset, self.batch_size, self.drop_last, self.rank, self.world = dataset, batch_size, drop_last, rank, world_size
@@ -145,16 +147,19 @@ class GPUBatchLoader:
 
     def __len__(self) -> int:
         n, g = len(self.dataset), self.batch_size * self.world
-        return n // g if self.drop_last else (n + g - 1) // g
+        tail = 0 if self.drop_last else (1 if (n - (n // g) * g) // self.world > 0 else 0)
+        return n // g + tail
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         self.dataset.set_epoch(self._epoch)
         self._epoch += 1
         n, g = len(self.dataset), self.batch_size * self.world
-        for i in range(len(self)):
-            lo = i * g + self.rank * self.batch_size
-            B = min(self.batch_size, max(0, n - lo))
-            yield self.dataset.batch(lo, B)
+        full = n // g
+        for i in range(full):
+            yield self.dataset.batch(i * g + self.rank * self.batch_size, self.batch_size)
+        per = (n - full * g) // self.world                          # the ragged last global batch, in equal shards
+        if not self.drop_last and per > 0:
+            yield self.dataset.batch(full * g + self.rank * per, per)
 
 
 def create_dataloader(dataset, batch_size: int = 32, shuffle: bool = True, num_workers: int = 4, drop_last: bool = True,

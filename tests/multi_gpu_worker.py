@@ -1,87 +1,20 @@
-"""Worker of tests/test_gpu_multi.py (one process per GPU, launched by torch.distributed.run)."""
+"""Worker of tests/test_gpu_multi.py (one process per GPU, launched by torch.distributed.run): runs tests/multi_gpu_checks.py."""
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import ofdm_gan_sr_b200 as pkg  # noqa: E402
-from ofdm_gan_sr_b200.train_step import CWGANGPStep  # noqa: E402
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import multi_gpu_checks  # noqa: E402
 
-ops = pkg.ops
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", torch.cuda.current_device())
 dist.init_process_group("nccl", device_id=dev)
-
-# ---- 1. the exchange alone: rank-ordered sum, identical bits on every rank, Adam applied to the prefix
-comm = ops.PeerComm(None, dev)
-rng = np.random.default_rng(1234)
-msgs = rng.standard_normal((world, 7, 528)).astype(np.float32)           # every rank knows every rank's messages
-p0 = rng.standard_normal(521).astype(np.float32)
-p, m, v = torch.as_tensor(p0).to(dev), torch.zeros(521, device=dev), torch.zeros(521, device=dev)
-pr, mr, vr = p.clone(), m.clone(), v.clone()
-for it in range(7):
-    g = torch.as_tensor(msgs[rank, it]).to(dev)
-    comm.allreduce_adam(g, p, m, v, 2e-4, 0.0, 0.9, 1e-8, it + 1)
-    want = torch.zeros(528, device=dev)
-    for r in range(world):                                               # the kernel's order: rank 0, 1, ...
-        want = want + torch.as_tensor(msgs[r, it]).to(dev)
-    assert torch.equal(g, want), (rank, it, float((g - want).abs().max()))
-    ops.adam(pr, mr, vr, want, 2e-4, 0.0, 0.9, 1e-8, it + 1)
-    assert torch.equal(p, pr) and torch.equal(m, mr) and torch.equal(v, vr)
-plain = torch.full((264,), float(rank + 1), device=dev)
-comm.allreduce_adam(plain)                                               # n_params = 0: plain all-reduce
-assert torch.equal(plain, torch.full((264,), world * (world + 1) / 2.0, device=dev))
-comm.check()
-everyone = [torch.empty_like(p) for _ in range(world)]
-dist.all_gather(everyone, p)
-assert all(torch.equal(e, everyone[0]) for e in everyone)                # replicas bit-identical
-comm.close()
-
-# ---- 2. the training step: peer exchange == NCCL exchange == one GPU on the whole batch (to rounding)
-B = 2048
-cfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
-clean_all, noisy_all, _ = ops.chan_sim(cfg, B * world, seed=5, frame0=0, device=dev)
-clean, noisy = clean_all[rank * B:(rank + 1) * B].contiguous(), noisy_all[rank * B:(rank + 1) * B].contiguous()
-gp = (np.random.default_rng(7).standard_normal(258) * 0.3).astype(np.float32)
-dp = (np.random.default_rng(8).standard_normal(521) * 0.2).astype(np.float32)
-runs = {}
-for mode in ("peer", "nccl", "peer+graph"):
-    t = CWGANGPStep(gp, dp, device=dev, exchange=mode.split("+")[0], graph=mode.endswith("graph"))
-    assert (t.comm is not None) == mode.startswith("peer") and t.use_graph == mode.endswith("graph")
-    for _ in range(4):
-        t.step(clean, noisy)
-    runs[mode] = (t.g.clone(), t.d.clone(), t.stats())
-    t.close()
-solo = CWGANGPStep(gp, dp, device=dev, process_group=None, exchange="nccl")
-solo.distributed, solo.world, solo.rank = False, 1, 0                    # the whole batch on this GPU, no exchange
-for _ in range(4):
-    solo.step(clean_all, noisy_all)
-for name, (g, d, st) in runs.items():
-    for a, b, what in ((g, solo.g, "G"), (d, solo.d, "D")):
-        err = float((a - b).abs().max()) / float(b.abs().max())
-        assert err < 2e-5, (name, what, err)
-    assert abs(st["d_loss"] - solo.stats()["d_loss"]) < 1e-4 * max(1.0, abs(solo.stats()["d_loss"]))
-err = float((runs["peer"][0] - runs["nccl"][0]).abs().max())
-assert err < 1e-6, err                                                   # same sums up to the order NCCL happens to use
-err = float((runs["peer+graph"][1] - runs["peer"][1]).abs().max()) / float(runs["peer"][1].abs().max())
-assert err < 1e-6, err                                                   # replayed graph == eager launches
-# ---- 3. the sweep: frame-sharded over the ranks == the whole range on one GPU (counts exact, sums to rounding)
-from ofdm_gan_sr_b200.sweep import run_benchmark, run_sweep  # noqa: E402
-cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=1000)
-total = 7 * 1000 * 37 + 13                                               # ragged on purpose
-sharded = run_sweep(cfg, total, gparams=gp, seed=9, device=dev)          # all ranks, all-reduced
-whole = ops.sim_gen_metrics(cfg, total, gparams=gp, seed=9, device=dev).cpu().numpy()
-assert np.array_equal(sharded[:, :, 0], whole[:, :, 0]) and sharded[:, :2, 0].sum() == 2 * total
-assert np.allclose(sharded[:, :2, 1:5], whole[:, :2, 1:5], rtol=5e-6, atol=0)      # fp32 per-thread partial sums regroup
-res = run_benchmark(gp, n_trials=5000, nonlinear=True, pa_saturation=0.8, device=dev, seed=4)
-every = [None] * world
-dist.all_gather_object(every, {m: {s: v["evm"] for s, v in res[m].items()} for m in res})
-assert all(e == every[0] for e in every)                                 # every rank holds the same table
-dist.barrier()
+res = multi_gpu_checks.run_all(dev, rank, world)
 if rank == 0:
-    print("multi-gpu worker ok: world", world)
+    print("multi-gpu worker ok: world", world, res)
 dist.destroy_process_group()

@@ -99,3 +99,29 @@ def test_fused_critic_iteration_is_bitwise_the_unfused_one(setup):
         for k in ("d", "m", "v", "ctr"):
             assert torch.equal(a[k], b[k]), (it, k)
     assert int(b["ctr"]) == 6
+
+
+def test_graph_is_recaptured_when_a_hyper_parameter_changes():
+    """the learning rate is a host scalar baked into the captured graph: assigning lr_d / lr_g (StepLR, train.py:497-514) must take
+    effect on the next step - graph replay == eager launches with the same schedule"""
+    import ofdm_gan_sr_b200 as pkg
+    from ofdm_gan_sr_b200.train_step import CWGANGPStep
+    ops = pkg.ops
+    rng = np.random.default_rng(3)
+    gp, dp = (rng.standard_normal(258) * 0.3).astype(np.float32), (rng.standard_normal(521) * 0.2).astype(np.float32)
+    clean, noisy, _ = ops.chan_sim(ops.make_cfg(), 512, seed=2)
+    runs = []
+    for graph in (True, False):
+        t = CWGANGPStep(gp, dp, graph=graph, seed=5)
+        for i in range(6):
+            if i == 3:
+                t.lr_d, t.lr_g = t.lr_d * 0.5, t.lr_g * 0.5
+            t.step(clean, noisy)
+        runs.append((t.g.clone(), t.d.clone()))
+    for a, b in zip(*runs):
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+    # and the halved rate really was used: a run that never halves ends elsewhere
+    t = CWGANGPStep(gp, dp, graph=True, seed=5)
+    for i in range(6):
+        t.step(clean, noisy)
+    assert float((t.d - runs[0][1]).abs().max()) > 1e-5 * float(t.d.abs().max())

@@ -155,3 +155,68 @@ def test_shard_ranges_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeDataset:
+    """stands in for SyntheticOFDMDataset (its batches are made on the GPU): records which frame ranges a loader asks for"""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def set_epoch(self, e):
+        self.epoch = e
+
+    def batch(self, lo, B):
+        return (lo, B)
+
+
+@pytest.mark.parametrize("n,bs,world", [(1000, 64, 1), (1000, 64, 4), (64 * 8 + 3, 64, 4), (64 * 8 + 37, 64, 8), (10, 64, 4)])
+def test_loader_shards_are_equal_and_disjoint(n, bs, world):
+    """every rank steps on the same local batch size (CWGANGPStep scales by 1 / (B_local x world)), also on a ragged last batch"""
+    from ofdm_gan_sr_b200.utils.dataset import GPUBatchLoader
+    for drop_last in (True, False):
+        per_rank = [list(GPUBatchLoader(_FakeDataset(n), bs, drop_last=drop_last, rank=r, world_size=world)) for r in range(world)]
+        assert len({len(p) for p in per_rank}) == 1                          # same number of steps everywhere
+        assert all(len(p) == len(GPUBatchLoader(_FakeDataset(n), bs, drop_last=drop_last, rank=0, world_size=world)) for p in per_rank)
+        covered = []
+        for step in zip(*per_rank):
+            assert len({B for _, B in step}) == 1 and step[0][1] > 0         # equal, non-empty shards
+            covered += [(lo, lo + B) for lo, B in step]
+        covered.sort()
+        assert all(a[1] <= b[0] for a, b in zip(covered[:-1], covered[1:]))  # disjoint
+        used = sum(hi - lo for lo, hi in covered)
+        assert used <= n and (drop_last or n - used < world)                 # drop_last=False loses at most world-1 frames
+
+
+def test_trainer_state_round_trips_and_maps_to_torch_adam():
+    """state_dict / adam_state_dict: resume continues bit for bit, and the moments land in torch.optim.Adam's own layout
+    (train.py:411-445 stores optimizer_G/D_state_dict)."""
+    from ofdm_gan_sr_b200.train_step import CWGANGPStep
+    r = dict(np.load(os.path.join(GOLDEN, "ref_fp32.npz")))
+    B = 32
+    clean, noisy = torch.from_numpy(r["tr_clean"].reshape(-1, 2, 16)[:B]), torch.from_numpy(r["tr_noisy"].reshape(-1, 2, 16)[:B])
+    a = CWGANGPStep(r["tr_g0"], r["tr_d0"], seed=3, backend=OracleBackend)
+    a.step(clean, noisy)
+    sd = a.state_dict()
+    b = CWGANGPStep(np.zeros(258, np.float32), np.zeros(521, np.float32), seed=3, backend=OracleBackend)
+    b.load_state_dict(sd)
+    a.step(clean, noisy)
+    b.step(clean, noisy)
+    assert torch.equal(a.g, b.g) and torch.equal(a.d, b.d) and torch.equal(a.d_v, b.d_v) and (a.d_steps, a.g_steps) == (b.d_steps, b.g_steps)
+    # torch.optim.Adam accepts the exported state and a step from it equals the flat kernel's step
+    G = torch.nn.ModuleList([torch.nn.Conv1d(2, 4, 3), torch.nn.Conv1d(4, 8, 3), torch.nn.Conv1d(8, 4, 3), torch.nn.Conv1d(4, 2, 3)])
+    assert sum(p.numel() for p in G.parameters()) == 258
+    a.store_to(generator=G)
+    opt = torch.optim.Adam(G.parameters(), lr=a.lr_g, betas=a.betas, eps=a.eps)
+    opt.load_state_dict(a.adam_state_dict("g", G))
+    st = opt.state_dict()["state"]
+    assert int(st[0]["step"]) == a.g_steps == 2
+    assert torch.equal(torch.cat([st[i]["exp_avg"].reshape(-1) for i in sorted(st)]), a.g_m)
+    c = CWGANGPStep(np.zeros(258, np.float32), np.zeros(521, np.float32), backend=OracleBackend)
+    c.load_adam_state_dict("g", opt.state_dict())
+    assert torch.equal(c.g_m, a.g_m) and torch.equal(c.g_v, a.g_v) and c.g_steps == 2 and c.lr_g == a.lr_g
+    with pytest.raises(Exception):
+        a.step(clean[:0], noisy[:0])                                        # an empty local batch is an error, not a silent no-op
