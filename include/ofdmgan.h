@@ -13,9 +13,14 @@
  *    on that stream unless it says "host" in its name; *_host entry points take host buffers, do their own
  *    H2D / D2H copies and synchronise the stream before returning.
  *  - returns 0 on success, a positive cudaError_t, or a negative OFDMGAN_E_* argument error.  Never throws,
- *    never calls exit().  Safe to call from several host threads and on several streams: the network weights live in
- *    one constant-memory image per device, so calls are serialised inside the library (a call on a new stream is
- *    ordered after the previous call's stream); streams do not overlap inside libofdmgan.
+ *    never calls exit().  Safe to call from several host threads and on several streams.
+ *  - weights: a `params` / ROM pointer in HOST memory (inference) is turned into the kernel's weight image on the host and passed BY
+ *    VALUE in the kernel's parameter block: ofdmgan_gen_fwd_f32, ofdmgan_gen_fwd_q and the headline configuration of
+ *    ofdmgan_sim_gen_metrics(_host) (ofdmgan_sim_impl_for == 1) then touch no shared state, take no lock, and calls on different
+ *    streams run independently (scratch is per stream).  A pointer in DEVICE memory (training: the optimiser updates the weights on
+ *    the device) goes through one constant-memory image per network and device, refreshed stream-ordered before the launch; those
+ *    calls, and the general simulator kernel, are serialised inside the library (a call on a new stream is ordered after the
+ *    previous such call's stream).
  *  - there is NO CPU fallback: without a CUDA device every compute entry point returns a cudaError_t.
  */
 #ifndef OFDMGAN_H

@@ -44,6 +44,9 @@ struct CallGuard {
 };
 // device scratch owned by the library (per slot), `bytes` each; returns the slot's pointer
 int scratch_for_slot(int slot, size_t bytes, int which, void** ptr);
+// device scratch owned by the library PER STREAM (and device): the entry points that carry their weights by value hold no lock, so
+// two streams must never share a scratch buffer
+int scratch_for_stream(cudaStream_t s, size_t bytes, int which, void** ptr);
 // copy `n` floats that may live on the host or the device into device scratch (no-op if already on device)
 int to_device_f32(const float* src, int n, int slot, int which, cudaStream_t s, const float** dev);
 

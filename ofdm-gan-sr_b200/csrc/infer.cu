@@ -10,12 +10,14 @@
 namespace og {
 
 // ------------------------------------------------------------------------------------------------ (2) fp32 G
+// BYVAL: the weight image arrives in the parameter block (host-resident weights) instead of the __constant__ image
+template <bool BYVAL>
 __global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_f32(const float* __restrict__ x, float* __restrict__ y, int64_t B,
-                                                            int slot, float slope) {
+                                                            float slope, const __grid_constant__ GImage gi) {
     __shared__ float4 sm[OG_THREADS * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* wsm = sm + warp * 32 * 8;
-    const float* W = c_g;
+    const float* W = BYVAL ? gi.w : c_g;
     const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t base = t * OG_THREADS + warp * 32;
@@ -34,13 +36,14 @@ __device__ __forceinline__ uint64_t digest_word(uint32_t v16, uint64_t index) {
     return h;
 }
 
+// the ROM image always travels by value: the ROMs are host memory (static inference weights)
 template <int MODE>
 __global__ void __launch_bounds__(OG_THREADS) k_gen_fwd_q(const int16_t* __restrict__ x, int16_t* __restrict__ y, int64_t B,
-                                                          int slot, unsigned long long* __restrict__ digest) {
+                                                          unsigned long long* __restrict__ digest, const __grid_constant__ QImage qi) {
     __shared__ uint4 sm[OG_THREADS * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* wsm = sm + warp * 32 * 4;
-    const float* Q = c_q;
+    const float* Q = qi.w;
     const int64_t ntiles = (B + OG_THREADS - 1) / OG_THREADS;
     unsigned long long dsum = 0, dxor = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -252,12 +255,18 @@ int ofdmgan_gen_fwd_f32(const float* x_dev, const float* gparams258, float* y_de
     if (B == 0 && gparams258) return 0;                       // empty batch: nothing to launch, pointers may be NULL
     if (!x_dev || !y_dev || !gparams258 || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    int slot, rc;
-    CallGuard guard(s);
+    static GImage none;                                        // (contents unused on the __constant__ path)
+    if (is_host_pointer(gparams258)) {                         // inference weights: by value, no shared state, no lock
+        GImage gi;
+        g_image_host(gparams258, gi);
+        k_gen_fwd_f32<true><<<grid_for(B, OG_THREADS, 4), OG_THREADS, 0, s>>>(x_dev, y_dev, B, leaky_slope, gi);
+        return (int)cudaGetLastError();
+    }
+    int rc;
+    CallGuard guard(s);                                        // device-resident (training) weights: the __constant__ image
     if ((rc = guard.rc)) return rc;
-    slot = 0;
-    if ((rc = upload_g(gparams258, slot, s))) return rc;
-    k_gen_fwd_f32<<<grid_for(B, OG_THREADS, 4), OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, leaky_slope);
+    if ((rc = upload_g(gparams258, 0, s))) return rc;
+    k_gen_fwd_f32<false><<<grid_for(B, OG_THREADS, 4), OG_THREADS, 0, s>>>(x_dev, y_dev, B, leaky_slope, none);
     return (int)cudaGetLastError();
 }
 
@@ -267,16 +276,13 @@ int ofdmgan_gen_fwd_q(const int16_t* x_dev, const int8_t* wrom_host, const int16
     if (B == 0 && wrom_host && brom_host) return 0;
     if (!x_dev || !y_dev || !wrom_host || !brom_host || B < 0 || !aligned16(x_dev) || !aligned16(y_dev)) return OFDMGAN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    int slot, rc;
-    CallGuard guard(s);
-    if ((rc = guard.rc)) return rc;
-    slot = 0;
-    if ((rc = upload_q(wrom_host, brom_host, slot, s))) return rc;
+    QImage qi;                                                 // built on the host, passed by value: no shared state, no lock
+    q_image_host(wrom_host, brom_host, qi);
     const int grid = grid_for(B, OG_THREADS, 4);
     if (mode == OFDMGAN_GEN_Q_SPEC)
-        k_gen_fwd_q<OFDMGAN_GEN_Q_SPEC><<<grid, OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, (unsigned long long*)digest_dev);
+        k_gen_fwd_q<OFDMGAN_GEN_Q_SPEC><<<grid, OG_THREADS, 0, s>>>(x_dev, y_dev, B, (unsigned long long*)digest_dev, qi);
     else
-        k_gen_fwd_q<OFDMGAN_GEN_Q_RTL><<<grid, OG_THREADS, 0, s>>>(x_dev, y_dev, B, slot, (unsigned long long*)digest_dev);
+        k_gen_fwd_q<OFDMGAN_GEN_Q_RTL><<<grid, OG_THREADS, 0, s>>>(x_dev, y_dev, B, (unsigned long long*)digest_dev, qi);
     return (int)cudaGetLastError();
 }
 

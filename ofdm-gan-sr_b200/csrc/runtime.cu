@@ -1,6 +1,8 @@
 // libofdmgan runtime: device query, per-stream weight slots, library-owned scratch, error strings and the FFMA
 // issue-rate microbenchmark that the fp32 roofline uses as its denominator.
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -93,6 +95,33 @@ int scratch_for_slot(int slot, size_t bytes, int which, void** ptr) {
         g_scratch_bytes[d][slot][which] = bytes;
     }
     *ptr = g_scratch[d][slot][which];
+    return 0;
+}
+
+namespace {
+struct StreamScratch {
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t bytes[4] = {0, 0, 0, 0};
+};
+std::map<std::pair<int, cudaStream_t>, StreamScratch> g_stream_scratch;
+}  // namespace
+
+int scratch_for_stream(cudaStream_t s, size_t bytes, int which, void** ptr) {
+    int d = -1;
+    OG_CHECK(cudaGetDevice(&d));
+    if (which < 0 || which >= 4) return OFDMGAN_E_ARG;
+    std::lock_guard<std::mutex> lk(g_mu);
+    StreamScratch& e = g_stream_scratch[std::make_pair(d, s)];
+    if (e.bytes[which] < bytes) {                                 // growth only on the first calls of a stream; never inside capture
+        if (e.p[which]) OG_CHECK(cudaFree(e.p[which]));
+        e.p[which] = nullptr;
+        e.bytes[which] = 0;
+        void* p = nullptr;
+        OG_CHECK(cudaMalloc(&p, bytes));
+        e.p[which] = p;
+        e.bytes[which] = bytes;
+    }
+    *ptr = e.p[which];
     return 0;
 }
 

@@ -289,8 +289,14 @@ __device__ __forceinline__ LnScal ln_scalars(const ofdmgan_chan_cfg& c) {
 // SyntheticOFDMDataset's default); 2: the reference's non-linear chain (Rapp with p = 3, IQ imbalance, phase noise with sigma <=
 // 0.2, AWGN: --nonlinear).  The specialised instantiations are straight-line code: no branch joins, no register shuffling.
 enum { CHAIN_ANY = 0, CHAIN_LINEAR = 1, CHAIN_NONLINEAR = 2 };
-template <int GEN, bool INJ, bool OUT, int CHAIN>
-__global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constant__ SimArgs a) {
+// BYVAL: the generator's weight image arrives in the parameter block (host-resident inference weights) instead of the __constant__ one
+struct LeanArgs {
+    SimArgs a;
+    GImage g;
+};
+template <int GEN, bool INJ, bool OUT, int CHAIN, bool BYVAL>
+__global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constant__ LeanArgs la) {
+    const SimArgs& a = la.a;
     extern __shared__ float4 sm[];
     double* table = reinterpret_cast<double*>(sm + LN_W * 32 * 8);    // [n_snr][LN_TBL_NM][NC]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
         // ---- reconstruct and compare: tanh(v) - kappa z = (1 - kappa z) - 2 / (1 + 2^v')
         float se_a = 0.f, se_b = 0.f;
         float zc[2][4];
-        gen_fwd_f32_scaled(c_g, a.slope, s_n, nr, ni, [&](int p, f32x2 e, f32x2 o) {
+        gen_fwd_f32_scaled(BYVAL ? la.g.w : c_g, a.slope, s_n, nr, ni, [&](int p, f32x2 e, f32x2 o) {
             if ((p & 1) == 0) {
                 const int c = p >> 1;
                 const float4 vr = park[lane * 8 + (c ^ (lane & 7))], vi = park[lane * 8 + ((c + 4) ^ (lane & 7))];
@@ -549,43 +555,55 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
     }
 }
 
-template <int GEN, bool INJ, bool OUT, int CHAIN>
-static int sim_lean_launch_one(const SimCall& c) {
+template <int GEN, bool INJ, bool OUT, int CHAIN, bool BYVAL>
+static int sim_lean_launch_impl(const SimCall& c, LeanArgs& la) {
     cudaStream_t s = c.stream;
-    int rc;
-    CallGuard guard(s);
-    if ((rc = guard.rc)) return rc;
-    const int slot = 0;
-    if (GEN == OFDMGAN_GEN_F32 && (rc = upload_g(c.gparams258, slot, s))) return rc;
-    int err = 0;
+    int rc, err = 0;
     const DeviceInfo& di = device_info(&err);
     const int sms = err ? 148 : di.sms;
     const int64_t ng = (c.B + 31) / 32;
     int64_t want = (ng + LN_W - 1) / LN_W;
     if (want < 1) want = 1;
     const int grid = (int)(want < sms ? want : sms);                 // persistent: one CTA per SM
-    OG_CHECK(cudaFuncSetAttribute(k_sim_lean<GEN, INJ, OUT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LN_SMEM));
+    OG_CHECK(cudaFuncSetAttribute(k_sim_lean<GEN, INJ, OUT, CHAIN, BYVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LN_SMEM));
     const int n = c.n_snr * NM * NC;
     void* partials = nullptr;
-    if (GEN >= 0 && c.metrics && (rc = scratch_for_slot(slot, (size_t)grid * n * sizeof(double), 4, &partials))) return rc;
-    SimArgs a{};
+    // per-stream scratch for the per-CTA partial tables: by-value calls hold no lock, so streams must not share it
+    if (GEN >= 0 && c.metrics && (rc = scratch_for_stream(s, (size_t)grid * n * sizeof(double), 0, &partials))) return rc;
+    SimArgs& a = la.a;
+    a = SimArgs{};
     a.cfg = *c.cfg;
     a.keys = philox_keys(c.seed);
     a.frame0 = c.frame0;
     a.B = c.B;
     if (c.rand) { a.sym = c.rand->sym; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; }
     a.clean = c.clean; a.noisy = c.noisy; a.snr_out = c.snr;
-    a.wslot = slot;
+    a.wslot = 0;
     a.slope = c.slope;
     a.partials = (double*)partials;
     a.n_snr = c.n_snr;
-    k_sim_lean<GEN, INJ, OUT, CHAIN><<<grid, LN_THREADS, LN_SMEM, s>>>(a);
+    k_sim_lean<GEN, INJ, OUT, CHAIN, BYVAL><<<grid, LN_THREADS, LN_SMEM, s>>>(la);
     OG_CHECK(cudaGetLastError());
     if (partials) {
         reduce_partials_launch((const double*)partials, grid, n, c.metrics, s);
         OG_CHECK(cudaGetLastError());
     }
     return 0;
+}
+template <int GEN, bool INJ, bool OUT, int CHAIN>
+static int sim_lean_launch_one(const SimCall& c) {
+    static thread_local LeanArgs la;                                 // (5 KB: not on the stack of every caller)
+    if constexpr (GEN == OFDMGAN_GEN_F32 && !INJ) {
+        if (is_host_pointer(c.gparams258)) {
+            g_image_host(c.gparams258, la.g);                        // inference weights by value: no shared state, no lock
+            return sim_lean_launch_impl<GEN, INJ, OUT, CHAIN, true>(c, la);
+        }
+    }
+    int rc;
+    CallGuard guard(c.stream);                                       // device-resident weights: the __constant__ image
+    if ((rc = guard.rc)) return rc;
+    if (GEN == OFDMGAN_GEN_F32 && (rc = upload_g(c.gparams258, 0, c.stream))) return rc;
+    return sim_lean_launch_impl<GEN, INJ, OUT, CHAIN, false>(c, la);
 }
 
 // Is this call the headline shape?  Gaussian source, no injected time-domain frames / fading draws, no late stages, no
@@ -597,6 +615,7 @@ bool sim_lean_eligible(const SimCall& c) {
     if (c.cfg->impair & (OFDMGAN_IMPAIR_SALEH | OFDMGAN_IMPAIR_DC | OFDMGAN_IMPAIR_CFO)) return false;
     if ((c.cfg->impair & OFDMGAN_IMPAIR_PA) && !(c.cfg->pa_saturation > 0.f)) return false;
     if (c.rand && (c.rand->tx || c.rand->fade)) return false;
+    if (c.gen_kind == OFDMGAN_GEN_F32 && (c.clean || c.noisy || c.snr)) return false;   // (not reachable through the C ABI)
     return true;
 }
 // the stage set of a configuration (CHAIN_*)
@@ -607,8 +626,11 @@ static int chain_of(const ofdmgan_chan_cfg& c) {
     if ((c.impair & nl) == nl && c.pa_smoothness == 3.0f && c.pn_sigma <= 0.2f) return CHAIN_NONLINEAR;
     return CHAIN_ANY;
 }
-template <int GEN, bool OUT>
+// The C ABI writes frames only from the simulate-only call (ofdmgan_chan_sim) and metrics only from the fused call
+// (ofdmgan_sim_gen_metrics), so OUT == (GEN < 0).
+template <int GEN>
 static int sim_lean_launch_chain(const SimCall& c, bool inj) {
+    constexpr bool OUT = GEN < 0;
     if (inj) return sim_lean_launch_one<GEN, true, OUT, CHAIN_ANY>(c);     // parity runs: one instantiation with every branch
     switch (chain_of(*c.cfg)) {
         case CHAIN_LINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_LINEAR>(c);
@@ -618,9 +640,8 @@ static int sim_lean_launch_chain(const SimCall& c, bool inj) {
 }
 int sim_launch_lean(const SimCall& c) {
     const bool inj = c.rand && (c.rand->sym || c.rand->pn || c.rand->snr_db || c.rand->noise);
-    const bool out = c.clean || c.noisy || c.snr;
-    if (c.gen_kind == -1) return sim_lean_launch_chain<-1, true>(c, inj);
-    return out ? sim_lean_launch_chain<OFDMGAN_GEN_F32, true>(c, inj) : sim_lean_launch_chain<OFDMGAN_GEN_F32, false>(c, inj);
+    if (c.gen_kind == -1) return sim_lean_launch_chain<-1>(c, inj);
+    return sim_lean_launch_chain<OFDMGAN_GEN_F32>(c, inj);
 }
 
 }  // namespace og

@@ -56,7 +56,7 @@ static __constant__ __align__(16) float c_d[OG_D_IMG];
 static __constant__ __align__(16) float c_q[OG_Q_IMG];
 
 // value of entry i (< GI2_ENC) of the G image from the raw parameters
-__device__ __forceinline__ float g_img_base(const float* __restrict__ p, int i) {
+__host__ __device__ __forceinline__ float g_img_base(const float* __restrict__ p, int i) {
     if (i < 132) return p[i];                                              // enc1 + bottleneck, verbatim
     if (i < 132 + 128) {                                                   // dec1 folded
         const int j = i - 132, pair = j >> 2, t = j & 3;
@@ -73,11 +73,11 @@ __device__ __forceinline__ float g_img_base(const float* __restrict__ p, int i) 
     return 0.f;
 }
 
-static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
-    int i = threadIdx.x;
-    if (i < GI2_ENC) { img[i] = g_img_base(p, i); return; }
-    if (i >= OG_G_IMG) return;
-    if (i >= GI_OUT_BT) { img[i] = i < GI_OUT_BT + 2 ? p[GP_OUT_B + (i - GI_OUT_BT)] * G_TANH_SCALE : 0.f; return; }
+// entry i of the whole G image
+__host__ __device__ __forceinline__ float g_img_entry(const float* __restrict__ p, int i) {
+    if (i < GI2_ENC) return g_img_base(p, i);
+    if (i >= OG_G_IMG) return 0.f;
+    if (i >= GI_OUT_BT) return i < GI_OUT_BT + 2 ? p[GP_OUT_B + (i - GI_OUT_BT)] * G_TANH_SCALE : 0.f;
     const float post = i >= GI2_OUT_T ? G_TANH_SCALE : 1.0f;
     if (i >= GI2_OUT_T) i -= GI2_OUT_T - GI2_OUT;
     // pair-interleaved copies: entry ((o2*IC + ic)*K + k)*2 + h  <-  base[((2*o2+h)*IC + ic)*K + k]
@@ -87,7 +87,32 @@ static __global__ void prep_g_image(const float* __restrict__ p, float* __restri
     else if (i < GI2_OUT) { e = i - GI2_DEC; base = GI_DEC_F; IC = 8; K = 4; }
     else { e = i - GI2_OUT; base = GI_OUT_F; IC = 4; K = 4; }
     const int h = e & 1, r = e >> 1, k = r % K, ic = (r / K) % IC, o2 = r / (K * IC);
-    img[threadIdx.x] = g_img_base(p, base + ((2 * o2 + h) * IC + ic) * K + k) * post;
+    return g_img_base(p, base + ((2 * o2 + h) * IC + ic) * K + k) * post;
+}
+
+static __global__ void prep_g_image(const float* __restrict__ p, float* __restrict__ img) {
+    const int i = threadIdx.x;
+    if (i < OG_G_IMG) img[i] = g_img_entry(p, i);
+}
+
+// The same images BY VALUE, for weights that live in host memory (inference): the image is built on the host and travels in the
+// kernel's parameter block (constant bank 0), so the call needs no preparation kernel, no copy into a __constant__ symbol and
+// therefore no lock - calls on different streams are independent (include/ofdmgan.h, "Conventions").
+struct GImage {
+    float w[OG_G_IMG];
+};
+struct QImage {
+    float w[OG_Q_IMG];
+};
+static inline void g_image_host(const float* params258_host, GImage& img) {
+    for (int i = 0; i < OG_G_IMG; ++i) img.w[i] = g_img_entry(params258_host, i);
+}
+// is p a host pointer (anything cudaPointerGetAttributes does not call device / managed memory)
+static inline bool is_host_pointer(const void* p) {
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return !(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
 }
 
 // entry i of the D image from the raw parameters
@@ -156,8 +181,8 @@ static int upload_d(const float* params521, int slot, cudaStream_t s) {
 }
 
 // ROMs are host pointers (weight_rom.v layout): converted on the host, exact (int8/128 and int16 are fp32-exact)
-static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot, cudaStream_t s) {
-    float img[OG_Q_IMG];
+static inline void q_image_host(const int8_t* wrom_host, const int16_t* brom_host, QImage& qi) {
+    float* img = qi.w;
     for (int i = 0; i < OG_Q_IMG; ++i) img[i] = 0.f;
     for (int i = 0; i < 226; ++i) img[i] = (float)wrom_host[i] * (1.0f / 128.0f);
     for (int i = 0; i < 18; ++i) img[QI_BIAS + i] = (float)brom_host[i];
@@ -173,8 +198,12 @@ static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot,
     pairs(QI2_BN, 24, 8, 4, 3);
     pairs(QI2_DEC, 120, 4, 8, 3);
     pairs(QI2_OUT, 216, 2, 4, 1);
+}
+static int upload_q(const int8_t* wrom_host, const int16_t* brom_host, int slot, cudaStream_t s) {
+    QImage qi;
+    q_image_host(wrom_host, brom_host, qi);
     // pageable source: the runtime stages it before returning, so the stack buffer may die afterwards
-    OG_CHECK(cudaMemcpyToSymbolAsync(c_q, img, sizeof img, 0, cudaMemcpyHostToDevice, s));
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_q, qi.w, sizeof qi.w, 0, cudaMemcpyHostToDevice, s));
     return 0;
 }
 

@@ -310,3 +310,53 @@ def test_quantize_helpers_on_the_device_match_reference(ref_channel):
     fq = utils.FakeQuantize(8, per_channel=False).cuda().train()
     y = fq(t.clone().requires_grad_(True))
     assert torch.allclose(y.detach().cpu(), torch.as_tensor(r["qt_deq"]), atol=1e-7)
+
+
+def test_inference_calls_on_two_streams_are_independent(pkg):
+    """Host-resident weights travel by value: no constant-image refresh, no library lock, per-stream scratch.  A call on stream B
+    completes while stream A is still busy - with the weights in device memory (the training path) B would be ordered after A."""
+    ops = pkg.ops
+    rng = np.random.default_rng(0)
+    gp = (rng.standard_normal(258) * 0.3).astype(np.float32)
+    x = torch.randn(8192, 2, 16, device="cuda")
+    cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=64)
+    ref_y = ops.gen_fwd_f32(x, gp)
+    ref_m = ops.sim_gen_metrics(cfg, 7 * 64 * 9, gparams=gp, seed=3)
+    W = rng.integers(-128, 128, 2048).astype(np.int8)
+    Bq = np.zeros(64, np.int16)
+    xq = ops.quantize_q88(x)
+    ref_q = ops.gen_fwd_q(xq, W, Bq, mode=ops.GEN_Q_SPEC)
+    torch.cuda.synchronize()
+    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(sA):
+        torch.cuda._sleep(int(3e9))                               # ~1.5 s of spinning in front of stream A's calls
+        yA = ops.gen_fwd_f32(x, gp)
+        mA = ops.sim_gen_metrics(cfg, 7 * 64 * 9, gparams=gp, seed=3)
+    with torch.cuda.stream(sB):
+        yB = ops.gen_fwd_f32(x, gp)
+        mB = ops.sim_gen_metrics(cfg, 7 * 64 * 9, gparams=gp, seed=3)
+        qB = ops.gen_fwd_q(xq, W, Bq, mode=ops.GEN_Q_SPEC)
+    sB.synchronize()
+    assert not sA.query(), "stream B's calls waited for stream A"
+    assert torch.equal(yB, ref_y) and torch.equal(mB, ref_m) and torch.equal(qB, ref_q)
+    sA.synchronize()
+    assert torch.equal(yA, ref_y) and torch.equal(mA, ref_m)
+    # two host threads, each on its own stream, at the same time
+    import threading
+    out = {}
+
+    def work(i):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for _ in range(20):
+                y = ops.gen_fwd_f32(x, gp)
+                m = ops.sim_gen_metrics(cfg, 7 * 64 * 9, gparams=gp, seed=3)
+        st.synchronize()
+        out[i] = (y, m)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert all(torch.equal(out[i][0], ref_y) and torch.equal(out[i][1], ref_m) for i in range(4))
