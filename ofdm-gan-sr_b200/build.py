@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 VARIANT = os.environ.get("OG_VARIANT", "")
 OBJ = os.path.join(CSRC, "_obj" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "lib", "libofdmgan" + ("_" + VARIANT if VARIANT else "") + ".so")
-UNITS = ["runtime.cu", "infer.cu", "sim_gauss.cu", "sim_qpsk.cu", "sim_lean.cu", "critic_step.cu", "critic_api.cu", "gen_train.cu", "ofdm_api.cu", "critic_q.cu", "peer_comm.cu"]
+UNITS = ["runtime.cu", "infer.cu", "sim_gauss.cu", "sim_gauss_ext.cu", "sim_qpsk.cu", "sim_lean.cu", "critic_step.cu", "critic_api.cu", "gen_train.cu", "ofdm_api.cu", "critic_q.cu", "peer_comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + os.environ.get("OG_NVCC_FLAGS", "").split()
 

@@ -53,6 +53,7 @@ struct SimCall {
 };
 int sim_launch_gauss(const SimCall& c);    // sim_gauss.cu
 int sim_launch_qpsk(const SimCall& c);     // sim_qpsk.cu
+int sim_launch_gauss_ext(const SimCall& c); // sim_gauss_ext.cu: the less common (generator, equaliser, late-stage) combinations
 int sim_launch_lean(const SimCall& c);     // sim_lean.cu: the headline kernel
 bool sim_lean_eligible(const SimCall& c);
 

@@ -233,22 +233,54 @@ static int sim_launch_one(const SimCall& c) {
     return 0;
 }
 
+// Which (generator, equaliser rows, late stages) combinations a translation unit builds.  SIM_TU_BASE: the headline combinations for
+// its sources; SIM_TU_EXT (sim_gauss_ext.cu, Gaussian source only - the signal run_benchmark uses): fp32 generator with equaliser
+// rows AND late stages (run_benchmark(channel_type='rayleigh' | 'rician' | 'multipath'), benchmark_comparison.py:154), and the integer
+// generators with equaliser rows and / or late stages.
+inline bool sim_needs_late(const ofdmgan_chan_cfg& c) {
+    return c.channel_type != OFDMGAN_CHAN_AWGN || (c.impair & (OFDMGAN_IMPAIR_SALEH | OFDMGAN_IMPAIR_DC | OFDMGAN_IMPAIR_CFO)) != 0;
+}
+inline bool sim_is_ext_combo(const SimCall& c) {
+    const bool eq = c.cfg->equalizers != 0, late = sim_needs_late(*c.cfg);
+    if (c.gen_kind == OFDMGAN_GEN_F32) return eq && late;
+    if (c.gen_kind == OFDMGAN_GEN_Q_SPEC || c.gen_kind == OFDMGAN_GEN_Q_RTL) return eq || late;
+    return false;
+}
+
+#ifndef SIM_TU_EXT
 template <int SRC>
 static int sim_launch_src(const SimCall& c) {
     const bool eq = c.cfg->equalizers != 0;
     // the rarely used stages live in their own instantiations so the headline kernels do not carry them
-    const bool late = c.cfg->channel_type != OFDMGAN_CHAN_AWGN ||
-                      (c.cfg->impair & (OFDMGAN_IMPAIR_SALEH | OFDMGAN_IMPAIR_DC | OFDMGAN_IMPAIR_CFO)) != 0;
+    const bool late = sim_needs_late(*c.cfg);
+    if (sim_is_ext_combo(c)) return SRC == SRC_GAUSS ? sim_launch_gauss_ext(c) : OFDMGAN_E_UNSUPPORTED;
     switch (c.gen_kind) {
         case -1: return late ? sim_launch_one<SRC, -1, false, true>(c) : sim_launch_one<SRC, -1, false, false>(c);
         case OFDMGAN_GEN_F32:
-            if (late) return eq ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_F32, false, true>(c);
+            if (late) return sim_launch_one<SRC, OFDMGAN_GEN_F32, false, true>(c);
             return eq ? sim_launch_one<SRC, OFDMGAN_GEN_F32, true, false>(c) : sim_launch_one<SRC, OFDMGAN_GEN_F32, false, false>(c);
-        // the equaliser rows / late stages are built with the fp32 generator only
-        case OFDMGAN_GEN_Q_SPEC: return (eq || late) ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC, false, false>(c);
-        case OFDMGAN_GEN_Q_RTL: return (eq || late) ? OFDMGAN_E_UNSUPPORTED : sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL, false, false>(c);
+        case OFDMGAN_GEN_Q_SPEC: return sim_launch_one<SRC, OFDMGAN_GEN_Q_SPEC, false, false>(c);
+        case OFDMGAN_GEN_Q_RTL: return sim_launch_one<SRC, OFDMGAN_GEN_Q_RTL, false, false>(c);
         default: return OFDMGAN_E_ARG;
     }
 }
+#else
+template <int GEN>
+static int sim_launch_ext_gen(const SimCall& c, bool eq, bool late) {
+    if (eq && late) return sim_launch_one<SRC_GAUSS, GEN, true, true>(c);
+    if (GEN == OFDMGAN_GEN_F32) return OFDMGAN_E_ARG;                // (the other fp32 combinations are base ones)
+    return eq ? sim_launch_one<SRC_GAUSS, GEN == OFDMGAN_GEN_F32 ? OFDMGAN_GEN_Q_SPEC : GEN, true, false>(c)
+              : sim_launch_one<SRC_GAUSS, GEN == OFDMGAN_GEN_F32 ? OFDMGAN_GEN_Q_SPEC : GEN, false, true>(c);
+}
+static int sim_launch_ext(const SimCall& c) {
+    const bool eq = c.cfg->equalizers != 0, late = sim_needs_late(*c.cfg);
+    switch (c.gen_kind) {
+        case OFDMGAN_GEN_F32: return sim_launch_ext_gen<OFDMGAN_GEN_F32>(c, eq, late);
+        case OFDMGAN_GEN_Q_SPEC: return sim_launch_ext_gen<OFDMGAN_GEN_Q_SPEC>(c, eq, late);
+        case OFDMGAN_GEN_Q_RTL: return sim_launch_ext_gen<OFDMGAN_GEN_Q_RTL>(c, eq, late);
+        default: return OFDMGAN_E_ARG;
+    }
+}
+#endif
 
 }  // namespace og

@@ -59,13 +59,15 @@ def run_benchmark(generator, n_trials: int = 100, frame_length: int = 16, snr_va
     adaptive filters and stay with the reference); the trial loop (SNR outer, trial inner, separate
     normalisation of noisy and clean, per-trial MSE / EVM in dB, mean and population std over trials) runs in one
     fused launch per rank.  `generator` is a MiniGenerator (its flat parameters are used) or a flat 258-vector."""
-    if frame_length != 16 or channel_type != "awgn":
-        raise OfdmGanError("run_benchmark: only frame_length 16 / 'awgn' are built (benchmark_comparison.py:355-472 defaults)")
+    if frame_length != 16:
+        raise OfdmGanError("run_benchmark: only frame_length 16 is built (benchmark_comparison.py:355-472 default)")
+    if channel_type not in ops.CHANNEL_TYPES:
+        raise ValueError(f"Unknown channel type: {channel_type}")             # utils/ofdm_utils.py:673
     snr_values = [float(s) for s in snr_values]
     gparams = ops.flatten_params(generator) if isinstance(generator, torch.nn.Module) else generator
     slope = getattr(generator, "leaky_slope", 0.2)
     common = dict(nonlinear=nonlinear, pa_saturation=pa_saturation if nonlinear else 1.0, normalize=ops.NORM_SEPARATE,
-                  snr_mode=ops.SNR_GRID, frames_per_snr=n_trials, equalizers=True)
+                  snr_mode=ops.SNR_GRID, frames_per_snr=n_trials, equalizers=True, channel_type=channel_type)
     tables = []
     if _is_arithmetic(snr_values):
         step = snr_values[1] - snr_values[0] if len(snr_values) > 1 else 0.0

@@ -360,3 +360,59 @@ def test_inference_calls_on_two_streams_are_independent(pkg):
     for t in ts:
         t.join()
     assert all(torch.equal(out[i][0], ref_y) and torch.equal(out[i][1], ref_m) for i in range(4))
+
+
+@pytest.mark.parametrize("channel_type", ["rayleigh", "rician", "multipath"])
+def test_run_benchmark_fading_channels_match_the_unfused_pieces(pkg, channel_type):
+    """run_benchmark(channel_type=...) (benchmark_comparison.py:154): the fused sweep with equaliser rows AND a fading channel ==
+    the same frames through ofdmgan_chan_sim -> generator / ofdmgan_equalize -> metrics"""
+    from ofdm_gan_sr_b200.sweep import run_benchmark
+    ops = pkg.ops
+    G, D, TG, TD = _pair(pkg, 8)
+    n = 1500
+    res = run_benchmark(G, n_trials=n, nonlinear=True, pa_saturation=0.8, channel_type=channel_type, seed=6)
+    assert set(res) == {"GAN", "ZF", "MMSE", "NoEQ"}
+    cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=2, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=n,
+                       channel_type=channel_type)
+    clean, noisy, snr = ops.chan_sim(cfg, 7 * n, seed=6)
+
+    def evm_rows(est):
+        e = ((est - clean) ** 2).sum(dim=(1, 2)).double()
+        r = (clean ** 2).sum(dim=(1, 2)).double()
+        return (20 * torch.log10(torch.sqrt(e / r) + 1e-10)).view(7, n).mean(dim=1)
+
+    with torch.no_grad():
+        rows = {"GAN": evm_rows(TG(noisy)), "NoEQ": evm_rows(noisy), "MMSE": evm_rows(ops.equalize(noisy, clean, pkg._lib.METHOD_MMSE, snr_db=snr))}
+    for m, want in rows.items():
+        for i, s in enumerate(res[m]):
+            assert abs(res[m][s]["evm"] - float(want[i])) <= 5e-5 * max(1.0, abs(float(want[i]))), (m, s)
+    with pytest.raises(ValueError):
+        run_benchmark(G, n_trials=10, channel_type="no-such-channel")
+
+
+@pytest.mark.parametrize("gen_kind", [1, 2])
+def test_integer_generators_inside_the_benchmark_sweep(pkg, gen_kind, monkeypatch):
+    """integer generator x equaliser rows x fading channel in ONE fused launch: the generator row equals the separate integer
+    entry point on the same Q8.8 frames, the equaliser rows equal the fp32 generator's sweep (they do not depend on the generator)"""
+    import oracle
+    ops = pkg.ops
+    monkeypatch.setenv("OFDMGAN_SIM_IMPL", "general")              # the stand-alone simulator call on the same kernel as the fused one
+    rng = np.random.default_rng(gen_kind)
+    W = rng.integers(-128, 128, 2048).astype(np.int8)
+    Bq = np.zeros(64, np.int16)
+    Bq[:18] = rng.integers(-300, 300, 18)
+    gp = (rng.standard_normal(258) * 0.3).astype(np.float32)
+    for kw in (dict(equalizers=True), dict(channel_type="rayleigh"), dict(equalizers=True, channel_type="multipath")):
+        cfg = ops.make_cfg(nonlinear=True, pa_saturation=0.8, normalize=2, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=128, **kw)
+        B = 7 * 128 * 5
+        fused = ops.sim_gen_metrics(cfg, B, gen_kind=gen_kind, wrom=W, brom=Bq, seed=3).cpu().numpy()
+        f32 = ops.sim_gen_metrics(cfg, B, gen_kind=ops.GEN_F32, gparams=gp, seed=3).cpu().numpy()
+        assert np.array_equal(fused[:, :, 0], f32[:, :, 0])
+        np.testing.assert_allclose(fused[:, 1:, 1:], f32[:, 1:, 1:], rtol=1e-12, atol=0)     # NoEQ / ZF / MMSE rows: same frames
+        clean, noisy, _ = ops.chan_sim(cfg, B, seed=3)
+        yq = ops.gen_fwd_q(ops.quantize_q88(noisy), W, Bq, mode=gen_kind)
+        bins = torch.as_tensor((np.arange(B) // 128 % 7).astype(np.int32)).cuda()
+        m = ops.frame_metrics(ops.dequantize_q88(yq), clean, bins, method=0, n_snr=7).cpu().numpy()
+        assert np.array_equal(m[:, 0, 0], fused[:, 0, 0])
+        for c in (1, 3):
+            np.testing.assert_allclose(fused[:, 0, c], m[:, 0, c], rtol=1e-6)
