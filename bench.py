@@ -538,6 +538,39 @@ def main():
             f1.record()
             barrier()
             ms_nccl = max_over_ranks(f0.elapsed_time(f1)) / K
+        # Where the data-parallel step's extra time goes: (a) the same iteration on every rank WITHOUT any exchange (each rank alone on
+        # its shard: the compute), (b) the exchange alone in a tight loop (ranks in lockstep: pure store + poll latency over NVLink).
+        # (step - compute) / 6 exchanges - latency = what is left for waiting on the slowest rank (skew between the ranks' kernels).
+        exch = None
+        if world > 1 and trainer.comm is not None:
+            t3 = CWGANGPStep(gp_h, dp_h, device=dev, graph=True)
+            t3.distributed, t3.world, t3.rank = False, 1, rank     # no exchange; scaling of the loss does not change the work
+            for _ in range(3):
+                t3.step(clean, noisy)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(K):
+                t3.step(clean, noisy)
+            f1.record()
+            barrier()
+            ms_compute = max_over_ranks(f0.elapsed_time(f1)) / K
+            buf = torch.zeros(528, device=dev)
+            for _ in range(20):
+                trainer.comm.allreduce_adam(buf)
+            barrier()
+            n_ex = 400
+            f0.record()
+            for _ in range(n_ex):
+                trainer.comm.allreduce_adam(buf)
+            f1.record()
+            barrier()
+            us_exchange = max_over_ranks(f0.elapsed_time(f1)) / n_ex * 1e3
+            per_ex = (ms - ms_compute) * 1e3 / 6.0
+            exch = {"ms_per_step_compute_only": ms_compute, "exchanges_per_step": 6, "us_per_exchange_in_step": per_ex,
+                    "us_per_exchange_alone": us_exchange, "us_waiting_for_slowest_rank": per_ex - us_exchange,
+                    "note": "exchange alone = launch of one 1024-thread CTA + P2P stores + polling, ranks in lockstep; inside the step the "
+                            "exchange is the tail of the critic kernel (no extra launch), so the difference is rank skew"}
         tflops = Bt * FLOP_TRAIN / (ms * 1e-3) / 1e12
         # end to end: every step's batch comes from pinned host memory (H2D inside the timed region, double-buffered on a copy
         # stream so the transfer of batch i+1 overlaps the compute of batch i - what a prefetching loader does), and the step's
@@ -582,7 +615,7 @@ def main():
                          "e2e_samples_per_s": e2e_train, "e2e_steps": Ke, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"],
                          "exchange": "none (1 GPU)" if world == 1 else ("peer-memory all-reduce fused with Adam" if trainer.comm is not None else "nccl"),
-                         "ms_per_step_with_nccl_exchange": ms_nccl,
+                         "ms_per_step_with_nccl_exchange": ms_nccl, "exchange_breakdown": exch,
                          "launch": "one CUDA graph per iteration" if trainer.use_graph else "eager, 27 launches per iteration",
                          "ms_per_step_eager": ms_eager, "reference_default_batch": small}
         launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
@@ -621,7 +654,7 @@ def main():
         summary = {"frames_per_s": value, "ms_per_step": ms_step, "roofline_frac": achieved / ffma, "e2e_frames_per_s": e2e_value,
                    "sustained_frames_per_s": sustained and sustained["value"], "train_ms_per_step": tr.get("ms_per_step"),
                    "train_samples_per_s": tr.get("samples_per_s"), "train_frac_of_ffma_peak": tr.get("fp32_frac_of_ffma_peak"),
-                   "train_ms_per_step_nccl": tr.get("ms_per_step_with_nccl_exchange"),
+                   "train_ms_per_step_nccl": tr.get("ms_per_step_with_nccl_exchange"), "train_exchange_breakdown": tr.get("exchange_breakdown"),
                    "multi_gpu_parity": parity["status"] if parity else ("n/a (1 GPU)" if world == 1 else None), "n_gpus": world}
         line = {"metric": "OFDM frames/s: fused channel sim + G inference", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
