@@ -295,33 +295,41 @@ def main():
     # ---- primary: fused sim + G + metrics, device-resident weights and accumulator
     table = torch.zeros(7, pkg._lib.N_METHODS, pkg._lib.METRIC_COLS, dtype=torch.float64, device=dev)
 
+    # A sweep is frame-sharded with ONE exchange at its end (BASELINE.json north_star: "SNR sweeps shard frames with only a final
+    # BER/EVM reduce"): every step adds its 2^24 frames per rank into the rank's device-resident table, and the < 2 KB table is
+    # all-reduced once after the last step - inside the timed region.
     def fused_step(s):
-        table.zero_()
         ops.sim_gen_metrics(cfg, F, gparams=gp_d, seed=1, frame0=(s * world + rank) * F, out=table)
+
+    def final_reduce():
         if world > 1:
-            dist.all_reduce(table)                               # the sweep's only exchange: < 2 KB
+            dist.all_reduce(table)                               # the sweep's only exchange
 
     for s in range(W):
         fused_step(s)
+    final_reduce()
     barrier()
     uuid = str(getattr(torch.cuda.get_device_properties(dev), "uuid", "")) or str(local_rank)
     clocks = ClockSampler(uuid if uuid.startswith("GPU-") or uuid.isdigit() else "GPU-" + uuid)
     if rank == 0:
         clocks.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 2)]
+    table.zero_()
     barrier()
     ev[0].record()
     for s in range(K):
         fused_step(W + s)
         ev[s + 1].record()
+    final_reduce()
+    ev[K + 1].record()
     barrier()
-    ms_total = max_over_ranks(ev[0].elapsed_time(ev[K]))
+    ms_total = max_over_ranks(ev[0].elapsed_time(ev[K + 1]))
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / K
     value = F * world / (ms_step * 1e-3)
     per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
     n_frames_seen = float(table[:, :2, 0].sum().item())
-    assert n_frames_seen == 2.0 * F * world, "metric table does not account for every frame"
+    assert n_frames_seen == 2.0 * F * world * K, "metric table does not account for every frame"
 
     # ---- sustained: the same step back to back for >= 2 s, clocks and power sampled over the whole stretch (the K-step headline above
     # lasts tens of milliseconds; this shows what the rate does once the part has warmed up under load)
@@ -336,6 +344,7 @@ def main():
         s0.record()
         for s_ in range(n_sus):
             fused_step(W + K + s_)
+        final_reduce()
         s1.record()
         barrier()
         sus_ms = max_over_ranks(s0.elapsed_time(s1))
@@ -401,7 +410,7 @@ def main():
                 "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "sustained": sustained}
 
     also = {}
-    launches = K * 3                                             # prep_g_image + k_sim + k_reduce_partials per step
+    launches = K * 3                                             # prep_g_image + k_sim_lean + k_reduce_partials per step
     if not args.skip_also:
         # ---- config 2: integer generator over 2^24 HBM-resident frames (1 GPU worth per rank)
         g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -543,8 +552,7 @@ def main():
         # (step - compute) / 6 exchanges - latency = what is left for waiting on the slowest rank (skew between the ranks' kernels).
         exch = None
         if world > 1 and trainer.comm is not None:
-            t3 = CWGANGPStep(gp_h, dp_h, device=dev, graph=True)
-            t3.distributed, t3.world, t3.rank = False, 1, rank     # no exchange; scaling of the loss does not change the work
+            t3 = CWGANGPStep(gp_h, dp_h, device=dev, graph=True, data_parallel=False)   # no exchange: every rank alone on its shard
             for _ in range(3):
                 t3.step(clean, noisy)
             barrier()

@@ -21,7 +21,8 @@ class CWGANGPStep:
     """
 
     def __init__(self, gparams, dparams, lr_g=2e-4, lr_d=2e-4, betas=(0.0, 0.9), eps=1e-8, n_critic=5, gp_weight=10.0,
-                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops, exchange="auto", graph=False):
+                 rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops, exchange="auto", graph=False,
+                 data_parallel=True):
         """`backend` is the kernel namespace (default: libofdmgan through `ops`).  It exists so the host-side logic
         of this class (sharding, all-reduce, optimiser bookkeeping) can be exercised by the CPU test-suite with a
         stand-in; the product never passes anything but `ops`."""
@@ -40,7 +41,8 @@ class CWGANGPStep:
         self.n_critic, self.gp_weight, self.rec_weight, self.adv_weight = n_critic, gp_weight, rec_weight, adv_weight
         self.slope, self.seed = leaky_slope, seed
         self.group = process_group
-        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        # data_parallel=False: a single replica even inside an initialised process group (no exchange; bench.py's compute-only leg)
+        self.distributed = bool(data_parallel) and dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         self.rank = dist.get_rank(process_group) if self.distributed else 0
         self.world = dist.get_world_size(process_group) if self.distributed else 1
         self.d_steps = self.g_steps = 0

@@ -196,8 +196,10 @@ def test_fused_equaliser_rows_vs_oracle_and_pieces(api):
     # run_benchmark now reports the four data-parallel methods
     res = pkg.sweep.run_benchmark(gp, n_trials=1000, nonlinear=True, pa_saturation=0.8, seed=2)
     assert list(res) == ["GAN", "ZF", "MMSE", "NoEQ"] and res["ZF"][10.0]["evm"] < -130 < res["MMSE"][10.0]["evm"] < res["NoEQ"][10.0]["evm"]
+    # integer generator x equaliser rows: built for the Gaussian source (tests/test_gpu_api.py), not for the QPSK sources
+    ops.sim_gen_metrics(ops.make_cfg(**kw), 64, gen_kind=1, wrom=np.zeros(2048, np.int8), brom=np.zeros(64, np.int16))
     with pytest.raises(pkg.OfdmGanError):
-        ops.sim_gen_metrics(ops.make_cfg(**kw), 64, gen_kind=1, wrom=np.zeros(2048, np.int8), brom=np.zeros(64, np.int16))
+        ops.sim_gen_metrics(ops.make_cfg(symbol_source=ops.SYM_QPSK, **kw), 64, gen_kind=1, wrom=np.zeros(2048, np.int8), brom=np.zeros(64, np.int16))
 
 
 # ------------------------------------------------------------------------------------------------ remaining models
