@@ -67,12 +67,18 @@ inline PhiloxKeys philox_keys(uint64_t seed) {
 }
 
 #ifdef __CUDACC__
+// one IMAD.WIDE.U32 for both halves of a 32 x 32 -> 64 product (separate mul.hi / mul.lo are not always re-fused by ptxas, and a
+// wide multiply holds the heavy FMA pipe for 4 cycles: it is the most expensive instruction of the simulator kernels)
+__device__ __forceinline__ void mulwide(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%1, %0}, t;\n\t}" : "=r"(hi), "=r"(lo) : "r"(x), "r"(m));
+}
 __device__ __forceinline__ void philox4x32_10(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t (&out)[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t hi0, lo0, hi1, lo1;
+        mulwide(0xD2511F53u, c0, hi0, lo0);
+        mulwide(0xCD9E8D57u, c2, hi1, lo1);
         uint32_t n0 = hi1 ^ c1 ^ k.k0[r];
         uint32_t n2 = hi0 ^ c3 ^ k.k1[r];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;

@@ -40,10 +40,6 @@ constexpr size_t LN_SMEM = (size_t)LN_W * 32 * 8 * sizeof(float4) + (size_t)OFDM
 // ---- Philox4x32-10 with the frame-invariant parts of rounds 1 and 2 hoisted ------------------------------------------
 // counter = (frame lo, frame hi, block, 0): round 1 multiplies frame lo (the same for all blocks of a frame) and the block
 // index; round 2's second multiply sees only frame-level values.  Per block: 2 + 8 x 2 wide multiplies instead of 20.
-// one IMAD.WIDE.U32 for both halves of a 32 x 32 -> 64 product (separate mul.hi / mul.lo are not always re-fused by ptxas)
-__device__ __forceinline__ void mulwide(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
-    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%1, %0}, t;\n\t}" : "=r"(hi), "=r"(lo) : "r"(x), "r"(m));
-}
 struct PhiloxFrame {
     uint32_t a;          // frame hi ^ k0[0]
     uint32_t lo1p;       // low word of M1 * n2
