@@ -469,6 +469,25 @@ def main():
                                       "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak,
                                       "fp32_tflops": Q_FRAMES * FLOP_GEN / (ms * 1e-3) / 1e12}
         del xf, yf
+        # ---- the dataset path: SyntheticOFDMDataset batches written to HBM (clean + noisy + snr = 260 B per frame), AWGN with SNR ~ U(0, 30)
+        # (config.yaml:20) and the --nonlinear chain; 2^22 frames per launch (1.1 GB of writes >> 126 MB L2)
+        DS_FRAMES = 1 << 22
+        for tag, dkw in (("awgn", dict()), ("nonlinear", dict(nonlinear=True, pa_saturation=0.8))):
+            dcfg = ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0, **dkw)
+            for _ in range(3):
+                dc, dn, dsn = ops.chan_sim(dcfg, DS_FRAMES, seed=3, frame0=rank * DS_FRAMES, device=dev)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s_ in range(K):
+                dc, dn, dsn = ops.chan_sim(dcfg, DS_FRAMES, seed=3, frame0=(s_ * world + rank) * DS_FRAMES, device=dev)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / K
+            also["dataset_" + tag] = {"frames_per_s": DS_FRAMES * world / (ms * 1e-3), "ms_per_launch": ms, "frames": DS_FRAMES,
+                                      "hbm_write_gbs": DS_FRAMES * 260 / (ms * 1e-3) / 1e9,
+                                      "what": "ofdmgan_chan_sim = SyntheticOFDMDataset.__getitem__ x frames (utils/dataset.py:236-293), k_sim_lean<-1>"}
+            del dc, dn, dsn
         # ---- QPSK variant of the primary workload (QAMModulator + OFDMModulator source, N = 16, no pilots / CP): adds hard-decision BER
         qcfg = ops.make_cfg(symbol_source=ops.SYM_QPSK, n_fft=16, cp_len=0, pilot_spacing=0, **WORKLOAD)
         qtab = None
@@ -626,7 +645,7 @@ def main():
                          "ms_per_step_with_nccl_exchange": ms_nccl, "exchange_breakdown": exch,
                          "launch": "one CUDA graph per iteration" if trainer.use_graph else "eager, 27 launches per iteration",
                          "ms_per_step_eager": ms_eager, "reference_default_batch": small}
-        launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step()
+        launches += 4 * K * 1 + K * 2 + K * 3 + K * trainer.launches_per_step() + 2 * K
         if rank == 0:
             also["torch_eager"] = torch_eager_bar(gp_d, torch.as_tensor(dp_h, device=dev), clean, noisy, K)
         barrier()
