@@ -54,7 +54,7 @@ class CWGANGPStep:
         # on the device.  With several ranks it needs the peer-memory exchange (a captured graph cannot hold the NCCL fallback here).
         self.use_graph = bool(graph) and backend is ops
         self._ctr = torch.zeros(2, dtype=torch.int32, device=self.device) if self.use_graph else None   # [critic steps, generator steps]
-        self._static, self._calls_with_shape = None, 0
+        self._graphs, self._seen, self._static, self._warm_shape = {}, [], None, None
         # gradient exchange: "peer" = all-reduce fused with Adam over NVLink peer memory (one launch, ops.PeerComm),
         # "nccl" = dist.all_reduce then the Adam kernel, "auto" = peer when the ranks can map each other's memory
         if exchange not in ("auto", "peer", "nccl"):
@@ -77,12 +77,12 @@ class CWGANGPStep:
 
     # Host scalars are baked into a captured CUDA graph: assigning any of them (e.g. the StepLR halving of train.py:497-514 writing
     # lr_g / lr_d) drops the captured graph, and the next step() captures a new one with the current values.
+    _MAX_GRAPHS = 5                                              # the static pair's graph + four caller-buffer graphs
     _GRAPH_SCALARS = ("lr_g", "lr_d", "betas", "eps", "n_critic", "gp_weight", "rec_weight", "adv_weight", "slope", "seed")
 
     def __setattr__(self, name, value):
         if name in CWGANGPStep._GRAPH_SCALARS and getattr(self, "_graph", None) is not None and getattr(self, name, None) != value:
-            object.__setattr__(self, "_graph", None)
-            object.__setattr__(self, "_calls_with_shape", 1)      # the library's scratch is sized already: capture on the next call
+            object.__setattr__(self, "_graph", None)             # every captured graph is stale; scratch stays sized
         object.__setattr__(self, name, value)
 
     # ---- checkpointing: everything train.py:411-445 saves for the two optimisers, in torch.optim.Adam's own layout
@@ -208,24 +208,44 @@ class CWGANGPStep:
         update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self._ctr[1:2])
 
     def _step_graph(self, clean, noisy):
+        """Replay the iteration as a CUDA graph.  Buffers that come back (a loop stepping on the same tensors, a double-buffered
+        loader alternating between a few) get a graph captured ON THEM, keyed by (address of clean, address of noisy, shape): no
+        copy at all.  An address seen for the first time goes through one pair of static buffers (two device-to-device copies,
+        then the static graph), so a loader that hands out fresh memory every step never pays for a capture per step."""
+        if not (clean.is_contiguous() and noisy.is_contiguous()):
+            clean, noisy = clean.contiguous(), noisy.contiguous()
         shape = tuple(clean.shape)
-        if self._static is None or tuple(self._static[0].shape) != shape:
+        key = (clean.data_ptr(), noisy.data_ptr(), shape)
+        if self._graph is None:                                   # (also after a hyper-parameter change: every captured graph is stale)
+            self._graphs, self._seen = {}, []
+            self._graph = self._graphs
+        if self._warm_shape != shape:
+            self._iteration_ctr(clean, noisy)                    # first call with this shape: eager (also sizes the library's scratch)
+            self._warm_shape = shape
             self._static = (torch.empty_like(clean), torch.empty_like(noisy))
-            self._graph, self._calls_with_shape = None, 0
-        self._static[0].copy_(clean)
-        self._static[1].copy_(noisy)
-        self._calls_with_shape += 1
-        if self._calls_with_shape == 1:
-            self._iteration_ctr(*self._static)                   # first call with this shape: eager (also sizes the library's scratch)
+            self._graphs.clear()
         else:
-            if self._graph is None:                               # second call: capture (capturing does not execute), then replay
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._iteration_ctr(*self._static)
-                self._graph = g
-            self._graph.replay()
+            g = self._graphs.get(key)
+            if g is None and key in self._seen and len(self._graphs) < self._MAX_GRAPHS:
+                g = self._capture(clean, noisy)
+                self._graphs[key] = g
+            if g is None:                                         # first sighting of these addresses: the static pair
+                self._seen = (self._seen + [key])[-8:]
+                skey = ("static", shape)
+                self._static[0].copy_(clean)
+                self._static[1].copy_(noisy)
+                g = self._graphs.get(skey)
+                if g is None:
+                    g = self._graphs[skey] = self._capture(*self._static)
+            g.replay()
         self.d_steps += self.n_critic
         self.g_steps += 1
+
+    def _capture(self, clean, noisy):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):                                 # capturing does not execute
+            self._iteration_ctr(clean, noisy)
+        return g
 
     def step(self, clean, noisy, alphas=None):
         """One trainer iteration on this rank's shard of the batch (train.py:327-344).

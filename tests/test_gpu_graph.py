@@ -28,7 +28,7 @@ def test_graph_replay_equals_eager(setup):
     for clean, noisy in data:
         eager.step(clean, noisy)
         graph.step(clean, noisy)
-    assert graph._graph is not None and graph.d_steps == eager.d_steps == 30 and graph.g_steps == 6
+    assert 1 <= len(graph._graphs) <= 5 and graph.d_steps == eager.d_steps == 30 and graph.g_steps == 6
     assert graph._ctr.tolist() == [30, 6]                      # the device counters advanced with every replay
     for a, b in ((graph.g, eager.g), (graph.d, eager.d), (graph.g_m, eager.g_m), (graph.d_v, eager.d_v)):
         # same alphas, same kernels; Adam's bias correction comes from beta^t by squaring on the device vs pow() on the host
@@ -125,3 +125,25 @@ def test_graph_is_recaptured_when_a_hyper_parameter_changes():
     for i in range(6):
         t.step(clean, noisy)
     assert float((t.d - runs[0][1]).abs().max()) > 1e-5 * float(t.d.abs().max())
+
+
+def test_graphs_are_keyed_by_the_callers_buffers():
+    """a double-buffered loader alternates between two buffer pairs: two graphs, no copies, same result as eager launches"""
+    import ofdm_gan_sr_b200 as pkg
+    from ofdm_gan_sr_b200.train_step import CWGANGPStep
+    ops = pkg.ops
+    rng = np.random.default_rng(4)
+    gp, dp = (rng.standard_normal(258) * 0.3).astype(np.float32), (rng.standard_normal(521) * 0.2).astype(np.float32)
+    bufs = [ops.chan_sim(ops.make_cfg(), 256, seed=s)[:2] for s in (1, 2, 3)]
+    g, e = CWGANGPStep(gp, dp, graph=True, seed=2), CWGANGPStep(gp, dp, graph=False, seed=2)
+    order = [0, 1, 0, 1, 2, 0, 1, 2, 2, 0]
+    for i in order:
+        g.step(*bufs[i])
+        e.step(*bufs[i])
+    assert len(g._graphs) == 4                                  # the static pair (first sightings) + one per recurring buffer pair
+    for a, b in ((g.g, e.g), (g.d, e.d)):
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+    # new contents in an old buffer are what the replay reads
+    bufs[0][0].copy_(bufs[2][0]); bufs[0][1].copy_(bufs[2][1])
+    g.step(*bufs[0]); e.step(*bufs[2])
+    assert float((g.d - e.d).abs().max()) <= 1e-6 * float(e.d.abs().max())
