@@ -27,7 +27,7 @@ class _CriticFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, candidate, condition, slope, *params):
-        flat = torch.cat([p.reshape(-1) for p in params]).to(torch.float32)
+        flat = ops.flat_cached(params)
         cand, cond = ops.frames(candidate), ops.frames(condition)
         score = ops.disc_fwd_f32(cand, cond, flat, slope)
         ctx.save_for_backward(cand, cond, flat)
@@ -53,7 +53,7 @@ class _GradientPenaltyFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, real, fake, cond, alpha, slope, *params):
-        flat = torch.cat([p.reshape(-1) for p in params]).to(torch.float32)
+        flat = ops.flat_cached(params)
         need = any(p.requires_grad for p in params)
         gp, grads = ops.gradient_penalty(ops.frames(real), ops.frames(fake), ops.frames(cond), flat, alpha=alpha, slope=slope,
                                          need_dparams=need)

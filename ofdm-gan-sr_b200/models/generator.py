@@ -20,7 +20,7 @@ class _GeneratorFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, slope, *params):
-        flat = torch.cat([p.reshape(-1) for p in params]).to(torch.float32)
+        flat = ops.flat_cached(params)
         xc = ops.frames(x)
         y = ops.gen_fwd_f32(xc, flat, slope)
         ctx.save_for_backward(xc, flat)

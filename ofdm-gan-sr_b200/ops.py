@@ -92,6 +92,24 @@ def flatten_params(module):
     return torch.cat([p.detach().reshape(-1) for p in module.parameters()]).to(torch.float32).contiguous()
 
 
+_FLAT_CACHE = {}
+
+
+def flat_cached(params):
+    """The flat fp32 vector of a parameter list, rebuilt only when a parameter changed (torch bumps a tensor's `_version` on every
+    in-place write, e.g. optimizer.step()): the module path of the fused forward / backward then launches no `cat` kernel per call."""
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ident = tuple(k[0] for k in key)
+    hit = _FLAT_CACHE.get(ident)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    flat = torch.cat([p.detach().reshape(-1) for p in params]).to(torch.float32).contiguous()
+    if len(_FLAT_CACHE) > 16:
+        _FLAT_CACHE.clear()
+    _FLAT_CACHE[ident] = (key, flat)
+    return flat
+
+
 # ---------------------------------------------------------------------------------------------- generator
 def gen_fwd_f32(x, gparams, slope=0.2):
     x = frames(x)

@@ -416,3 +416,21 @@ def test_integer_generators_inside_the_benchmark_sweep(pkg, gen_kind, monkeypatc
         assert np.array_equal(m[:, 0, 0], fused[:, 0, 0])
         for c in (1, 3):
             np.testing.assert_allclose(fused[:, 0, c], m[:, 0, c], rtol=1e-6)
+
+
+def test_module_path_reflattens_only_when_parameters_change(pkg):
+    """the flat parameter vector of the fused modules is cached on the parameters' version counters: an optimiser step (in-place
+    write) invalidates it, repeated forwards reuse it"""
+    G, D, TG, TD = _pair(pkg, 11)
+    x = torch.randn(64, 2, 16, device="cuda")
+    y0 = G(x)
+    f0 = pkg.ops.flat_cached(list(G.parameters()))
+    assert pkg.ops.flat_cached(list(G.parameters())) is f0                   # unchanged parameters: the same tensor, no new cat
+    opt = torch.optim.SGD(G.parameters(), lr=0.1)
+    G(x).sum().backward()
+    opt.step()
+    f1 = pkg.ops.flat_cached(list(G.parameters()))
+    assert f1 is not f0 and not torch.equal(f1, f0)
+    with torch.no_grad():
+        TG.load_state_dict(G.state_dict())
+        assert float((G(x) - TG(x)).abs().max()) < 1e-5 and float((G(x) - y0).abs().max()) > 1e-6
