@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 12
+#define OFDMGAN_ABI_VERSION 13
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -120,6 +120,10 @@ typedef struct ofdmgan_chan_rand {
                                   (NonLinearImpairments.apply_* / ChannelModel.apply on caller-supplied signals) */
     const float*    fade;      /* [B][8]   fading draws in the reference's order: rayleigh {randn, randn}; rician {uniform(0, 2 pi),
                                   randn, randn}; multipath {randn, randn} per tap */
+    const float*    tx_gain;   /* [B]      with tx: the channel sees tx * tx_gain[b] while the clean output stays tx, and the joint
+                                  normalisation divides both by max(max|noisy|, max|tx|) - OFDMDataset.__getitem__,
+                                  utils/dataset.py:131-147 (clean_iq * normalization_factor through the channel, then
+                                  max(|noisy_iq|, |clean_iq|)) */
 } ofdmgan_chan_rand;
 
 /* per-SNR-bin, per-method accumulator row produced by ofdmgan_sim_gen_metrics (doubles):

@@ -44,7 +44,7 @@ class ChanCfg(ctypes.Structure):
 
 class ChanRand(ctypes.Structure):
     """`ofdmgan_chan_rand`: device pointers to host-generated draws (any may be NULL)."""
-    _fields_ = [("sym", c_p), ("bits", c_p), ("pn", c_p), ("snr_db", c_p), ("noise", c_p), ("tx", c_p), ("fade", c_p)]
+    _fields_ = [("sym", c_p), ("bits", c_p), ("pn", c_p), ("snr_db", c_p), ("noise", c_p), ("tx", c_p), ("fade", c_p), ("tx_gain", c_p)]
 
 
 _SIGNATURES = {
@@ -113,7 +113,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 12:
+        if L.ofdmgan_abi_version() != 13:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

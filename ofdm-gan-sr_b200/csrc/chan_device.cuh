@@ -23,6 +23,7 @@ struct SimArgs {
     const float* noise;
     const float* tx;         // injected time-domain frames (device, nullable)
     const float* fade;       // injected fading draws [B][8] (device, nullable)
+    const float* tx_gain;    // [B] with tx: the channel sees tx * tx_gain[b], the clean output stays tx (device, nullable)
     float* clean;            // outputs (device, nullable)
     float* noisy;
     float* snr_out;
@@ -291,8 +292,9 @@ __device__ __forceinline__ void impair_channel(const SimArgs& a, int64_t b, uint
                                                const float (&cr)[16], const float (&ci)[16], float (&nr)[16],
                                                float (&ni)[16]) {
     const ofdmgan_chan_cfg& c = a.cfg;
+    const float g_in = a.tx && a.tx_gain ? a.tx_gain[b] : 1.0f;   // OFDMDataset: the cached clean frame back at signal scale
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { nr[i] = cr[i]; ni[i] = ci[i]; }
+    for (int i = 0; i < 16; ++i) { nr[i] = cr[i] * g_in; ni[i] = ci[i] * g_in; }
     if (c.impair & OFDMGAN_IMPAIR_PA) {
         const float invA2 = 1.0f / (c.pa_saturation * c.pa_saturation);
         const float p = c.pa_smoothness, ninv2p = -0.5f / p;

@@ -218,7 +218,7 @@ static int sim_launch_one(const SimCall& c) {
     a.keys = philox_keys(c.seed);
     a.frame0 = c.frame0;
     a.B = c.B;
-    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; a.tx = c.rand->tx; a.fade = c.rand->fade; }
+    if (c.rand) { a.sym = c.rand->sym; a.bits = c.rand->bits; a.pn = c.rand->pn; a.snr_db = c.rand->snr_db; a.noise = c.rand->noise; a.tx = c.rand->tx; a.fade = c.rand->fade; a.tx_gain = c.rand->tx_gain; }
     a.clean = c.clean; a.noisy = c.noisy; a.snr_out = c.snr;
     a.wslot = slot;
     a.slope = c.slope;

@@ -205,7 +205,7 @@ def _dev(device):
 
 
 def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None, snr_db=None, noise=None, tx=None, fade=None,
-             want_clean=True, want_noisy=True, want_snr=True):
+             tx_gain=None, want_clean=True, want_noisy=True, want_snr=True):
     """frames frame0..frame0+B-1 of SyntheticOFDMDataset / run_benchmark -> (clean, noisy, snr) CUDA tensors.
     Any of the draw tensors may be injected (host-generated randomness in the reference's draw order)."""
     device = _dev(device)
@@ -215,6 +215,8 @@ def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None
         snr = torch.empty(B, dtype=torch.float32, device=device) if want_snr else None
         rand = None
         keep = []
+        if tx_gain is not None and tx is None:
+            raise OfdmGanError("tx_gain scales an injected time-domain frame: pass tx as well")
         if any(a is not None for a in (sym, bits, pn, snr_db, noise, tx, fade)):
             def f32(a, shape):
                 if a is None:
@@ -229,6 +231,7 @@ def chan_sim(cfg, B, seed=0, frame0=0, device=None, sym=None, bits=None, pn=None
             rand.noise = f32(noise, (B, 32))
             rand.tx = f32(tx, (B, 32))
             rand.fade = f32(fade, (B, 8))
+            rand.tx_gain = f32(tx_gain, (B,))
             if bits is not None:
                 tb = torch.as_tensor(np.ascontiguousarray(bits, dtype=np.uint32).view(np.int32)).to(device).contiguous()
                 keep.append(tb)

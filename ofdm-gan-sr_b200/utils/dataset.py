@@ -80,6 +80,8 @@ class OFDMDataset(torch.utils.data.Dataset):
         self.image_files = self._find_images()
         self.cfg = ops.make_cfg(pa=False, iq=False, pn=False, snr_mode=ops.SNR_UNIFORM, snr_lo=float(snr_range[0]),
                                 snr_hi=float(snr_range[1]), normalize=ops.NORM_NONE, channel_type=self.channel_type)
+        self._cfg_joint = ops.make_cfg(pa=False, iq=False, pn=False, snr_mode=ops.SNR_UNIFORM, snr_lo=float(snr_range[0]),
+                                       snr_hi=float(snr_range[1]), normalize=ops.NORM_JOINT, channel_type=self.channel_type)
         self._clean, self._factor = None, None
 
     def _find_images(self):
@@ -116,12 +118,11 @@ class OFDMDataset(torch.utils.data.Dataset):
         clean_all, factor_all = self.clean_frames()
         idx = torch.arange(start, start + B, device=clean_all.device) // self.samples_per_image
         clean_n, factor = clean_all[idx], factor_all[idx]
-        tx = (clean_n * factor[:, None, None]).reshape(B, 32).contiguous()               # back to signal scale, Re[16] | Im[16]
-        _, noisy, snr = ops.chan_sim(self.cfg, B, seed=self.seed, frame0=self.epoch * len(self) + start, device=clean_all.device,
-                                     tx=tx, want_clean=False)
-        m = torch.maximum(noisy.abs().amax(dim=(1, 2)), clean_n.abs().amax(dim=(1, 2)))
-        m = torch.where(m > 0, m, torch.ones_like(m))[:, None, None]
-        noisy, clean = noisy / m, clean_n / m
+        # one launch: the cached frame goes through the channel at signal scale (tx * tx_gain), the clean output stays the cached
+        # frame, and both are divided by max(max|noisy|, max|clean|) inside the kernel (dataset.py:131-147)
+        cfg = self._cfg_joint
+        clean, noisy, snr = ops.chan_sim(cfg, B, seed=self.seed, frame0=self.epoch * len(self) + start, device=clean_all.device,
+                                         tx=clean_n.reshape(B, 32).contiguous(), tx_gain=factor.contiguous())
         if self.transform:
             noisy, clean = self.transform(noisy, clean)
         return {"noisy": noisy, "clean": clean, "snr": snr}

@@ -1,3 +1,8 @@
+// EXPERIMENT RECORD - not part of the build (it refers to helper names of the day it was written and is kept for its structure,
+// not to be compiled).  A warp-specialised producer / consumer form of the fused simulator: RNG producer warpgroups (setmaxnreg.dec)
+// feed consumer warpgroups (setmaxnreg.inc) through mbarrier-guarded shared-memory sections.  Measured slower than the single-role
+// kernel that ships (csrc/sim_lean.cu): numbers and analysis in profiles/r2_notes.md ("Negative results").
+//
 // Warp-specialised fused simulator: the headline path (Gaussian-symbol OFDM frames -> non-linear chain -> AWGN ->
 // normalisation [-> fp32 MiniGenerator -> per-SNR MSE / EVM rows]) as a producer / consumer kernel.
 //   utils/dataset.py:236-293 (SyntheticOFDMDataset.__getitem__), utils/ofdm_utils.py:394-421 (Rapp), :458-488 (IQ),
