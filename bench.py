@@ -595,9 +595,11 @@ def main():
             us_exchange = max_over_ranks(f0.elapsed_time(f1)) / n_ex * 1e3
             per_ex = (ms - ms_compute) * 1e3 / 6.0
             exch = {"ms_per_step_compute_only": ms_compute, "exchanges_per_step": 6, "us_per_exchange_in_step": per_ex,
-                    "us_per_exchange_alone": us_exchange, "us_waiting_for_slowest_rank": per_ex - us_exchange,
-                    "note": "exchange alone = launch of one 1024-thread CTA + P2P stores + polling, ranks in lockstep; inside the step the "
-                            "exchange is the tail of the critic kernel (no extra launch), so the difference is rank skew"}
+                    "us_per_exchange_alone_incl_launch": us_exchange,
+                    "note": "in step = (data-parallel step - the same iteration on every rank without any exchange) / 6: store to every "
+                            "peer, poll, rank-ordered sum, plus waiting for the slowest rank; alone = one stand-alone launch of the "
+                            "exchange kernel per call in a tight loop (inside the step five of the six exchanges are the tail of the "
+                            "critic kernel and cost no launch)"}
         tflops = Bt * FLOP_TRAIN / (ms * 1e-3) / 1e12
         # end to end: every step's batch comes from pinned host memory (H2D inside the timed region, double-buffered on a copy
         # stream so the transfer of batch i+1 overlaps the compute of batch i - what a prefetching loader does), and the step's
