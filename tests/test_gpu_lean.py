@@ -72,10 +72,15 @@ def test_lean_injected_draws_equal_oracle(ops, tag):
     assert_close(snr, osnr, 1e-6, f"lean injected snr [{tag}]")
 
 
-@pytest.mark.parametrize("tag", ["nl_sep_grid", "awgn_joint", "nl_p2_bigpn"])
+METRIC_CASES = dict(CASES, grid16_ragged=dict(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=-2.0, snr_step=2.0, n_snr=16,
+                                               frames_per_snr=7),
+                    uniform_snr=dict(nonlinear=True, pa_saturation=0.9, normalize=2, snr_lo=3.0, snr_hi=27.0))
+
+
+@pytest.mark.parametrize("tag", ["nl_sep_grid", "awgn_joint", "nl_p2_bigpn", "grid16_ragged", "uniform_snr"])
 def test_lean_metrics_equal_general_and_oracle(ops, monkeypatch, tag):
-    kw = dict(CASES[tag])
-    if kw.get("snr_mode", 0) != 1:
+    kw = dict(METRIC_CASES[tag])
+    if kw.get("snr_mode", 0) != 1 and tag != "uniform_snr":
         kw.update(snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=64)
     rng = np.random.default_rng(2)
     gp = (rng.standard_normal(258) * 0.3).astype(np.float32)
