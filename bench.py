@@ -488,6 +488,23 @@ def main():
                                       "hbm_write_gbs": DS_FRAMES * 260 / (ms * 1e-3) / 1e9,
                                       "what": "ofdmgan_chan_sim = SyntheticOFDMDataset.__getitem__ x frames (utils/dataset.py:236-293), k_sim_lean<-1>"}
             del dc, dn, dsn
+        # ---- the separately named fast-RNG workload: the primary workload with Philox4x32-7 (the smallest round count Random123 documents
+        # as passing BigCrush) instead of Philox4x32-10.  NOT the headline and NOT the parity workload: a different random stream.
+        fcfg = ops.make_cfg(rng_rounds=7, **WORKLOAD)
+        ftab = torch.zeros_like(table)
+        for s_ in range(3):
+            ops.sim_gen_metrics(fcfg, F, gparams=gp_d, seed=1, frame0=(s_ * world + rank) * F, out=ftab)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s_ in range(K):
+            ops.sim_gen_metrics(fcfg, F, gparams=gp_d, seed=1, frame0=(s_ * world + rank) * F, out=ftab)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / K
+        also["fused_philox7"] = {"workload": "C4-fastrng: the primary workload with Philox4x32-7 draws (ofdmgan_chan_cfg.rng_rounds = 7)",
+                                 "frames_per_s": F * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": F,
+                                 "fp32_frac_of_ffma_peak": F * flop_frame / (ms * 1e-3) / 1e12 / ffma}
         # ---- QPSK variant of the primary workload (QAMModulator + OFDMModulator source, N = 16, no pilots / CP): adds hard-decision BER
         qcfg = ops.make_cfg(symbol_source=ops.SYM_QPSK, n_fft=16, cp_len=0, pilot_spacing=0, **WORKLOAD)
         qtab = None
@@ -681,7 +698,10 @@ def main():
     if rank == 0:
         tr = also.get("train") or {}
         summary = {"frames_per_s": value, "ms_per_step": ms_step, "roofline_frac": achieved / ffma, "e2e_frames_per_s": e2e_value,
-                   "sustained_frames_per_s": sustained and sustained["value"], "train_ms_per_step": tr.get("ms_per_step"),
+                   "sustained_frames_per_s": sustained and sustained["value"],
+                   "fast_rng_workload_frames_per_s": (also.get("fused_philox7") or {}).get("frames_per_s"),
+                   "fast_rng_workload_frac": (also.get("fused_philox7") or {}).get("fp32_frac_of_ffma_peak"),
+                   "train_ms_per_step": tr.get("ms_per_step"),
                    "train_samples_per_s": tr.get("samples_per_s"), "train_frac_of_ffma_peak": tr.get("fp32_frac_of_ffma_peak"),
                    "train_ms_per_step_nccl": tr.get("ms_per_step_with_nccl_exchange"), "train_exchange_breakdown": tr.get("exchange_breakdown"),
                    "multi_gpu_parity": parity["status"] if parity else ("n/a (1 GPU)" if world == 1 else None), "n_gpus": world}

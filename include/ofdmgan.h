@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 13
+#define OFDMGAN_ABI_VERSION 14
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -105,6 +105,10 @@ typedef struct ofdmgan_chan_cfg {
     float   saleh_alpha_a, saleh_beta_a, saleh_alpha_p, saleh_beta_p;
     float   dc_i, dc_q;        /* DC offset relative to sqrt(mean |x|^2)                     :541-543 */
     float   cfo_step;          /* 2 pi cfo_hz / sample_rate (radians per sample)             :565-566 */
+    int32_t rng_rounds;        /* rounds of the Philox4x32 counter RNG behind the on-chip draws: 0 or 10 = Philox4x32-10 (the default and
+                                  the parity workload); 7 = Philox4x32-7, the smallest round count Random123 documents as passing
+                                  BigCrush - a separately named "fast RNG" workload, built for the headline configurations only
+                                  (ofdmgan_sim_impl_for == 1 without injected draws; otherwise OFDMGAN_E_UNSUPPORTED) */
 } ofdmgan_chan_cfg;
 
 /* Host-generated randomness for parity runs, in the reference's np.random draw order per frame

@@ -39,6 +39,7 @@ class ChanCfg(ctypes.Structure):
         ("tap_delay", ctypes.c_int32 * 4), ("tap_amp", ctypes.c_float * 4),
         ("saleh_alpha_a", ctypes.c_float), ("saleh_beta_a", ctypes.c_float), ("saleh_alpha_p", ctypes.c_float),
         ("saleh_beta_p", ctypes.c_float), ("dc_i", ctypes.c_float), ("dc_q", ctypes.c_float), ("cfo_step", ctypes.c_float),
+        ("rng_rounds", ctypes.c_int32),
     ]
 
 
@@ -113,7 +114,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 13:
+        if L.ofdmgan_abi_version() != 14:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

@@ -113,12 +113,12 @@ __device__ __forceinline__ void fft_inplace(float (&re)[N], float (&im)[N]) {
 // (normals 0-15 Re, 16-31 Im), 8-10 the 8 phase-increment pairs, 12 {snr uniform, payload bits, LOS phase}, 13-18 the 16 noise
 // pairs (Re then Im), 21 / 22 two fading pairs each.  See oracle/channel.c header.
 // the section of NP pairs that starts at block blk0, as 2 NP normals of variance var
-template <int NP>
+template <int NP, int R = 10>
 __device__ __forceinline__ void draw_section(const SimArgs& a, uint64_t frame, uint32_t blk0, float (&n)[2 * NP], float var = 1.0f) {
 #pragma unroll
     for (int b = 0; b < (NP + 2) / 3; ++b) {
         uint32_t x[4];
-        philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), blk0 + b, 0u, x);
+        philox4x32<R>(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), blk0 + b, 0u, x);
         constexpr int last = NP - 3 * ((NP + 2) / 3 - 1);         // pairs in the last block
         const float k = OG_BM_K * var;
 #pragma unroll

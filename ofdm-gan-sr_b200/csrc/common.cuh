@@ -72,10 +72,17 @@ inline PhiloxKeys philox_keys(uint64_t seed) {
 __device__ __forceinline__ void mulwide(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
     asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%1, %0}, t;\n\t}" : "=r"(hi), "=r"(lo) : "r"(x), "r"(m));
 }
+// R rounds (10: the default everywhere; 7: the "fast RNG" workload of ofdmgan_chan_cfg.rng_rounds)
+template <int R>
+__device__ __forceinline__ void philox4x32(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]);
 __device__ __forceinline__ void philox4x32_10(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t (&out)[4]) {
+    philox4x32<10>(k, c0, c1, c2, c3, out);
+}
+template <int R>
+__device__ __forceinline__ void philox4x32(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < R; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulwide(0xD2511F53u, c0, hi0, lo0);
         mulwide(0xCD9E8D57u, c2, hi1, lo1);

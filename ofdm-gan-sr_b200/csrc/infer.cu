@@ -169,18 +169,19 @@ __global__ void __launch_bounds__(OG_THREADS) k_equalize(const float* __restrict
 }
 
 // raw draws (test hook)
+template <int R>
 __global__ void k_chan_draws(const __grid_constant__ SimArgs a, float* sym, uint32_t* bits, float* pn, float* snr_db,
                              float* noise) {
     const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const uint64_t frame = a.frame0 + (uint64_t)b;
     float n[32];
-    if (sym) { draw_section<16>(a, frame, 0u, n); for (int t = 0; t < 32; ++t) sym[b * 32 + t] = n[t]; }
-    if (pn) { float m[16]; draw_section<8>(a, frame, 8u, m); for (int t = 0; t < 16; ++t) pn[b * 16 + t] = m[t]; }
-    if (noise) { draw_section<16>(a, frame, 13u, n); for (int t = 0; t < 32; ++t) noise[b * 32 + t] = n[t]; }
+    if (sym) { draw_section<16, R>(a, frame, 0u, n); for (int t = 0; t < 32; ++t) sym[b * 32 + t] = n[t]; }
+    if (pn) { float m[16]; draw_section<8, R>(a, frame, 8u, m); for (int t = 0; t < 16; ++t) pn[b * 16 + t] = m[t]; }
+    if (noise) { draw_section<16, R>(a, frame, 13u, n); for (int t = 0; t < 32; ++t) noise[b * 32 + t] = n[t]; }
     if (bits || snr_db) {
         uint32_t x[4];
-        philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x);
+        philox4x32<R>(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x);
         if (bits) bits[b] = x[1];
         if (snr_db) snr_db[b] = fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x[0]), a.cfg.snr_lo);
     }
@@ -224,6 +225,7 @@ static int check_cfg(const ofdmgan_chan_cfg* c, int* n_snr) {
     if (c->normalize < 0 || c->normalize > 2 || c->ifft_scale < 0 || c->ifft_scale > 1 || c->pilot_spacing < 0) return OFDMGAN_E_ARG;
     if ((c->impair & OFDMGAN_IMPAIR_PA) && !(c->pa_saturation > 0.f && c->pa_smoothness > 0.f)) return OFDMGAN_E_ARG;
     if (c->impair & ~63) return OFDMGAN_E_ARG;
+    if (c->rng_rounds != 0 && c->rng_rounds != 7 && c->rng_rounds != 10) return OFDMGAN_E_ARG;
     if (c->channel_type < OFDMGAN_CHAN_AWGN || c->channel_type > OFDMGAN_CHAN_MULTIPATH) return OFDMGAN_E_ARG;
     if (c->channel_type == OFDMGAN_CHAN_RICIAN && !(c->rician_k >= 0.f)) return OFDMGAN_E_ARG;
     if (c->channel_type == OFDMGAN_CHAN_MULTIPATH) {
@@ -328,6 +330,7 @@ static bool sim_lean_enabled() {
 }
 static int sim_dispatch(const SimCall& c) {
     if (sim_lean_enabled() && sim_lean_eligible(c)) return sim_launch_lean(c);
+    if (c.cfg->rng_rounds == 7) return OFDMGAN_E_UNSUPPORTED;       // the fast-RNG workload is built for the headline kernel only
     return c.src == SRC_GAUSS ? sim_launch_gauss(c) : sim_launch_qpsk(c);
 }
 
@@ -354,7 +357,10 @@ int ofdmgan_chan_draws(const ofdmgan_chan_cfg* cfg_host, uint64_t seed, uint64_t
     a.keys = philox_keys(seed);
     a.frame0 = frame0;
     a.B = B;
-    k_chan_draws<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, sym_dev, bits_dev, pn_dev, snr_db_dev, noise_dev);
+    if (cfg_host->rng_rounds == 7)
+        k_chan_draws<7><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, sym_dev, bits_dev, pn_dev, snr_db_dev, noise_dev);
+    else
+        k_chan_draws<10><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, sym_dev, bits_dev, pn_dev, snr_db_dev, noise_dev);
     return (int)cudaGetLastError();
 }
 

@@ -59,6 +59,7 @@ __device__ __forceinline__ PhiloxFrame philox_frame(const PhiloxKeys& k, uint64_
     f.cc = lo0 ^ k.k1[1];
     return f;
 }
+template <int R>
 __device__ __forceinline__ void philox_block(const PhiloxKeys& k, const PhiloxFrame& f, uint32_t blk, uint32_t (&out)[4]) {
     uint32_t hi1, lo1, c2, c3;
     mulwide(0xCD9E8D57u, blk, hi1, lo1);
@@ -67,7 +68,7 @@ __device__ __forceinline__ void philox_block(const PhiloxKeys& k, const PhiloxFr
     mulwide(0xD2511F53u, n0, c2, c3);
     c2 ^= f.cc;
 #pragma unroll
-    for (int r = 2; r < 10; ++r) {
+    for (int r = 2; r < R; ++r) {
         uint32_t h0, l0, h1, l1;
         mulwide(0xD2511F53u, c0, h0, l0);
         mulwide(0xCD9E8D57u, c2, h1, l1);
@@ -79,13 +80,13 @@ __device__ __forceinline__ void philox_block(const PhiloxKeys& k, const PhiloxFr
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 // NP pairs of the section that starts at block blk0, in polar pieces: normal 2p = r[p] c[p], normal 2p+1 = r[p] s[p]
-template <int NP>
+template <int NP, int R>
 __device__ __forceinline__ void section_polar(const PhiloxKeys& keys, const PhiloxFrame& f, uint32_t blk0, float k, float (&r)[NP],
                                               float (&c)[NP], float (&s)[NP]) {
 #pragma unroll
     for (int b = 0; b < (NP + 2) / 3; ++b) {
         uint32_t x[4];
-        philox_block(keys, f, blk0 + b, x);
+        philox_block<R>(keys, f, blk0 + b, x);
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             if (3 * b + q < NP) bm_polar(x, q, k, r[3 * b + q], c[3 * b + q], s[3 * b + q]);
@@ -290,7 +291,8 @@ struct LeanArgs {
     SimArgs a;
     GImage g;
 };
-template <int GEN, bool INJ, bool OUT, int CHAIN, bool BYVAL>
+// R: Philox rounds (10; 7 = the separately named fast-RNG workload, ofdmgan_chan_cfg.rng_rounds)
+template <int GEN, bool INJ, bool OUT, int CHAIN, bool BYVAL, int R>
 __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constant__ LeanArgs la) {
     const SimArgs& a = la.a;
     extern __shared__ float4 sm[];
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
             snr_db = inj_snr[bb];
         } else {
             uint32_t x12[4];
-            philox4x32_10(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
+            philox4x32<R>(a.keys, (uint32_t)frame, (uint32_t)(frame >> 32), 12u, 0u, x12);
             snr_db = fmaf(a.cfg.snr_hi - a.cfg.snr_lo, u_half(x12[0]), a.cfg.snr_lo);
         }
 
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
             for (int k = 0; k < 16; ++k) { zr[k] = inj_sym[bb * 32 + k] * sc.sc_in; zi[k] = inj_sym[bb * 32 + 16 + k] * sc.sc_in; }
         } else {
             float r[16], c[16], s[16];
-            section_polar<16>(a.keys, pf, 0u, sc.k_sym, r, c, s);
+            section_polar<16, R>(a.keys, pf, 0u, sc.k_sym, r, c, s);
             ifft16_polar(r, c, s, zr, zi);
         }
         if (inj_sym) ifft16(zr, zi);
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
         if (pn_on) {
             auto steps = [&](auto fast) {
                 float th = 0.f, r[8], c[8], s[8];
-                if (!inj_pn) section_polar<8>(a.keys, pf, 8u, sc.k_pn, r, c, s);
+                if (!inj_pn) section_polar<8, R>(a.keys, pf, 8u, sc.k_pn, r, c, s);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     if (inj_pn) th = fmaf(inj_pn[bb * 16 + i], sc.pn_sigma, th);
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
                 }
             } else {
                 float r[16], c[16], s[16];
-                section_polar<16>(a.keys, pf, 13u, OG_BM_K * nv, r, c, s);
+                section_polar<16, R>(a.keys, pf, 13u, OG_BM_K * nv, r, c, s);
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
                     nr[2 * p] = fmaf(r[p], c[p], nr[2 * p]); nr[2 * p + 1] = fmaf(r[p], s[p], nr[2 * p + 1]);
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(LN_THREADS, 1) k_sim_lean(const __grid_constan
     }
 }
 
-template <int GEN, bool INJ, bool OUT, int CHAIN, bool BYVAL>
+template <int GEN, bool INJ, bool OUT, int CHAIN, bool BYVAL, int R>
 static int sim_lean_launch_impl(const SimCall& c, LeanArgs& la) {
     cudaStream_t s = c.stream;
     int rc, err = 0;
@@ -561,7 +563,7 @@ static int sim_lean_launch_impl(const SimCall& c, LeanArgs& la) {
     int64_t want = (ng + LN_W - 1) / LN_W;
     if (want < 1) want = 1;
     const int grid = (int)(want < sms ? want : sms);                 // persistent: one CTA per SM
-    OG_CHECK(cudaFuncSetAttribute(k_sim_lean<GEN, INJ, OUT, CHAIN, BYVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LN_SMEM));
+    OG_CHECK(cudaFuncSetAttribute(k_sim_lean<GEN, INJ, OUT, CHAIN, BYVAL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LN_SMEM));
     const int n = c.n_snr * NM * NC;
     void* partials = nullptr;
     // per-stream scratch for the per-CTA partial tables: by-value calls hold no lock, so streams must not share it
@@ -578,7 +580,7 @@ static int sim_lean_launch_impl(const SimCall& c, LeanArgs& la) {
     a.slope = c.slope;
     a.partials = (double*)partials;
     a.n_snr = c.n_snr;
-    k_sim_lean<GEN, INJ, OUT, CHAIN, BYVAL><<<grid, LN_THREADS, LN_SMEM, s>>>(la);
+    k_sim_lean<GEN, INJ, OUT, CHAIN, BYVAL, R><<<grid, LN_THREADS, LN_SMEM, s>>>(la);
     OG_CHECK(cudaGetLastError());
     if (partials) {
         reduce_partials_launch((const double*)partials, grid, n, c.metrics, s);
@@ -586,20 +588,20 @@ static int sim_lean_launch_impl(const SimCall& c, LeanArgs& la) {
     }
     return 0;
 }
-template <int GEN, bool INJ, bool OUT, int CHAIN>
+template <int GEN, bool INJ, bool OUT, int CHAIN, int R = 10>
 static int sim_lean_launch_one(const SimCall& c) {
     static thread_local LeanArgs la;                                 // (5 KB: not on the stack of every caller)
     if constexpr (GEN == OFDMGAN_GEN_F32 && !INJ) {
         if (is_host_pointer(c.gparams258)) {
             g_image_host(c.gparams258, la.g);                        // inference weights by value: no shared state, no lock
-            return sim_lean_launch_impl<GEN, INJ, OUT, CHAIN, true>(c, la);
+            return sim_lean_launch_impl<GEN, INJ, OUT, CHAIN, true, R>(c, la);
         }
     }
     int rc;
     CallGuard guard(c.stream);                                       // device-resident weights: the __constant__ image
     if ((rc = guard.rc)) return rc;
     if (GEN == OFDMGAN_GEN_F32 && (rc = upload_g(c.gparams258, 0, c.stream))) return rc;
-    return sim_lean_launch_impl<GEN, INJ, OUT, CHAIN, false>(c, la);
+    return sim_lean_launch_impl<GEN, INJ, OUT, CHAIN, false, R>(c, la);
 }
 
 // Is this call the headline shape?  Gaussian source, no injected time-domain frames / fading draws, no late stages, no
@@ -612,6 +614,7 @@ bool sim_lean_eligible(const SimCall& c) {
     if ((c.cfg->impair & OFDMGAN_IMPAIR_PA) && !(c.cfg->pa_saturation > 0.f)) return false;
     if (c.rand && (c.rand->tx || c.rand->fade)) return false;
     if (c.gen_kind == OFDMGAN_GEN_F32 && (c.clean || c.noisy || c.snr)) return false;   // (not reachable through the C ABI)
+    if (c.cfg->rng_rounds == 7 && c.rand && (c.rand->sym || c.rand->pn || c.rand->snr_db || c.rand->noise)) return false;
     return true;
 }
 // the stage set of a configuration (CHAIN_*)
@@ -628,6 +631,13 @@ template <int GEN>
 static int sim_lean_launch_chain(const SimCall& c, bool inj) {
     constexpr bool OUT = GEN < 0;
     if (inj) return sim_lean_launch_one<GEN, true, OUT, CHAIN_ANY>(c);     // parity runs: one instantiation with every branch
+    if (c.cfg->rng_rounds == 7) {                                          // the fast-RNG workload: the two reference chains only
+        switch (chain_of(*c.cfg)) {
+            case CHAIN_LINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_LINEAR, 7>(c);
+            case CHAIN_NONLINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_NONLINEAR, 7>(c);
+            default: return OFDMGAN_E_UNSUPPORTED;
+        }
+    }
     switch (chain_of(*c.cfg)) {
         case CHAIN_LINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_LINEAR>(c);
         case CHAIN_NONLINEAR: return sim_lean_launch_one<GEN, false, OUT, CHAIN_NONLINEAR>(c);

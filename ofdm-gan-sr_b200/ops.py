@@ -23,7 +23,7 @@ def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pi
              nonlinear=False, pa=None, iq=None, pn=None, pa_saturation=1.0, pa_smoothness=3.0, iq_imbalance_db=1.0,
              iq_phase_deg=5.0, phase_noise_dbchz=-80.0, sample_rate=1e6, snr_mode=SNR_UNIFORM, snr_lo=0.0, snr_hi=30.0,
              snr_step=5.0, n_snr=1, frames_per_snr=1, normalize=NORM_JOINT, equalizers=False, channel_type=CHAN_AWGN,
-             rician_k=3.0, delays=(0, 1, 2), powers=(1.0, 0.5, 0.25), saleh=None, dc_offset=None, cfo_hz=None):
+             rician_k=3.0, delays=(0, 1, 2), powers=(1.0, 0.5, 0.25), saleh=None, dc_offset=None, cfo_hz=None, rng_rounds=10):
     """ChanCfg from the reference's user-facing parameters: SyntheticOFDMDataset.__init__ (utils/dataset.py:195-206),
     NonLinearImpairments defaults (utils/ofdm_utils.py:394-521), run_benchmark's SNR grid
     (benchmark_comparison.py:179-182)."""
@@ -61,6 +61,7 @@ def make_cfg(symbol_source=SYM_GAUSSIAN, n_fft=16, cp_len=0, pilot_spacing=0, pi
     if cfo_hz is not None:
         c.impair |= IMPAIR_CFO
         c.cfo_step = 2.0 * math.pi * float(cfo_hz) / float(sample_rate)
+    c.rng_rounds = int(rng_rounds)         # 10: Philox4x32-10 (default, the parity workload); 7: the "fast RNG" workload
     return c
 
 

@@ -43,13 +43,14 @@ class ChanCfg(ctypes.Structure):
         ("tap_delay", ctypes.c_int32 * 4), ("tap_amp", ctypes.c_float * 4),
         ("saleh_alpha_a", ctypes.c_float), ("saleh_beta_a", ctypes.c_float), ("saleh_alpha_p", ctypes.c_float),
         ("saleh_beta_p", ctypes.c_float), ("dc_i", ctypes.c_float), ("dc_q", ctypes.c_float), ("cfo_step", ctypes.c_float),
+        ("rng_rounds", ctypes.c_int32),
     ]
 
 
 def make_cfg(symbol_source=0, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j, ifft_scale=0, nonlinear=False,
              pa=None, iq=None, pn=None, pa_saturation=1.0, pa_smoothness=3.0, iq_imbalance_db=1.0, iq_phase_deg=5.0,
              phase_noise_dbchz=-80.0, sample_rate=1e6, snr_mode=0, snr_lo=0.0, snr_hi=30.0, snr_step=5.0, n_snr=1,
-             frames_per_snr=1, normalize=1, equalizers=False):
+             frames_per_snr=1, normalize=1, equalizers=False, rng_rounds=10):
     """Build a ChanCfg from the reference's user-facing parameters (SyntheticOFDMDataset.__init__,
     utils/dataset.py:195-206; NonLinearImpairments defaults, utils/ofdm_utils.py:394-521)."""
     pa = nonlinear if pa is None else pa
@@ -68,6 +69,7 @@ def make_cfg(symbol_source=0, n_fft=16, cp_len=0, pilot_spacing=0, pilot=1 + 0j,
     c.snr_mode, c.snr_lo, c.snr_hi, c.snr_step = snr_mode, snr_lo, snr_hi, snr_step
     c.n_snr, c.frames_per_snr, c.normalize = n_snr, frames_per_snr, normalize
     c.equalizers = 1 if equalizers else 0
+    c.rng_rounds = int(rng_rounds)
     return c
 
 

@@ -38,8 +38,15 @@
 #endif
 
 /* ------------------------------------------------------------------ Philox4x32-10 ------------------------ */
+static int g_rounds = 10;   /* set per call from cfg->rng_rounds by the entry points below (the oracle is test infrastructure: not re-entrant across
+                               different round counts at the same time; every OpenMP thread of one call sees the same value) */
+static void set_rounds(const ofdmgan_chan_cfg* cfg) { g_rounds = (cfg && cfg->rng_rounds == 7) ? 7 : 10; }
+void oracle_philox4x32_r(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, int rounds, uint32_t out[4]);
 void oracle_philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
-    for (int r = 0; r < 10; ++r) {
+    oracle_philox4x32_r(k0, k1, c0, c1, c2, c3, 10, out);
+}
+void oracle_philox4x32_r(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, int rounds, uint32_t out[4]) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -68,8 +75,8 @@ static void section_normals(uint64_t seed, uint64_t frame, uint32_t blk0, uint32
     for (int p = 0; p < npairs; ++p) {
         int slot = p % 3;
         if (slot == 0)
-            oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), blk0 + (uint32_t)(p / 3),
-                                 purpose, x);
+            oracle_philox4x32_r((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), blk0 + (uint32_t)(p / 3),
+                                purpose, purpose == 0 ? g_rounds : 10, x);
         uint32_t a16 = slot == 0 ? (x[3] & 0xFFFFu) : slot == 1 ? (x[3] >> 16) : ((x[0] >> 24) | ((x[1] >> 24) << 8));
         double u1 = ((double)(x[slot] & 0x7FFFFFu) + 0.5) * (1.0 / 8388608.0);
         double r = sqrt(-2.0 * log(u1)), th = 2.0 * M_PI * (double)a16 * (1.0 / 65536.0);
@@ -79,14 +86,21 @@ static void section_normals(uint64_t seed, uint64_t frame, uint32_t blk0, uint32
 }
 
 /* the draws frame `frame` consumes; any output may be NULL */
+static void frame_draws(const ofdmgan_chan_cfg* cfg, uint64_t seed, uint64_t frame, double* sym32, uint32_t* bits,
+                        double* pn16, double* snr_db, double* noise32);
 void oracle_frame_draws(const ofdmgan_chan_cfg* cfg, uint64_t seed, uint64_t frame, double* sym32, uint32_t* bits,
+                        double* pn16, double* snr_db, double* noise32) {
+    set_rounds(cfg);
+    frame_draws(cfg, seed, frame, sym32, bits, pn16, snr_db, noise32);
+}
+static void frame_draws(const ofdmgan_chan_cfg* cfg, uint64_t seed, uint64_t frame, double* sym32, uint32_t* bits,
                         double* pn16, double* snr_db, double* noise32) {
     if (sym32) section_normals(seed, frame, 0, 0, 16, sym32);
     if (pn16) section_normals(seed, frame, 8, 0, 8, pn16);
     if (noise32) section_normals(seed, frame, 13, 0, 16, noise32);
     if (bits || snr_db) {
         uint32_t x[4];
-        oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), 12, 0, x);
+        oracle_philox4x32_r((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), 12, 0, g_rounds, x);
         if (bits) *bits = x[1];
         if (snr_db) *snr_db = (double)cfg->snr_lo + ((double)cfg->snr_hi - (double)cfg->snr_lo) * u_half(x[0]);
     }
@@ -205,7 +219,7 @@ static void sim_frame(const ofdmgan_chan_cfg* cfg, const double* sym, const uint
                       float* noisy, float* snr_out, uint32_t* bits_out) {
     double s32[32], p16[16], n32[32], snr_u = 0, xr[16], xi[16], yr[16], yi[16];
     uint32_t bw = 0;
-    oracle_frame_draws(cfg, seed, frame, sym ? NULL : s32, bits ? NULL : &bw, pn ? NULL : p16, snr_db ? NULL : &snr_u,
+    frame_draws(cfg, seed, frame, sym ? NULL : s32, bits ? NULL : &bw, pn ? NULL : p16, snr_db ? NULL : &snr_u,
                        noise ? NULL : n32);
     if (sym) memcpy(s32, sym, sizeof s32);
     if (pn) memcpy(p16, pn, sizeof p16);
@@ -228,6 +242,7 @@ int oracle_chan_sim(const ofdmgan_chan_cfg* cfg, const double* sym, const uint32
                     const double* snr_db, const double* noise, uint64_t seed, uint64_t frame0, float* clean,
                     float* noisy, float* snr_out, int64_t B) {
     if (!cfg || (cfg->n_fft != 8 && cfg->n_fft != 16) || cfg->cp_len < 0 || cfg->cp_len > cfg->n_fft) return -1;
+    set_rounds(cfg);
 #pragma omp parallel for schedule(static)
     for (int64_t b = 0; b < B; ++b) {
         float c[32], n[32], s;
@@ -308,6 +323,7 @@ int oracle_sim_gen_metrics(const ofdmgan_chan_cfg* cfg, int gen_kind, const floa
     if (n_snr < 1 || n_snr > OFDMGAN_MAX_SNR_BINS) return -1;
     size_t rows = (size_t)n_snr * OFDMGAN_N_METHODS * OFDMGAN_METRIC_COLS;
     int rc = 0;
+    set_rounds(cfg);
 #pragma omp parallel
     {
         double* local = (double*)calloc(rows, sizeof(double));
@@ -339,7 +355,7 @@ int oracle_sim_gen_metrics(const ofdmgan_chan_cfg* cfg, int gen_kind, const floa
                 double snr_db = oracle_snr_of_frame(cfg, frame, 0.0);
                 if (cfg->snr_mode != OFDMGAN_SNR_GRID) {
                     uint32_t x12[4];
-                    oracle_philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), 12, 0, x12);
+                    oracle_philox4x32_r((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)frame, (uint32_t)(frame >> 32), 12, 0, g_rounds, x12);
                     snr_db = (double)(float)((double)cfg->snr_lo + ((double)cfg->snr_hi - (double)cfg->snr_lo) * u_half(x12[0]));
                 }
                 for (int method = OFDMGAN_METHOD_ZF; method <= OFDMGAN_METHOD_MMSE; ++method) {

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_abi_version_and_error_strings(pkg):
     L = pkg._lib.lib()
-    assert L.ofdmgan_abi_version() == 13
+    assert L.ofdmgan_abi_version() == 14
     assert L.ofdmgan_error_string(0) == b"ok"
     assert b"invalid argument" in L.ofdmgan_error_string(-1)
     assert b"streams" in L.ofdmgan_error_string(-2)
@@ -52,11 +52,11 @@ def test_abi_version_and_error_strings(pkg):
 
 def test_struct_layout_matches_header(pkg):
     # ofdmgan_chan_cfg: 14 x 4-byte fields + (4 x 4) + int64 + 2 x int32, natural alignment
-    assert ctypes.sizeof(pkg._lib.ChanCfg) == 168
+    assert ctypes.sizeof(pkg._lib.ChanCfg) == 176
     assert pkg._lib.ChanCfg.frames_per_snr.offset == 80
     assert ctypes.sizeof(pkg._lib.ChanRand) == 8 * ctypes.sizeof(ctypes.c_void_p)
     import oracle
-    assert ctypes.sizeof(oracle.ChanCfg) == 168
+    assert ctypes.sizeof(oracle.ChanCfg) == 176
     for (n1, t1), (n2, t2) in zip(pkg._lib.ChanCfg._fields_, oracle.ChanCfg._fields_):
         assert n1 == n2 and ctypes.sizeof(t1) == ctypes.sizeof(t2)
 

@@ -112,3 +112,38 @@ def test_lean_is_what_the_headline_calls_run_on(ops):
     assert f(ctypes.byref(ops.make_cfg(channel_type="rayleigh")), ops.GEN_F32, 0) == 0
     assert f(ctypes.byref(ops.make_cfg(symbol_source=1)), -1, 0) == 0
     assert f(ctypes.byref(head), ops.GEN_F32, 1) == 0                # caller-supplied time-domain frames / fading draws
+
+
+# ------------------------------------------------------------------------------------------------ the fast-RNG workload (Philox4x32-7)
+def test_philox7_workload_matches_its_oracle_and_is_a_different_stream(ops):
+    """ofdmgan_chan_cfg.rng_rounds = 7: the separately named fast-RNG workload.  Same algorithm with seven rounds on both sides (the
+    ten-round generator is the one pinned by Random123's known answers); frames and metrics against the oracle like the default."""
+    import ofdm_gan_sr_b200 as pkg
+    kw = dict(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7, frames_per_snr=64)
+    c7, c10 = ops.make_cfg(rng_rounds=7, **kw), ops.make_cfg(**kw)
+    d = ops.chan_draws(c7, 2048, seed=5, frame0=77)
+    o = oracle.frame_draws(oracle.make_cfg(rng_rounds=7, **kw), 5, 77, 2048)
+    for k in ("sym", "pn", "noise"):
+        e = np.abs(host(d[k]) - o[k])
+        assert e.mean() < 1e-6 and np.quantile(e, 0.999) < 5e-6 and e.max() < 2e-4, k
+    assert np.abs(host(d["sym"]) - host(ops.chan_draws(c10, 2048, seed=5, frame0=77)["sym"])).max() > 0.5
+    B = 7 * 64 * 5 + 3
+    clean, noisy, _ = (host(t) for t in ops.chan_sim(c7, B, seed=5, frame0=77))
+    oc, on, _ = oracle.chan_sim(oracle.make_cfg(rng_rounds=7, **kw), B, seed=5, frame0=77)
+    assert_close(clean, oc, 5e-5, "philox-7 clean vs oracle")
+    assert_close(noisy, on, 5e-5, "philox-7 noisy vs oracle")
+    gp = (np.random.default_rng(1).standard_normal(258) * 0.3).astype(np.float32)
+    m = host(ops.sim_gen_metrics(c7, B, gparams=gp, seed=5, frame0=77))
+    om = oracle.sim_gen_metrics(oracle.make_cfg(rng_rounds=7, **kw), 0, B, gparams=gp, seed=5, frame0=77)
+    assert np.array_equal(m[:, :2, 0], om[:, :2, 0])
+    for c in (1, 3):
+        assert_close(m[:, :2, c], om[:, :2, c], 5e-5, f"philox-7 metrics col {c}")
+    m10 = host(ops.sim_gen_metrics(c10, B, gparams=gp, seed=5, frame0=77))
+    assert not np.allclose(m[:, :2, 1], m10[:, :2, 1], rtol=1e-6)
+    # built for the headline kernel only
+    with pytest.raises(pkg.OfdmGanError):
+        ops.sim_gen_metrics(ops.make_cfg(rng_rounds=7, equalizers=True, **kw), 64, gparams=gp)
+    with pytest.raises(pkg.OfdmGanError):
+        ops.chan_sim(ops.make_cfg(rng_rounds=7, symbol_source=1, **kw), 64)
+    with pytest.raises(pkg.OfdmGanError):
+        ops.chan_sim(ops.make_cfg(rng_rounds=5, **kw), 64)
