@@ -28,7 +28,7 @@ struct CriticArgs {
 // ------------------------------------------------------------------------------------------------ critic step, v2
 // Work item = (term, 128-sample tile) with term in {penalty, -D(real), +D(fake)}: three times the parallelism of one
 // thread doing all three terms of its sample, which matters at 65,536 samples per GPU (443 samples per SM).  The
-// heaviest term (penalty) is scheduled first.  <= 128 registers: 4 CTAs (16 warps) per SM, see critic_stream.cuh.
+// heaviest term (penalty, 1.15x a score term by instruction count) is scheduled first.  <= 128 registers: 4 CTAs (16 warps) per SM, see critic_stream.cuh.
 #ifndef OG_CRITIC_PER_SM
 #define OG_CRITIC_PER_SM 4
 #endif
@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(OG_THREADS, CRITIC_PER_SM) k_critic2(const __g
 #pragma unroll
     for (int g = 0; g < CS_NG; ++g) sacc[g * OG_THREADS + threadIdx.x] = 0.f;     // thread-private entries: no barrier needed
     float s_real = 0.f, s_fake = 0.f, s_gp = 0.f;
+    // Static round-robin of tile items over the CTAs (the summation order is fixed).  With 4 CTAs per SM placed at stride 148 (traced
+    // with %smid) every scheduler of an SM holds one warp of each CTA, so 1 536 items over 592 CTAs are 10 or 11 warp items per
+    // scheduler - as even as 32-sample items get.  Handing items out per warp, spreading the last round's items evenly over the CTAs,
+    // or steering the (15 % dearer) penalty items to the SMs with 10 items all measured slower (profiles/r2_notes.md).
     const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
     const int64_t ntasks = ntiles * (SCORE ? 3 : 1);
     for (int64_t task = blockIdx.x; task < ntasks; task += gridDim.x) {

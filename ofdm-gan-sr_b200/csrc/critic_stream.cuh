@@ -19,8 +19,11 @@
 //                         spare j = 24..31: group 0 -> conv1.bias[8]; group 1 -> dense.bias (24), sum D(real) (25),
 //                         sum D(fake) (26), sum penalty (27)
 //   group 4 + 2*o2 + q    (o2 = output-channel pair 0..7, q = input-channel half 0..1)
-//                         conv2.weight[2*o2+h][4*q+c][k] at j = h*12 + c*3 + k (24 slots); in the q = 0 group additionally
-//                         conv2.bias[2*o2+h] at j = 24+h and dense.weight[2*o2+h] at j = 26+h
+//                         conv2.weight[2*o2+h][4*q+c][k] at j = h*16 + c*3 + k (24 slots); in the q = 0 group additionally
+//                         conv2.bias[2*o2+h] at j = h*16 + 12 and dense.weight[2*o2+h] at j = h*16 + 13.
+//                         Channel h of the pair sits in half h of the group, so the first (16-lane) stage of the transpose-reduce
+//                         is an exchange of the two halves of an FFMA2 result: lanes 16-31 build their pairs swapped and the
+//                         stage needs no selects (warp_transpose_reduce_pairs below).
 // Maths: models/discriminator.py:112-152 (forward), :172-236 (penalty), closed-form double backward as in
 // oracle/fp32_models.c gp_sample.
 #pragma once
@@ -38,10 +41,48 @@ constexpr int CS_FCB = 32 + 24, CS_SREAL = 32 + 25, CS_SFAKE = 32 + 26, CS_SGP =
 __host__ __device__ constexpr int cs_param_of(int grp, int j) {
     if (grp < 4) return j < 24 ? ((j / 3) * 4 + grp) * 3 + j % 3 : (grp == 0 ? DP_C1_B + (j - 24) : (grp == 1 && j == 24 ? DP_FC_B : -1));
     const int o2 = (grp - 4) >> 1, q = (grp - 4) & 1;
-    if (j < 24) return DP_C2_W + ((2 * o2 + j / 12) * 8 + 4 * q + (j % 12) / 3) * 3 + j % 3;
-    if (q == 0 && j < 26) return DP_C2_B + 2 * o2 + (j - 24);
-    if (q == 0 && j < 28) return DP_FC_W + 2 * o2 + (j - 26);
+    const int h = j >> 4, r = j & 15;
+    if (r < 12) return DP_C2_W + ((2 * o2 + h) * 8 + 4 * q + r / 3) * 3 + r % 3;
+    if (q == 0 && r == 12) return DP_C2_B + 2 * o2 + h;
+    if (q == 0 && r == 13) return DP_FC_W + 2 * o2 + h;
     return -1;
+}
+
+// (lo, hi) -> (hi, lo) in the lanes that `up` selects
+__device__ __forceinline__ f32x2 cs_swap_if(bool up, f32x2 v) {
+    float lo, hi;
+    upk2(v, lo, hi);
+    return pk2(up ? hi : lo, up ? lo : hi);
+}
+
+// Transpose-reduce of a 32-slot group given as N <= 16 PAIRS: pv[i] = (slot i, slot 16 + i) in lanes 0-15 and (slot 16 + i, slot i)
+// in lanes 16-31, slots N..15 and 16+N..31 empty.  Every lane keeps the first half and sends the second: the 16-lane stage costs
+// SHFL + FADD per pair and no selects; the remaining four stages are the generic ones on 16 values.  Lane l returns slot l.
+template <int N, int M>
+__device__ __forceinline__ float warp_transpose_reduce_pairs(const f32x2 (&pv)[M], int lane) {
+    static_assert(N <= M && N <= 16, "pairs in use");
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < N) {
+            float keep, send;
+            upk2(pv[i], keep, send);
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        } else {
+            v[i] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = upper ? v[i] : v[i + s];
+            const float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
 }
 
 // shared-memory gradient accumulator of one CTA: [CS_NG][threads]
@@ -172,10 +213,15 @@ __device__ __forceinline__ uint64_t cs_conv2_pass(const float* W, float slope, f
             score = fmaf(wd.x, pl_lo, fmaf(wd.y, pl_hi, score));
         }
         if (MODE >= 1) {
-            const f32x2 gw = pk2(g * wd.x, g * wd.y);
+            // lanes 16-31 carry the pair's two output channels swapped (see warp_transpose_reduce_pairs)
+            const bool up = (lane & 16) != 0;
+            const f32x2 gw = cs_swap_if(up, pk2(g * wd.x, g * wd.y));
+            f32x2 mg[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) mg[p] = cs_swap_if(up, mk[p]);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {                       // input-channel half: one 32-slot group each
-                float v[32];
+                f32x2 pv[14];
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -186,27 +232,24 @@ __device__ __forceinline__ uint64_t cs_conv2_pass(const float* W, float slope, f
                             const int i = 2 * p + k - 1;
                             if (i >= 0) {
                                 const float a = CS_CH(in, 4 * q + c, i);
-                                a2 = fma2(mk[p], pk2(a, a), a2);
+                                a2 = fma2(mg[p], pk2(a, a), a2);
                             }
                         }
-                        a2 = fma2(a2, gw, pk2(0.f, 0.f));
-                        upk2(a2, v[c * 3 + k], v[12 + c * 3 + k]);
+                        pv[c * 3 + k] = fma2(a2, gw, pk2(0.f, 0.f));
                     }
-#pragma unroll
-                for (int j = 24; j < 32; ++j) v[j] = 0.f;
                 if (q == 0) {
+                    const f32x2 pl = cs_swap_if(up, pk2(pl_lo, pl_hi));
                     if (MODE == 1) {
-                        const float2 m0 = f2(mk[0]), m1 = f2(mk[1]), m2f = f2(mk[2]), m3 = f2(mk[3]);
-                        v[24] = g * wd.x * ((m0.x + m1.x) + (m2f.x + m3.x));      // conv2.bias = sum_p dz2
-                        v[25] = g * wd.y * ((m0.y + m1.y) + (m2f.y + m3.y));
-                        v[26] = g * pl_lo;                                        // dense.weight = g * pool
-                        v[27] = g * pl_hi;
+                        pv[12] = mul2(gw, add2(add2(mg[0], mg[1]), add2(mg[2], mg[3])));     // conv2.bias = sum_p dz2
+                        pv[13] = mul2(pk2(g, g), pl);                                        // dense.weight = g * pool
                     } else {
-                        v[26] = pl_lo;                                            // penalty: d wd, no bias gradient
-                        v[27] = pl_hi;
+                        pv[12] = pk2(0.f, 0.f);                                   // penalty: no bias gradient
+                        pv[13] = pl;                                              // d wd
                     }
+                    acc.add(4 + 2 * o2 + q, warp_transpose_reduce_pairs<14>(pv, lane));
+                } else {
+                    acc.add(4 + 2 * o2 + q, warp_transpose_reduce_pairs<12>(pv, lane));
                 }
-                acc.add(4 + 2 * o2 + q, warp_transpose_reduce(v, lane));
             }
         }
     }

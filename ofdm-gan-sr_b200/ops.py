@@ -2,6 +2,7 @@
 asynchronous on torch's current stream.  No CPU path - a CPU tensor raises OfdmGanError."""
 import ctypes
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -98,16 +99,19 @@ _FLAT_CACHE = {}
 
 def flat_cached(params):
     """The flat fp32 vector of a parameter list, rebuilt only when a parameter changed (torch bumps a tensor's `_version` on every
-    in-place write, e.g. optimizer.step()): the module path of the fused forward / backward then launches no `cat` kernel per call."""
+    in-place write, e.g. optimizer.step()): the module path of the fused forward / backward then launches no `cat` kernel per call.
+    An entry belongs to the tensor OBJECTS it was built from (held weakly): a new module whose parameters were allocated at the
+    addresses of a freed one, with the same version counters, must not see the old module's weights."""
+    params = tuple(params)
     key = tuple((p.data_ptr(), p._version) for p in params)
     ident = tuple(k[0] for k in key)
     hit = _FLAT_CACHE.get(ident)
-    if hit is not None and hit[0] == key:
+    if hit is not None and hit[0] == key and len(hit[2]) == len(params) and all(r() is p for r, p in zip(hit[2], params)):
         return hit[1]
     flat = torch.cat([p.detach().reshape(-1) for p in params]).to(torch.float32).contiguous()
     if len(_FLAT_CACHE) > 16:
         _FLAT_CACHE.clear()
-    _FLAT_CACHE[ident] = (key, flat)
+    _FLAT_CACHE[ident] = (key, flat, tuple(weakref.ref(p) for p in params))
     return flat
 
 

@@ -92,3 +92,26 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src, f
+
+
+def test_flat_parameter_cache_belongs_to_the_tensor_objects(pkg):
+    """ops.flat_cached keys on (address, version); a NEW tensor that reuses a freed tensor's address with the same version counter
+    (torch's caching allocator does that between two freshly built modules) must not get the old tensor's values."""
+    import torch
+    ops = pkg.ops
+    ops._FLAT_CACHE.clear()
+    a = [torch.arange(6.0), torch.ones(3)]
+    fa = ops.flat_cached(a)
+    assert ops.flat_cached(a) is fa                                       # unchanged parameters: the cached vector
+    a[0].mul_(2.0)
+    assert torch.equal(ops.flat_cached(a), torch.cat([x.reshape(-1) for x in a]))     # in-place write: rebuilt
+    # the same storage and version counters seen through different tensor objects = what address reuse looks like to the key
+    key = tuple((p.data_ptr(), p._version) for p in a)
+    b = [torch.empty(0).set_(p.untyped_storage(), 0, p.shape) for p in a]
+    stale = torch.full((9,), -1.0)
+    import weakref
+    dead = [torch.zeros(1), torch.zeros(1)]
+    ops._FLAT_CACHE[tuple(k[0] for k in key)] = (tuple((p.data_ptr(), p._version) for p in b), stale, tuple(weakref.ref(d) for d in dead))
+    del dead
+    got = ops.flat_cached(b)
+    assert got is not stale and torch.equal(got, torch.cat([x.reshape(-1) for x in b]))
