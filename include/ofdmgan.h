@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 14
+#define OFDMGAN_ABI_VERSION 15
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -301,6 +301,13 @@ int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, con
 int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float* dparams521, const float* gparams258,
                      float adv_weight, float rec_weight, float leaky_slope, int64_t B_local, int64_t B_global,
                      float* out_dev, float* fake_out_dev, void* stream);
+/* The same step when G(noisy) already exists: fake_dev = the output of ofdmgan_gen_fwd_f32(noisy_dev, gparams258) - a training
+ * iteration computes it once for its critic updates (train.py:228-232) and train.py:285 is the same forward with the same
+ * generator, so the step skips its first forward pass.  The backward pass still recomputes the forward with its tape from
+ * gparams258: fake_dev only feeds the critic term and the L1 term.  Passing anything but G(noisy) is the caller's error. */
+int ofdmgan_gen_step_fake(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* dparams521,
+                          const float* gparams258, float adv_weight, float rec_weight, float leaky_slope, int64_t B_local,
+                          int64_t B_global, float* out_dev, void* stream);
 /* replaces torch.optim.Adam.step for one flat parameter vector (train.py:114-127,253,299): fp32 state,
  * no weight decay, no amsgrad.  g = grad_scale * g_dev[i].  All device pointers; lr/betas/eps are doubles like the
  * python floats the optimizer holds (1-beta is formed in double before narrowing, as ATen does). */

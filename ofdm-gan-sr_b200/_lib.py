@@ -96,6 +96,7 @@ _SIGNATURES = {
     "ofdmgan_gradient_penalty": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_u64, c_u64, ctypes.c_uint32, c_p, c_p, c_p, c_i64, c_f, c_p]),
     "ofdmgan_critic_step": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_u64, c_u64, ctypes.c_uint32, c_p, c_f, c_f, c_i64, c_i64, c_p, c_p]),
     "ofdmgan_gen_step": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_p, c_p, c_p]),
+    "ofdmgan_gen_step_fake": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_p, c_p]),
     "ofdmgan_adam": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_double, ctypes.c_int, c_f, c_p]),
     "ofdmgan_ffma_peak": (ctypes.c_int, [ctypes.c_int, c_p, c_p]),
@@ -114,7 +115,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 14:
+        if L.ofdmgan_abi_version() != 15:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

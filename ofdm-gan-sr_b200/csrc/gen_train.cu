@@ -9,6 +9,7 @@ namespace og {
 struct GenStepArgs {
     const float* clean;
     const float* noisy;
+    const float* fake_in;     // HAVE_FAKE: G(noisy) under the installed generator image, computed by an earlier launch
     float* fake_out;          // nullable
     int64_t B;
     int slot;
@@ -17,13 +18,15 @@ struct GenStepArgs {
     float* partials;          // [grid][GS_SLOTS]
 };
 
-// Per sample: (1) fake = G(noisy); (2) adversarial term through the critic -> d L / d fake, plus the L1 term;
+// Per sample: (1) fake = G(noisy), or - HAVE_FAKE - read from memory (a training iteration has already computed it for its critic
+// updates with the same generator: train.py:228-232 and :285 are the same forward); (2) adversarial term through the critic -> d L / d fake, plus the L1 term;
 // (3) G forward again with its tape and backward (recomputing 1.2k FMAs is cheaper than carrying 130 activations across
 // the critic pass).  Register-lean rolled-loop passes (gen_stream.cuh, critic_stream.cuh); four resident 4 KB tiles per
 // warp: noisy | clean -> upstream gradient | fake -> parked rows | scratch.
 constexpr int GENSTEP_PER_SM = 3;
 constexpr size_t GENSTEP_SMEM = (size_t)4 * OG_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * OG_THREADS * sizeof(float);
 
+template <bool HAVE_FAKE>
 __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const __grid_constant__ GenStepArgs a) {
     extern __shared__ float4 sm[];
     float* sacc = reinterpret_cast<float*>(sm + 4 * OG_THREADS * 8);
@@ -49,12 +52,15 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
         tile_fill_f32(a.clean, base, a.B, t_c, lane);
         __syncwarp();
         // (1) fake = G(noisy) -> t_y
-        {
+        if (HAVE_FAKE) {
+            tile_fill_f32(a.fake_in, base, a.B, t_y, lane);
+            __syncwarp();
+        } else {
             float a1[4][8], a2[8][4], sk[4][8];
             uint32_t z;
             gs_fwd<false>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z);
         }
-        if (a.fake_out) {
+        if (!HAVE_FAKE && a.fake_out) {
             __syncwarp();
             tile_drain_f32(a.fake_out, base, a.B, t_y, lane);
             __syncwarp();
@@ -222,13 +228,14 @@ using namespace og;
 
 extern "C" {
 
-int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float* dparams521, const float* gparams258, float adv_weight,
-                     float rec_weight, float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, float* fake_out_dev,
-                     void* stream) {
+static int gen_step_impl(const float* clean_dev, const float* noisy_dev, const float* fake_in_dev, const float* dparams521,
+                         const float* gparams258, float adv_weight, float rec_weight, float leaky_slope, int64_t B_local, int64_t B_global,
+                         float* out_dev, float* fake_out_dev, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!dparams521 || !gparams258 || !out_dev || B_local < 0 || B_global < 1 || B_global < B_local) return OFDMGAN_E_ARG;
     if (B_local > 0 && (!clean_dev || !noisy_dev || !aligned16(clean_dev) || !aligned16(noisy_dev))) return OFDMGAN_E_ARG;
     if (fake_out_dev && !aligned16(fake_out_dev)) return OFDMGAN_E_ARG;
+    if (fake_in_dev && !aligned16(fake_in_dev)) return OFDMGAN_E_ARG;
     if (B_local == 0) {
         OG_CHECK(cudaMemsetAsync(out_dev, 0, OFDMGAN_GEN_OUT * sizeof(float), s));
         return 0;
@@ -242,16 +249,36 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
     const int grid = grid_for(B_local, OG_THREADS, GENSTEP_PER_SM);
     void* partials = nullptr;
     if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
-    OG_CHECK(cudaFuncSetAttribute(k_gen_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
     GenStepArgs a{};
-    a.clean = clean_dev; a.noisy = noisy_dev; a.fake_out = fake_out_dev;
+    a.clean = clean_dev; a.noisy = noisy_dev; a.fake_in = fake_in_dev; a.fake_out = fake_out_dev;
     a.B = B_local; a.slot = slot; a.slope = leaky_slope; a.adv_w = adv_weight; a.rec_w = rec_weight;
     a.partials = (float*)partials;
-    k_gen_step<<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+    if (fake_in_dev) {
+        OG_CHECK(cudaFuncSetAttribute(k_gen_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
+        k_gen_step<true><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+    } else {
+        OG_CHECK(cudaFuncSetAttribute(k_gen_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
+        k_gen_step<false><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+    }
     OG_CHECK(cudaGetLastError());
     k_finalize_gen<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
                                           out_dev, out_dev + OFDMGAN_G_NPARAMS);
     return (int)cudaGetLastError();
+}
+
+int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float* dparams521, const float* gparams258, float adv_weight,
+                     float rec_weight, float leaky_slope, int64_t B_local, int64_t B_global, float* out_dev, float* fake_out_dev,
+                     void* stream) {
+    return gen_step_impl(clean_dev, noisy_dev, nullptr, dparams521, gparams258, adv_weight, rec_weight, leaky_slope, B_local, B_global,
+                         out_dev, fake_out_dev, stream);
+}
+
+int ofdmgan_gen_step_fake(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* dparams521,
+                          const float* gparams258, float adv_weight, float rec_weight, float leaky_slope, int64_t B_local,
+                          int64_t B_global, float* out_dev, void* stream) {
+    if (B_local > 0 && !fake_dev) return OFDMGAN_E_ARG;
+    return gen_step_impl(clean_dev, noisy_dev, fake_dev, dparams521, gparams258, adv_weight, rec_weight, leaky_slope, B_local, B_global,
+                         out_dev, nullptr, stream);
 }
 
 int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float* dy_dev, float* dx_dev, float* dparams258_dev,

@@ -527,14 +527,23 @@ def critic_train(clean, noisy, fake, dparams, m, v, step_dev, lr, beta1, beta2, 
 
 
 def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, slope=0.2, b_global=None, out=None,
-             fake_out=None):
-    """-> out[264] = grad[258] (local sum / B_global), stats[3] (g_loss, adv, rec), 3 pad."""
+             fake_out=None, fake=None):
+    """-> out[264] = grad[258] (local sum / B_global), stats[3] (g_loss, adv, rec), 3 pad.
+    fake: G(noisy) from an earlier gen_fwd_f32 with the same gparams (a training iteration has it for its critic updates): the step
+    then skips its first forward pass (ofdmgan_gen_step_fake)."""
     clean, noisy = frames(clean), frames(noisy)
     if out is None:
         out = torch.empty(GEN_OUT, dtype=torch.float32, device=clean.device)
     B = clean.shape[0]
     keepd, dp = _params(dparams, D_NPARAMS, "dparams")
     keepg, gp = _params(gparams, G_NPARAMS, "gparams")
+    if fake is not None:
+        fake = frames(fake)
+        if fake.shape[0] != B or fake_out is not None:
+            raise OfdmGanError("gen_step: fake must hold one frame per sample, and excludes fake_out")
+        check(_lib.lib().ofdmgan_gen_step_fake(dptr(clean), dptr(noisy), dptr(fake), dp, gp, adv_weight, rec_weight, slope, B,
+                                               B if b_global is None else b_global, dptr(out), stream_ptr(clean.device)))
+        return out
     check(_lib.lib().ofdmgan_gen_step(dptr(clean), dptr(noisy), dp, gp, adv_weight, rec_weight, slope, B,
                                       B if b_global is None else b_global, dptr(out), dptr(fake_out), stream_ptr(clean.device)))
     return out

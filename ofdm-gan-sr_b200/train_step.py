@@ -22,11 +22,14 @@ class CWGANGPStep:
 
     def __init__(self, gparams, dparams, lr_g=2e-4, lr_d=2e-4, betas=(0.0, 0.9), eps=1e-8, n_critic=5, gp_weight=10.0,
                  rec_weight=100.0, adv_weight=1.0, leaky_slope=0.2, seed=0, process_group=None, device=None, backend=ops, exchange="auto", graph=False,
-                 data_parallel=True):
+                 data_parallel=True, reuse_fake=True):
         """`backend` is the kernel namespace (default: libofdmgan through `ops`).  It exists so the host-side logic
         of this class (sharding, all-reduce, optimiser bookkeeping) can be exercised by the CPU test-suite with a
         stand-in; the product never passes anything but `ops`."""
         self.k = backend
+        # reuse_fake: the generator update is fed the G(noisy) of this iteration's critic updates (the generator has not changed in
+        # between, so train.py:285's forward IS that one) instead of recomputing it; False = the step computes its own forward
+        self.reuse_fake = bool(reuse_fake)
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if backend is ops else torch.device("cpu")
         self.device = torch.device(device)
@@ -204,7 +207,8 @@ class CWGANGPStep:
             self.k.critic_step(clean, noisy, self._fake, self.d, seed=self.seed, sample0=self.rank * B, gp_weight=self.gp_weight,
                                slope=self.slope, b_global=Bg, out=out, alpha_iter_dev=self._ctr[0:1])
             update(out, self.d, self.d_m, self.d_v, self.lr_d, self._ctr[0:1])
-        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
+        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout,
+                        fake=self._fake if self.reuse_fake else None)
         update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self._ctr[1:2])
 
     def _step_graph(self, clean, noisy):
@@ -271,7 +275,8 @@ class CWGANGPStep:
                             b_global=Bg, out=out)
             self.d_steps += 1
             self._reduce_and_update(out, self.d, self.d_m, self.d_v, self.lr_d, self.d_steps)
-        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout)
+        self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout,
+                        fake=self._fake if self.reuse_fake else None)
         self.g_steps += 1
         self._reduce_and_update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self.g_steps)
 

@@ -140,6 +140,32 @@ def test_generator_step_vs_oracle(ops, ref_fp32, B):
     assert_close(out[258:261], stats, TOL, f"generator stats B={B}")
 
 
+@pytest.mark.parametrize("B", [1, 33, 129, 4096, 10007])
+def test_generator_step_from_a_precomputed_fake_vs_oracle(ops, ref_fp32, B):
+    """ofdmgan_gen_step_fake: the step fed with G(noisy) from ofdmgan_gen_fwd_f32 (what a training iteration has at hand) is the
+    same step - against the oracle, and against the entry point that computes the forward itself."""
+    clean, noisy, _ = _batch(B, 300 + B)
+    dp, gp = ref_fp32["dparams"], ref_fp32["gparams"]
+    fake = ops.gen_fwd_f32(cu(noisy), gp)
+    out = host(ops.gen_step(cu(clean), cu(noisy), dp, gp, 1.0, 100.0, fake=fake))
+    grads, stats, _ = oracle.gen_step(clean, noisy, dp, gp, 1.0, 100.0)
+    assert_close(out[:258], grads, TOL, f"generator grads from fake B={B}")
+    assert_close(out[258:261], stats, TOL, f"generator stats from fake B={B}")
+    assert np.all(out[261:] == 0)
+    own = host(ops.gen_step(cu(clean), cu(noisy), dp, gp, 1.0, 100.0))
+    assert_close(out[:261], own[:261], 2e-6, f"from fake vs own forward B={B}")
+
+
+def test_generator_step_from_fake_argument_errors(ops, ref_fp32):
+    clean, noisy, _ = _batch(64, 1)
+    dp, gp = ref_fp32["dparams"], ref_fp32["gparams"]
+    fake = ops.gen_fwd_f32(cu(noisy), gp)
+    with pytest.raises(Exception):
+        ops.gen_step(cu(clean), cu(noisy), dp, gp, fake=fake[:32])
+    with pytest.raises(Exception):
+        ops.gen_step(cu(clean), cu(noisy), dp, gp, fake=fake, fake_out=torch.empty_like(fake))
+
+
 @pytest.mark.parametrize("B", [1, 95, 4097])
 def test_backward_entry_points_vs_oracle(ops, ref_fp32, B):
     clean, noisy, alpha = _batch(B, 200 + B)

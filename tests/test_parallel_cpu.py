@@ -50,7 +50,8 @@ class OracleBackend:
         return out
 
     @staticmethod
-    def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, slope=0.2, b_global=None, out=None, fake_out=None):
+    def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, slope=0.2, b_global=None, out=None, fake_out=None,
+                 fake=None):
         B = clean.shape[0]
         grads, stats, _ = oracle.gen_step(clean.numpy(), noisy.numpy(), dparams.numpy(), gparams.numpy(), adv_weight, rec_weight, slope)
         w = B / float(b_global or B)

@@ -14,7 +14,7 @@ from ofdm_gan_sr_b200.train_step import CWGANGPStep  # noqa: E402
 gp, dp = bench.seed_params()
 cfg = pkg.ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
 clean, noisy, _ = pkg.ops.chan_sim(cfg, 65536, seed=0)
-tr = CWGANGPStep(gp, dp, graph=True)
+tr = CWGANGPStep(gp, dp, graph=True, reuse_fake=os.environ.get('OWN_FWD') is None)
 for _ in range(20):
     tr.step(clean, noisy)
 ms = []
