@@ -44,7 +44,8 @@ __device__ __forceinline__ void unpark48(const float4* wsm, int lane, float (&a)
 
 // ---- forward.  x rows come from t_x; y rows are written to t_y; t_s is a scratch slot (free on return).
 // TAPE: returns a1 = lrelu(enc1), a2 = lrelu(bottleneck), sk = skip sum, z3pos (bit oc*8+q: dec1 pre-activation > 0).
-template <bool TAPE>
+// WRITE_Y = false: the output layer is skipped (the caller already holds what it needs of y; t_y is left alone).
+template <bool TAPE, bool WRITE_Y = true>
 __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4* t_x, float4* t_y, float4* t_s, int lane,
                                        float (&a1)[4][8], float (&a2)[8][4], float (&sk)[4][8], uint32_t& z3pos) {
     // enc1: Conv1d(2->4, k3, s2, p1) + LeakyReLU, one input row per iteration
@@ -131,7 +132,7 @@ __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4
         for (int q = 0; q < 8; ++q) sk[oc][q] += a1[oc][q];                      // additive skip (models/generator.py:199)
     // upsample x2 + out_conv Conv1d(4->2, k3, s1, p1), folded; tanh; one output row per iteration, written to t_y
 #pragma unroll 1
-    for (int oc = 0; oc < 2; ++oc) {
+    for (int oc = 0; oc < (WRITE_Y ? 2 : 0); ++oc) {
         const float* F = W + GI_OUT_F + oc * 16;
         float y[16];
 #pragma unroll
@@ -154,23 +155,33 @@ __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4
 // ---- backward.  On entry: t_x = input rows, t_y = y rows, t_dy = upstream gradient rows, (a1, a2, sk, z3pos) = tape.
 // t_y and t_dy are used as parking space once their contents are consumed; t_p is a further free slot.
 // Accumulates the 10 parameter-gradient groups into acc.  NEED_DX: the input gradient rows are left in t_dy.
-template <bool NEED_DX>
+// THREE_SLOTS (the fused generator step): on entry t_y already holds dz4 = upstream gradient * tanh' (the caller had y in registers
+// when it formed the upstream gradient), and t_dy IS the slot of the input rows: it is used as parking space like any other, and the
+// input rows are fetched again from x_glob (frames base .. of B) for the last gradient group.  One 4 KB tile per warp less.
+template <bool NEED_DX, bool THREE_SLOTS = false>
 __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4* t_x, float4* t_y, float4* t_dy, float4* t_p, int lane,
-                                       float (&a1)[4][8], const float (&a2)[8][4], const float (&sk)[4][8], uint32_t z3pos, SAcc& acc) {
+                                       float (&a1)[4][8], const float (&a2)[8][4], const float (&sk)[4][8], uint32_t z3pos, SAcc& acc,
+                                       const float* x_glob = nullptr, int64_t base = 0, int64_t B = 0) {
     float bias_g[14];                                            // bn.b[8], dec.b[4], out.b[2] -> group 9
     park48(t_p, lane, a1);                                       // a1 is next needed at the bottleneck weight gradient
     // ---- tanh' and the out_conv weight gradient
     float dz4[2][16];
 #pragma unroll
     for (int oc = 0; oc < 2; ++oc) {
-        float y[16];
-        row_read(t_dy, lane, oc, dz4[oc]);
-        row_read(t_y, lane, oc, y);
         float s = 0.f;
+        if (THREE_SLOTS) {
+            row_read(t_y, lane, oc, dz4[oc]);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            dz4[oc][q] *= fmaf(-y[q], y[q], 1.0f);
-            s += dz4[oc][q];
+            for (int q = 0; q < 16; ++q) s += dz4[oc][q];
+        } else {
+            float y[16];
+            row_read(t_dy, lane, oc, dz4[oc]);
+            row_read(t_y, lane, oc, y);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                dz4[oc][q] *= fmaf(-y[q], y[q], 1.0f);
+                s += dz4[oc][q];
+            }
         }
         bias_g[12 + oc] = s;
     }
@@ -323,6 +334,11 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
             for (int i = 0; i < 8; ++i) dz1[ic][i] = (dz1[ic][i] + dsk[ic][i]) * (a1[ic][i] > 0.f ? 1.0f : slope);
     }
     // ---- enc1 weight + bias gradient (group 8)
+    if (THREE_SLOTS) {                                           // t_dy's parked rows are consumed: bring the input rows back
+        __syncwarp();
+        tile_fill_f32(x_glob, base, B, t_dy, lane);
+        __syncwarp();
+    }
     {
         float x[2][16], v[32];
         row_read(t_x, lane, 0, x[0]);

@@ -19,22 +19,23 @@ struct GenStepArgs {
 };
 
 // Per sample: (1) fake = G(noisy), or - HAVE_FAKE - read from memory (a training iteration has already computed it for its critic
-// updates with the same generator: train.py:228-232 and :285 are the same forward); (2) adversarial term through the critic -> d L / d fake, plus the L1 term;
-// (3) G forward again with its tape and backward (recomputing 1.2k FMAs is cheaper than carrying 130 activations across
-// the critic pass).  Register-lean rolled-loop passes (gen_stream.cuh, critic_stream.cuh); four resident 4 KB tiles per
-// warp: noisy | clean -> upstream gradient | fake -> parked rows | scratch.
-constexpr int GENSTEP_PER_SM = 3;
-constexpr size_t GENSTEP_SMEM = (size_t)4 * OG_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * OG_THREADS * sizeof(float);
+// updates with the same generator: train.py:228-232 and :285 are the same forward); (2) adversarial term through the critic ->
+// d L / d fake, plus the L1 term, times tanh' while y is in registers; (3) G forward again with its tape and backward (recomputing
+// 1.2k FMAs is cheaper than carrying 130 activations across the critic pass).  Register-lean rolled-loop passes (gen_stream.cuh,
+// critic_stream.cuh).  THREE resident 4 KB tiles per warp - noisy (later parking space; refetched for the last gradient group) |
+// fake -> dz4 rows -> parked rows | clean -> scratch / parked rows - and <= 128 registers: 4 CTAs per SM, so the 512 tiles of a
+// 65,536-sample shard are ONE round (592 slots) instead of 1.15 rounds of 444.
+constexpr int GENSTEP_PER_SM = 4;
+constexpr size_t GENSTEP_SMEM = (size_t)3 * OG_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * OG_THREADS * sizeof(float);
 
 template <bool HAVE_FAKE>
 __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const __grid_constant__ GenStepArgs a) {
     extern __shared__ float4 sm[];
-    float* sacc = reinterpret_cast<float*>(sm + 4 * OG_THREADS * 8);
+    float* sacc = reinterpret_cast<float*>(sm + 3 * OG_THREADS * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* t_x = sm + warp * TILE4;
-    float4* t_c = sm + (NWARP + warp) * TILE4;
-    float4* t_y = sm + (2 * NWARP + warp) * TILE4;
-    float4* t_p = sm + (3 * NWARP + warp) * TILE4;
+    float4* t_y = sm + (NWARP + warp) * TILE4;
+    float4* t_p = sm + (2 * NWARP + warp) * TILE4;
     const float* WG = c_g;
     const float* WD = c_d;
     SAcc acc{sacc + threadIdx.x, OG_THREADS};
@@ -49,23 +50,24 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
         const bool live = base + lane < a.B;
         __syncwarp();
         tile_fill_f32(a.noisy, base, a.B, t_x, lane);
-        tile_fill_f32(a.clean, base, a.B, t_c, lane);
-        __syncwarp();
         // (1) fake = G(noisy) -> t_y
         if (HAVE_FAKE) {
             tile_fill_f32(a.fake_in, base, a.B, t_y, lane);
-            __syncwarp();
         } else {
+            __syncwarp();
             float a1[4][8], a2[8][4], sk[4][8];
             uint32_t z;
             gs_fwd<false>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z);
         }
+        __syncwarp();
         if (!HAVE_FAKE && a.fake_out) {
-            __syncwarp();
             tile_drain_f32(a.fake_out, base, a.B, t_y, lane);
             __syncwarp();
         }
-        // (2) critic on (fake, noisy): d(-adv_w * D)/d fake, + rec_w * sign(fake - clean)/32 -> upstream gradient rows in t_c
+        tile_fill_f32(a.clean, base, a.B, t_p, lane);
+        __syncwarp();
+        // (2) critic on (fake, noisy): d(-adv_w * D)/d fake, + rec_w * sign(fake - clean)/32 = upstream gradient; times tanh'(z) =
+        // 1 - y^2 while the y row is in registers -> dz4 rows, which replace the y rows in t_y
         {
             f32x2 dz1[4][8];
             {
@@ -79,26 +81,27 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
                 float row[16], y[16], c[16];
                 cs_conv1T_row(WD, dz1, ic, row);
                 row_read(t_y, lane, ic, y);
-                row_read(t_c, lane, ic, c);
+                row_read(t_p, lane, ic, c);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float e = y[i] - c[i];
                     if (live) {
                         s_l1 += fabsf(e);
                         row[i] += e > 0.f ? rec_g : (e < 0.f ? -rec_g : 0.f);       // l1_loss backward: sign(e)
+                        row[i] *= fmaf(-y[i], y[i], 1.0f);
                     } else {
                         row[i] = 0.f;
                     }
                 }
-                row_write(t_c, lane, ic, row);
+                row_write(t_y, lane, ic, row);
             }
         }
-        // (3) forward with tape, backward
+        // (3) forward with tape (t_p is scratch again), backward
         {
             float a1[4][8], a2[8][4], sk[4][8];
             uint32_t z3pos;
-            gs_fwd<true>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z3pos);
-            gs_bwd<false>(WG, a.slope, t_x, t_y, t_c, t_p, lane, a1, a2, sk, z3pos, acc);
+            gs_fwd<true, false>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z3pos);
+            gs_bwd<false, true>(WG, a.slope, t_x, t_y, t_x, t_p, lane, a1, a2, sk, z3pos, acc, a.noisy, base, a.B);
         }
     }
     {
@@ -158,8 +161,11 @@ __global__ void __launch_bounds__(1024) k_finalize_gen(const float* __restrict__
 
 // ------------------------------------------------------------------------------------------------ generator backward (API)
 // what autograd needs for MiniGenerator.forward: dparams = sum_b backward(dy_b) and (optionally) dx
+// (four tiles per warp - x | dy | y | scratch - and up to 168 registers: 3 CTAs per SM)
+constexpr int GENBWD_PER_SM = 3;
+constexpr size_t GENBWD_SMEM = (size_t)4 * OG_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * OG_THREADS * sizeof(float);
 template <bool NEED_DX>
-__global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_bwd(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(OG_THREADS, GENBWD_PER_SM) k_gen_bwd(const float* __restrict__ x, const float* __restrict__ dy,
                                                                         float* __restrict__ dx, float* __restrict__ partials, int64_t B,
                                                                         float slope) {
     extern __shared__ float4 sm[];
@@ -296,15 +302,15 @@ int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float
     if ((rc = guard.rc)) return rc;
     slot = 0;
     if ((rc = upload_g(gparams258, slot, s))) return rc;
-    const int grid = grid_for(B, OG_THREADS, GENSTEP_PER_SM);
+    const int grid = grid_for(B, OG_THREADS, GENBWD_PER_SM);
     void* partials = nullptr;
     if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
     if (dx_dev) {
-        OG_CHECK(cudaFuncSetAttribute(k_gen_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
-        k_gen_bwd<true><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(x_dev, dy_dev, dx_dev, (float*)partials, B, leaky_slope);
+        OG_CHECK(cudaFuncSetAttribute(k_gen_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENBWD_SMEM));
+        k_gen_bwd<true><<<grid, OG_THREADS, GENBWD_SMEM, s>>>(x_dev, dy_dev, dx_dev, (float*)partials, B, leaky_slope);
     } else {
-        OG_CHECK(cudaFuncSetAttribute(k_gen_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
-        k_gen_bwd<false><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(x_dev, dy_dev, nullptr, (float*)partials, B, leaky_slope);
+        OG_CHECK(cudaFuncSetAttribute(k_gen_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENBWD_SMEM));
+        k_gen_bwd<false><<<grid, OG_THREADS, GENBWD_SMEM, s>>>(x_dev, dy_dev, nullptr, (float*)partials, B, leaky_slope);
     }
     OG_CHECK(cudaGetLastError());
     k_finalize_gen<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0, 0.0, 0.0, dparams258_dev, nullptr);
