@@ -34,23 +34,31 @@ __device__ __forceinline__ void cta_store_partials(const GradAcc<NG>& acc, float
 __device__ __forceinline__ void reduce_group_rows(const float* __restrict__ partials, int nblocks, int slots, int grp, double* red /*[32][32]*/,
                                                   double* total /*[32]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // four independent chains per warp keep four row loads in flight (one chain was a ~19-deep load-add dependency per block)
+    // Every row load of a warp is issued before the first add (up to 20 in flight: a full B200 grid is 592 rows = 18.5 per warp, and
+    // the tail kernels sit on the critical path of a training iteration); four chains, fixed order.
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const float* col = partials + grp * 32 + lane;
-    int b = warp;
-    for (; b + 96 < nblocks; b += 128) {
-        const float v0 = col[(size_t)b * slots], v1 = col[(size_t)(b + 32) * slots], v2 = col[(size_t)(b + 64) * slots],
-                    v3 = col[(size_t)(b + 96) * slots];
-        s0 += (double)v0; s1 += (double)v1; s2 += (double)v2; s3 += (double)v3;
+    for (int b0 = warp; b0 < nblocks; b0 += 32 * 20) {
+        float v[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+            const int b = b0 + 32 * k;
+            v[k] = b < nblocks ? __ldcg(col + (size_t)b * slots) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 20; k += 4) {
+            s0 += (double)v[k]; s1 += (double)v[k + 1]; s2 += (double)v[k + 2]; s3 += (double)v[k + 3];
+        }
     }
-    for (; b < nblocks; b += 32) s0 += (double)col[(size_t)b * slots];
     red[warp * 32 + lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (warp == 0) {
-        double a = 0.0;
-#pragma unroll 4
-        for (int w = 0; w < 32; ++w) a += red[w * 32 + lane];
-        total[lane] = a;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 32; w += 4) {
+            a0 += red[w * 32 + lane]; a1 += red[(w + 1) * 32 + lane]; a2 += red[(w + 2) * 32 + lane]; a3 += red[(w + 3) * 32 + lane];
+        }
+        total[lane] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
 }
