@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
     float s_d = 0.f, s_l1 = 0.f;
     const float rec_g = a.rec_w * 0.03125f;                      // rec_w / 32: l1_loss is a mean over B*32 elements
     const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
+#pragma unroll 1
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t base = t * OG_THREADS + warp * 32;
         if (base >= a.B) continue;
