@@ -32,6 +32,7 @@ TRAIN_FRAMES_PER_GPU = 65536       # BASELINE config 3
 FLOP_SIM = 900                     # nominal channel-sim FLOP per frame (Philox integer work not credited)
 FLOP_GEN = 3456                    # 2 x 1728 MAC, models/generator.py:227-233
 FLOP_TRAIN = 311424                # 5 x 57,504 + 23,904 per sample, SURVEY.md 8(d)
+FLOP_TRAIN_EXECUTED = FLOP_TRAIN - 5 * FLOP_GEN   # the step runs ONE G(noisy) forward for its five critic updates and its generator update
 Q_BYTES = 128                      # int16 frame in + out
 WORKLOAD = dict(nonlinear=True, pa_saturation=0.8, normalize=1, snr_mode=1, snr_lo=0.0, snr_step=5.0, n_snr=7,
                 frames_per_snr=1 << 10)
@@ -658,6 +659,10 @@ def main():
         e2e_train = Bt * world * Ke / max_over_ranks(time.perf_counter() - t0)
         also["train"] = {"samples_per_s": Bt * world / (ms * 1e-3), "ms_per_step": ms, "frames_per_gpu": Bt, "n_critic": 5,
                          "fp32_tflops_per_gpu": tflops, "fp32_frac_of_ffma_peak": tflops / ffma,
+                         "fp32_frac_of_ffma_peak_executed_work": tflops / ffma * FLOP_TRAIN_EXECUTED / FLOP_TRAIN,
+                         "flop_per_sample": {"credited": FLOP_TRAIN, "executed": FLOP_TRAIN_EXECUTED,
+                                             "note": "credited = SURVEY.md 8(d), the reference's own iteration (a generator forward per critic update); executed = "
+                                                     "what this step computes: the generator is unchanged during the critic updates, so its forward runs once"},
                          "e2e_samples_per_s": e2e_train, "e2e_steps": Ke, "e2e_h2d_bytes_per_step": 2 * Bt * 128, "e2e_d2h_bytes_per_step": 28 * 4,
                          "launches_per_step": trainer.launches_per_step(), "d_loss": st["d_loss"], "g_loss": st["g_loss"],
                          "exchange": "none (1 GPU)" if world == 1 else ("peer-memory all-reduce fused with Adam" if trainer.comm is not None else "nccl"),
@@ -702,7 +707,7 @@ def main():
                    "fast_rng_workload_frames_per_s": (also.get("fused_philox7") or {}).get("frames_per_s"),
                    "fast_rng_workload_frac": (also.get("fused_philox7") or {}).get("fp32_frac_of_ffma_peak"),
                    "train_ms_per_step": tr.get("ms_per_step"),
-                   "train_samples_per_s": tr.get("samples_per_s"), "train_frac_of_ffma_peak": tr.get("fp32_frac_of_ffma_peak"),
+                   "train_samples_per_s": tr.get("samples_per_s"), "train_frac_of_ffma_peak": tr.get("fp32_frac_of_ffma_peak"), "train_frac_of_ffma_peak_executed_work": tr.get("fp32_frac_of_ffma_peak_executed_work"),
                    "train_ms_per_step_nccl": tr.get("ms_per_step_with_nccl_exchange"), "train_exchange_breakdown": tr.get("exchange_breakdown"),
                    "multi_gpu_parity": parity["status"] if parity else ("n/a (1 GPU)" if world == 1 else None), "n_gpus": world}
         line = {"metric": "OFDM frames/s: fused channel sim + G inference", "value": value, "unit": "frames/s", "n_gpus": world,
