@@ -198,6 +198,7 @@ __device__ __forceinline__ uint64_t cs_conv2_pass(const float* W, float slope, f
             upk2(s, pl_lo, pl_hi);                              // d wd[2*o2+h]
         } else {
             uint32_t blo = 0, bhi = 0;
+            f32x2 pl = pk2(0.f, 0.f);                           // pooled LeakyReLU of the channel pair: sum_p mk[p] * z[p], packed
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 float lo, hi;
@@ -206,9 +207,9 @@ __device__ __forceinline__ uint64_t cs_conv2_pass(const float* W, float slope, f
                 blo |= (plo ? 1u : 0u) << p;
                 bhi |= (phi ? 1u : 0u) << p;
                 mk[p] = pk2(plo ? 1.0f : slope, phi ? 1.0f : slope);
-                pl_lo += plo ? lo : slope * lo;
-                pl_hi += phi ? hi : slope * hi;
+                pl = fma2(mk[p], z[p], pl);
             }
+            upk2(pl, pl_lo, pl_hi);
             m2 |= (uint64_t)(blo | (bhi << 4)) << (o2 * 8);
             score = fmaf(wd.x, pl_lo, fmaf(wd.y, pl_hi, score));
         }
@@ -268,9 +269,10 @@ __device__ __forceinline__ void cs_bwd_to_z1(const float* W, float slope, float 
         const float* w = W + DI2_C2T + oc * 24;                 // pair (oc, i2, k) at (i2*3 + k)*2
         const float gw = g * W[DP_FC_W + oc];
         const uint32_t nib = (uint32_t)(m2 >> (oc * 4)) & 15u;
+        const float gws = gw * slope;
         float d[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) d[p] = gw * (((nib >> p) & 1u) ? 1.0f : slope);
+        for (int p = 0; p < 4; ++p) d[p] = ((nib >> p) & 1u) ? gw : gws;
 #pragma unroll
         for (int i2 = 0; i2 < 4; ++i2)
 #pragma unroll
@@ -418,14 +420,14 @@ __device__ __forceinline__ float cs_gp_pass(const float* W, float slope, float s
     }
     // u1 = m1 . conv1x(h) (no bias): conv1x(v) from the parked rows, then coef and the masks in one packed multiply
     f32x2 u1[4][8];
+    const float coef_s = coef * slope;
     cs_conv1_fwd<false>(W, slope, t_xh, t_xh, 2, lane, u1);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const uint32_t half = (uint32_t)(m1 >> (c * 16)) & 65535u;
 #pragma unroll
         for (int p = 0; p < 8; ++p)
-            u1[c][p] = fma2(u1[c][p], pk2(coef * (((half >> p) & 1u) ? 1.0f : slope), coef * (((half >> (8 + p)) & 1u) ? 1.0f : slope)),
-                            pk2(0.f, 0.f));
+            u1[c][p] = fma2(u1[c][p], pk2(((half >> p) & 1u) ? coef : coef_s, ((half >> (8 + p)) & 1u) ? coef : coef_s), pk2(0.f, 0.f));
     }
     // dW2 += dz2 (x) u1 ; d wd[oc] = sum_p m2 * conv2(u1) ; no bias gradient
     float unused;
