@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OFDMGAN_ABI_VERSION 15
+#define OFDMGAN_ABI_VERSION 16
 #define OFDMGAN_FRAME_LEN 16
 #define OFDMGAN_FRAME_ELEMS 32            /* 2 x 16 */
 #define OFDMGAN_G_NPARAMS 258             /* models/generator.py:102 */
@@ -308,6 +308,19 @@ int ofdmgan_gen_step(const float* clean_dev, const float* noisy_dev, const float
 int ofdmgan_gen_step_fake(const float* clean_dev, const float* noisy_dev, const float* fake_dev, const float* dparams521,
                           const float* gparams258, float adv_weight, float rec_weight, float leaky_slope, int64_t B_local,
                           int64_t B_global, float* out_dev, void* stream);
+/* One whole generator update of a training iteration in two launches (the generator-side twin of ofdmgan_critic_train_ctr,
+ * train.py:282-299): ofdmgan_gen_step_fake's loss + backward, then ONE tail launch = fixed-order reduction of the gradient, sum
+ * over the ranks of `comm` through peer memory (comm may be NULL), Adam in place on gparams258_dev / m_dev / v_dev with the step
+ * count in *step_dev.  out_dev: OFDMGAN_GEN_OUT floats as ofdmgan_gen_step (global sums when comm is given).
+ * d_image_staged / g_image_staged != 0: the caller states that this device's staging buffer already holds the weight image of
+ * dparams521_dev (true right after ofdmgan_critic_train_ctr on them) / of gparams258_dev (true right after ofdmgan_gen_fwd_f32 with
+ * that device pointer) and nothing else has run on the library in between: the image is copied instead of rebuilt.  Pass 0
+ * whenever in doubt. */
+int ofdmgan_gen_train_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, int32_t* step_dev,
+                          float* gparams258_dev, float* m_dev, float* v_dev, double lr, double beta1, double beta2, double eps,
+                          const float* dparams521_dev, float adv_weight, float rec_weight, float leaky_slope, int64_t B_local,
+                          int64_t B_global, float* out_dev, int d_image_staged, int g_image_staged, ofdmgan_comm* comm,
+                          void* stream);
 /* replaces torch.optim.Adam.step for one flat parameter vector (train.py:114-127,253,299): fp32 state,
  * no weight decay, no amsgrad.  g = grad_scale * g_dev[i].  All device pointers; lr/betas/eps are doubles like the
  * python floats the optimizer holds (1-beta is formed in double before narrowing, as ATen does). */

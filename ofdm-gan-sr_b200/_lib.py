@@ -97,6 +97,8 @@ _SIGNATURES = {
     "ofdmgan_critic_step": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_u64, c_u64, ctypes.c_uint32, c_p, c_f, c_f, c_i64, c_i64, c_p, c_p]),
     "ofdmgan_gen_step": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_p, c_p, c_p]),
     "ofdmgan_gen_step_fake": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_i64, c_i64, c_p, c_p]),
+    "ofdmgan_gen_train_ctr": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, c_p, c_f, c_f, c_f, c_i64, c_i64, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p]),
     "ofdmgan_adam": (ctypes.c_int, [c_p, c_p, c_p, c_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_double, ctypes.c_int, c_f, c_p]),
     "ofdmgan_ffma_peak": (ctypes.c_int, [ctypes.c_int, c_p, c_p]),
@@ -115,7 +117,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.ofdmgan_abi_version() != 15:
+        if L.ofdmgan_abi_version() != 16:
             raise OfdmGanError("libofdmgan ABI version mismatch")
         _lib = L
     return _lib

@@ -2,6 +2,7 @@
 // MiniGenerator backward, and fused Adam.   ofdmgan_gen_step / ofdmgan_gen_bwd_f32 / ofdmgan_adam
 #include "train_common.cuh"
 #include "gen_stream.cuh"
+#include "peer_comm.cuh"
 
 namespace og {
 
@@ -125,39 +126,87 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
 // upsample+conv layers accumulate gradients of their FOLDED taps {F0=w0, F1=w1+w2, F2=w0+w1, F3=w2}; the raw taps follow
 // linearly: dw0 = dF0+dF2, dw1 = dF1+dF2, dw2 = dF1+dF3 (all four slots of a pair sit in the same group).
 // stats (nullable): g_loss, adv_loss, rec_loss (train.py:301-305) + 3 pad, written by the block of group 9.
+// slot j of group grp -> (parameter index, gradient sum) from the group's 32 totals; index -1 = no parameter in this slot
+__device__ __forceinline__ int gs_param_of(int grp, int j, const double* total, double& v) {
+    int i = -1;
+    v = total[j];
+    if (grp <= 4) {                                               // folded layers: thread (pair, t<3) emits raw tap k = t
+        const int pair = j >> 2, k = j & 3;
+        const double* F = total + pair * 4;
+        if (k < 3) {
+            v = k == 0 ? F[0] + F[2] : (k == 1 ? F[1] + F[2] : F[1] + F[3]);
+            i = grp == 0 ? GP_OUT_W + pair * 3 + k : GP_DEC_W + ((grp - 1) * 8 + pair) * 3 + k;
+        }
+    } else if (grp <= 7) {
+        i = GP_BN_W + (grp - 5) * 32 + j;
+    } else if (grp == 8) {
+        i = j < 24 ? GP_ENC_W + j : (j < 28 ? GP_ENC_B + (j - 24) : -1);
+    } else {
+        i = j < 8 ? GP_BN_B + j : (j < 12 ? GP_DEC_B + (j - 8) : (j < 14 ? GP_OUT_B + (j - 12) : -1));
+    }
+    return i;
+}
+__device__ __forceinline__ void gs_write_stats(const double* total, double inv_b, double adv_w, double rec_w, float* stats) {
+    const double adv = -total[GS_S0 - 288] * inv_b, rec = total[GS_S0 + 1 - 288] * inv_b * 0.03125;
+    stats[0] = (float)(adv_w * adv + rec_w * rec);
+    stats[1] = (float)adv;
+    stats[2] = (float)rec;
+    stats[3] = 0.f;
+    stats[4] = 0.f;
+    stats[5] = 0.f;
+}
+
 __global__ void __launch_bounds__(1024) k_finalize_gen(const float* __restrict__ partials, int nblocks, double inv_b, double adv_w,
                                                        double rec_w, float* __restrict__ grads, float* __restrict__ stats) {
     __shared__ double red[32 * 32], total[32];
     const int grp = blockIdx.x, j = threadIdx.x;
     reduce_group_rows(partials, nblocks, GS_SLOTS, grp, red, total);
     if (grads && j < 32) {
-        int i = -1;
-        double v = total[j];
-        if (grp <= 4) {                                           // folded layers: thread (pair, t<3) emits raw tap k = t
-            const int pair = j >> 2, k = j & 3;
-            const double* F = total + pair * 4;
-            if (k < 3) {
-                v = k == 0 ? F[0] + F[2] : (k == 1 ? F[1] + F[2] : F[1] + F[3]);
-                i = grp == 0 ? GP_OUT_W + pair * 3 + k : GP_DEC_W + ((grp - 1) * 8 + pair) * 3 + k;
-            }
-        } else if (grp <= 7) {
-            i = GP_BN_W + (grp - 5) * 32 + j;
-        } else if (grp == 8) {
-            i = j < 24 ? GP_ENC_W + j : (j < 28 ? GP_ENC_B + (j - 24) : -1);
-        } else {
-            i = j < 8 ? GP_BN_B + j : (j < 12 ? GP_DEC_B + (j - 8) : (j < 14 ? GP_OUT_B + (j - 12) : -1));
-        }
+        double v;
+        const int i = gs_param_of(grp, j, total, v);
         if (i >= 0) grads[i] = (float)(v * inv_b);
     }
-    if (grp == 9 && stats && j == 0) {
-        const double adv = -total[GS_S0 - 288] * inv_b, rec = total[GS_S0 + 1 - 288] * inv_b * 0.03125;
-        stats[0] = (float)(adv_w * adv + rec_w * rec);
-        stats[1] = (float)adv;
-        stats[2] = (float)rec;
-        stats[3] = 0.f;
-        stats[4] = 0.f;
-        stats[5] = 0.f;
+    if (grp == 9 && stats && j == 0) gs_write_stats(total, inv_b, adv_w, rec_w, stats);
+}
+
+// Tail of a generator update in ONE launch (as k_critic_tail): the fixed-order reduction of k_finalize_gen and - in the block that
+// finishes last - the sum over the ranks through peer memory, Adam on the 258 parameters with the step count in device memory.
+__global__ void __launch_bounds__(1024) k_gen_tail(const float* __restrict__ partials, int nblocks, double inv_b, double adv_w, double rec_w,
+                                                   float* __restrict__ out, float* __restrict__ p, float* __restrict__ m,
+                                                   float* __restrict__ v, double lr, double b1, double b2, double eps,
+                                                   int32_t* __restrict__ step_dev, unsigned int* __restrict__ arrivals, PeerPtrs peers,
+                                                   int rank, int world) {
+    __shared__ double red[32 * 32], total[32];
+    __shared__ unsigned int ticket;
+    const int grp = blockIdx.x, j = threadIdx.x;
+    reduce_group_rows(partials, nblocks, GS_SLOTS, grp, red, total);
+    if (j < 32) {
+        double g;
+        const int i = gs_param_of(grp, j, total, g);
+        if (i >= 0) out[i] = (float)(g * inv_b);
     }
+    if (grp == 9 && j == 0) gs_write_stats(total, inv_b, adv_w, rec_w, out + OFDMGAN_G_NPARAMS);
+    __threadfence();                                             // this block's gradients are visible before it takes its ticket
+    __syncthreads();
+    if (j == 0) ticket = atomicAdd(arrivals, 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+    if (j == 0) *arrivals = 0u;
+    if (world > 1) {
+        PeerBlock* mine = peers.p[rank];
+        const unsigned int seq = mine->seq + 1u;
+        peer_allreduce_block(peers, rank, world, seq, out, OFDMGAN_GEN_OUT);     // traps if a peer never arrives
+        if (j == 0) mine->seq = seq;
+    }
+    const int t = *step_dev + 1;
+    const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);
+    if (j < OFDMGAN_G_NPARAMS) {
+        float pi = p[j], mi = m[j], vi = v[j];
+        adam_one(pi, mi, vi, __ldcg(out + j), c);
+        p[j] = pi; m[j] = mi; v[j] = vi;
+    }
+    __syncthreads();
+    if (j == 0) *step_dev = t;
 }
 
 // ------------------------------------------------------------------------------------------------ generator backward (API)
@@ -286,6 +335,50 @@ int ofdmgan_gen_step_fake(const float* clean_dev, const float* noisy_dev, const 
     if (B_local > 0 && !fake_dev) return OFDMGAN_E_ARG;
     return gen_step_impl(clean_dev, noisy_dev, fake_dev, dparams521, gparams258, adv_weight, rec_weight, leaky_slope, B_local, B_global,
                          out_dev, nullptr, stream);
+}
+
+int ofdmgan_gen_train_ctr(const float* clean_dev, const float* noisy_dev, const float* fake_dev, int32_t* step_dev, float* gparams258_dev,
+                          float* m_dev, float* v_dev, double lr, double beta1, double beta2, double eps, const float* dparams521_dev,
+                          float adv_weight, float rec_weight, float leaky_slope, int64_t B, int64_t B_global, float* out_dev,
+                          int d_image_staged, int g_image_staged, ofdmgan_comm* comm, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!clean_dev || !noisy_dev || !fake_dev || !step_dev || !gparams258_dev || !m_dev || !v_dev || !dparams521_dev || !out_dev || B < 1 ||
+        B_global < B)
+        return OFDMGAN_E_ARG;
+    if (!aligned16(clean_dev) || !aligned16(noisy_dev) || !aligned16(fake_dev)) return OFDMGAN_E_ARG;
+    PeerPtrs peers{};
+    int rank = 0, world = 1;
+    if (comm && !comm_view(comm, &peers, &rank, &world)) return OFDMGAN_E_ARG;
+    int rc;
+    CallGuard guard(s);
+    if ((rc = guard.rc)) return rc;
+    const int slot = 0;
+    // *_staged: the staging buffer of this device already holds the image of these parameters (D: the tail of
+    // ofdmgan_critic_train_ctr left it; G: ofdmgan_gen_fwd_f32 with the same device parameters built it) - copy it, skip the rebuild
+    if ((rc = d_image_staged ? commit_d_image(slot, s) : upload_d(dparams521_dev, slot, s))) return rc;
+    if ((rc = g_image_staged ? commit_g_image(slot, s) : upload_g(gparams258_dev, slot, s))) return rc;
+    const int grid = grid_for(B, OG_THREADS, GENSTEP_PER_SM);
+    void *partials = nullptr, *arrivals = nullptr;
+    if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
+    if ((rc = scratch_for_slot(slot, 256, 9, &arrivals))) return rc;
+    static bool zeroed[64] = {false};
+    int dev = 0;
+    OG_CHECK(cudaGetDevice(&dev));
+    if (!zeroed[dev]) {                                          // the tail leaves the counter at zero; only the very first use needs this
+        OG_CHECK(cudaMemsetAsync(arrivals, 0, 256, s));
+        zeroed[dev] = true;
+    }
+    GenStepArgs a{};
+    a.clean = clean_dev; a.noisy = noisy_dev; a.fake_in = fake_dev; a.fake_out = nullptr;
+    a.B = B; a.slot = slot; a.slope = leaky_slope; a.adv_w = adv_weight; a.rec_w = rec_weight;
+    a.partials = (float*)partials;
+    OG_CHECK(cudaFuncSetAttribute(k_gen_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
+    k_gen_step<true><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+    OG_CHECK(cudaGetLastError());
+    k_gen_tail<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight, out_dev,
+                                      gparams258_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, peers, rank,
+                                      world);
+    return (int)cudaGetLastError();
 }
 
 int ofdmgan_gen_bwd_f32(const float* x_dev, const float* gparams258, const float* dy_dev, float* dx_dev, float* dparams258_dev,

@@ -150,6 +150,15 @@ static int upload_g(const float* params258, int slot, cudaStream_t s) {
     return 0;
 }
 
+// copy the G image that an earlier upload_g on this device left in the staging buffer into THIS translation unit's constant bank
+static int commit_g_image(int slot, cudaStream_t s) {
+    void* img = nullptr;
+    int rc = scratch_for_slot(slot, OG_G_IMG * sizeof(float), 1, &img);
+    if (rc) return rc;
+    OG_CHECK(cudaMemcpyToSymbolAsync(c_g, img, OG_G_IMG * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 // the staging buffer of the D image (device), for kernels that refresh the image themselves
 static int d_image_staging(int slot, float** img) {
     void* p = nullptr;

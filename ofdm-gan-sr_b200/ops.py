@@ -549,6 +549,21 @@ def gen_step(clean, noisy, dparams, gparams, adv_weight=1.0, rec_weight=100.0, s
     return out
 
 
+def gen_train(clean, noisy, fake, gparams, m, v, step_dev, lr, beta1, beta2, eps, dparams, adv_weight=1.0, rec_weight=100.0, slope=0.2,
+              out=None, d_image_staged=False, g_image_staged=False, comm=None, b_global=None):
+    """One whole generator update (loss, backward, gradient sum over the ranks of `comm` if given, Adam in place on gparams / m / v):
+    two launches.  fake = gen_fwd_f32(noisy, gparams).  *_image_staged: see ofdmgan_gen_train_ctr - only right after critic_train on
+    `dparams` / gen_fwd_f32 with this `gparams` tensor, with nothing else on the library in between."""
+    clean, noisy, fake = frames(clean), frames(noisy), frames(fake)
+    if out is None:
+        out = torch.empty(GEN_OUT, dtype=torch.float32, device=clean.device)
+    check(_lib.lib().ofdmgan_gen_train_ctr(dptr(clean), dptr(noisy), dptr(fake), dptr(step_dev), dptr(gparams), dptr(m), dptr(v), lr, beta1,
+                                           beta2, eps, dptr(dparams), adv_weight, rec_weight, slope, clean.shape[0],
+                                           clean.shape[0] if b_global is None else b_global, dptr(out), 1 if d_image_staged else 0,
+                                           1 if g_image_staged else 0, comm._h if comm is not None else None, stream_ptr(clean.device)))
+    return out
+
+
 def adam(p, m, v, g, lr, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None):
     """In-place fused Adam on flat fp32 CUDA vectors (torch.optim.Adam semantics, train.py:114-127).
     step_dev (int32 CUDA tensor, 1 element): the step count lives on the device - t = step_dev + 1 is used and stored back."""

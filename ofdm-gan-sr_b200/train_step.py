@@ -194,10 +194,11 @@ class CWGANGPStep:
             else:
                 self.k.adam(p, m, v, buf, lr, self.betas[0], self.betas[1], self.eps, 0, step_dev=ctr)
 
+        fused = hasattr(self.k, "critic_train") and hasattr(self.k, "gen_train")
         self._fake = self.k.gen_fwd_f32(noisy, self.g, self.slope)
         for c in range(self.n_critic):
             out = self._dout[c]
-            if hasattr(self.k, "critic_train"):
+            if fused:
                 # loss + backward, then ONE tail launch (gradient reduction, the sum over the ranks through peer memory, Adam,
                 # weight-image refresh); from the second iteration on the image installed by the previous tail is still current
                 self.k.critic_train(clean, noisy, self._fake, self.d, self.d_m, self.d_v, self._ctr[0:1], self.lr_d, self.betas[0],
@@ -207,6 +208,13 @@ class CWGANGPStep:
             self.k.critic_step(clean, noisy, self._fake, self.d, seed=self.seed, sample0=self.rank * B, gp_weight=self.gp_weight,
                                slope=self.slope, b_global=Bg, out=out, alpha_iter_dev=self._ctr[0:1])
             update(out, self.d, self.d_m, self.d_v, self.lr_d, self._ctr[0:1])
+        if self.reuse_fake and fused:
+            # loss + backward, then ONE tail launch (reduction, sum over the ranks, Adam).  Inside this iteration the staging buffers
+            # still hold the critic image the last critic tail wrote and the generator image gen_fwd_f32 built: copied, not rebuilt
+            self.k.gen_train(clean, noisy, self._fake, self.g, self.g_m, self.g_v, self._ctr[1:2], self.lr_g, self.betas[0], self.betas[1],
+                             self.eps, self.d, adv_weight=self.adv_weight, rec_weight=self.rec_weight, slope=self.slope, out=self._gout,
+                             d_image_staged=self.n_critic > 0, g_image_staged=True, comm=self.comm, b_global=Bg)
+            return
         self.k.gen_step(clean, noisy, self.d, self.g, self.adv_weight, self.rec_weight, self.slope, b_global=Bg, out=self._gout,
                         fake=self._fake if self.reuse_fake else None)
         update(self._gout, self.g, self.g_m, self.g_v, self.lr_g, self._ctr[1:2])
@@ -319,5 +327,5 @@ class CWGANGPStep:
     # 4 (image, k_critic, finalize, adam), generator step 6 (2 images, k_gen_step, finalize, adam)... see DESIGN.md
     def launches_per_step(self):
         if self.use_graph:                                       # fused critic iterations: kernel + tail, one image refresh per step
-            return 2 + (2 * self.n_critic + 1) + 5
+            return 2 + (2 * self.n_critic + 1) + 2
         return 2 + self.n_critic * 4 + 5                         # (the fused exchange kernel takes the Adam kernel's place)

@@ -29,7 +29,7 @@ def _declared():
 def test_header_declares_the_documented_surface():
     names = _declared()
     for n in ("ofdmgan_gen_fwd_f32", "ofdmgan_gen_bwd_f32", "ofdmgan_gen_fwd_q", "ofdmgan_chan_sim", "ofdmgan_sim_gen_metrics",
-              "ofdmgan_sim_gen_metrics_host", "ofdmgan_critic_step", "ofdmgan_gen_step", "ofdmgan_gen_step_fake", "ofdmgan_adam",
+              "ofdmgan_sim_gen_metrics_host", "ofdmgan_critic_step", "ofdmgan_gen_step", "ofdmgan_gen_step_fake", "ofdmgan_gen_train_ctr", "ofdmgan_adam",
               "ofdmgan_gradient_penalty", "ofdmgan_disc_fwd_f32", "ofdmgan_disc_bwd_f32"):
         assert n in names
 
@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_abi_version_and_error_strings(pkg):
     L = pkg._lib.lib()
-    assert L.ofdmgan_abi_version() == 15
+    assert L.ofdmgan_abi_version() == 16
     assert L.ofdmgan_error_string(0) == b"ok"
     assert b"invalid argument" in L.ofdmgan_error_string(-1)
     assert b"streams" in L.ofdmgan_error_string(-2)

@@ -156,6 +156,49 @@ def test_generator_step_from_a_precomputed_fake_vs_oracle(ops, ref_fp32, B):
     assert_close(out[:261], own[:261], 2e-6, f"from fake vs own forward B={B}")
 
 
+def test_fused_generator_update_equals_step_plus_adam(ops, ref_fp32):
+    """ofdmgan_gen_train_ctr (step + one tail launch: reduction, Adam) == ofdmgan_gen_step_fake followed by ofdmgan_adam_ctr, bit for
+    bit; and with the weight images taken from the staging buffers (as inside a training iteration) instead of rebuilt."""
+    B = 4097
+    clean, noisy, _ = _batch(B, 77)
+    c, n = cu(clean), cu(noisy)
+    d = cu(ref_fp32["dparams"]).clone()
+    g0 = cu(ref_fp32["gparams"]).clone()
+    hp = dict(lr=2e-4, beta1=0.0, beta2=0.9, eps=1e-8)
+    z = lambda k: torch.zeros(k, dtype=torch.float32, device="cuda")
+
+    def separate():
+        p, m, v, ctr = g0.clone(), z(258), z(258), torch.zeros(1, dtype=torch.int32, device="cuda")
+        fake = ops.gen_fwd_f32(n, p)
+        out = ops.gen_step(c, n, d, p, 1.0, 100.0, fake=fake)
+        ops.adam(p, m, v, out, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], 0, step_dev=ctr)
+        return out.clone(), p, m, v, ctr
+
+    def fused(staged):
+        p, m, v, ctr = g0.clone(), z(258), z(258), torch.zeros(1, dtype=torch.int32, device="cuda")
+        if staged:                                           # a critic update first: its tail leaves the image of `dd` staged
+            dd, dm, dv, dctr = d.clone(), z(521), z(521), torch.zeros(1, dtype=torch.int32, device="cuda")
+            fk = ops.gen_fwd_f32(n, p)
+            ops.critic_train(c, n, fk, dd, dm, dv, dctr, 2e-4, 0.0, 0.9, 1e-8)
+        else:
+            dd = d
+        fake = ops.gen_fwd_f32(n, p)                          # (stages the generator image of p)
+        out = ops.gen_train(c, n, fake, p, m, v, ctr, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], dd, 1.0, 100.0,
+                            d_image_staged=staged, g_image_staged=staged)
+        return out.clone(), p, m, v, ctr, dd
+
+    o0, p0, m0, v0, c0 = separate()
+    o1, p1, m1, v1, c1, _ = fused(False)
+    assert torch.equal(o0, o1) and torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+    assert int(c0.item()) == 1 and int(c1.item()) == 1
+    o2, p2, m2, v2, c2, dd = fused(True)                      # different critic (one update applied): compare with rebuilt images
+    p, m, v, ctr = g0.clone(), z(258), z(258), torch.zeros(1, dtype=torch.int32, device="cuda")
+    fake = ops.gen_fwd_f32(n, p)
+    o3 = ops.gen_train(c, n, fake, p, m, v, ctr, hp["lr"], hp["beta1"], hp["beta2"], hp["eps"], dd, 1.0, 100.0)
+    assert torch.equal(o2, o3) and torch.equal(p2, p) and torch.equal(m2, m) and torch.equal(v2, v)
+    assert not torch.equal(o2, o1)                            # (the critic update did change the step)
+
+
 def test_generator_step_from_fake_argument_errors(ops, ref_fp32):
     clean, noisy, _ = _batch(64, 1)
     dp, gp = ref_fp32["dparams"], ref_fp32["gparams"]

@@ -11,6 +11,8 @@ import bench  # noqa: E402
 import ofdm_gan_sr_b200 as pkg  # noqa: E402
 from ofdm_gan_sr_b200.train_step import CWGANGPStep  # noqa: E402
 
+if os.environ.get('NO_GEN_TRAIN'):
+    del pkg.ops.gen_train                  # A/B: generator update as gen_step + separate Adam launch
 gp, dp = bench.seed_params()
 cfg = pkg.ops.make_cfg(normalize=1, snr_lo=0.0, snr_hi=30.0)
 clean, noisy, _ = pkg.ops.chan_sim(cfg, 65536, seed=0)
