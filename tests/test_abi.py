@@ -67,6 +67,11 @@ def test_argument_errors_need_no_device(pkg):
     assert L.ofdmgan_gen_fwd_f32(None, None, None, 4, 0.2, None) == -1
     assert L.ofdmgan_critic_step(None, None, None, None, 0, 0, 0, None, 10.0, 0.2, 4, 4, None, None) == -1
     assert L.ofdmgan_adam(None, None, None, None, 10, 2e-4, 0.0, 0.9, 1e-8, 1, 1.0, None) == -1
+    assert L.ofdmgan_gen_step_fake(None, None, None, None, None, 1.0, 100.0, 0.2, 4, 4, None, None) == -1
+    assert L.ofdmgan_gen_train_ctr(None, None, None, None, None, None, None, 2e-4, 0.0, 0.9, 1e-8, None, 1.0, 100.0, 0.2, 4, 4, None, 0, 0,
+                                   None, None) == -1
+    assert L.ofdmgan_critic_train_ctr(None, None, None, 0, 0, None, None, None, None, 2e-4, 0.0, 0.9, 1e-8, 10.0, 0.2, 4, 4, None, 0, None,
+                                      None) == -1
     cfg = pkg.ops.make_cfg(normalize=7)
     assert L.ofdmgan_chan_sim(ctypes.byref(cfg), None, 0, 0, None, None, None, 4, None) == -1
     cfg = pkg.ops.make_cfg(n_fft=64)
