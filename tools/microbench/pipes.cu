@@ -18,14 +18,15 @@ __device__ __forceinline__ void mulwide(unsigned x, unsigned& hi, unsigned& lo) 
 __device__ __forceinline__ unsigned mulhi(unsigned x) { unsigned r; asm volatile("mul.hi.u32 %0, %1, 0xD2511F53;" : "=r"(r) : "r"(x)); return r; }
 __device__ __forceinline__ unsigned mullo(unsigned x, unsigned y) { unsigned r; asm volatile("mad.lo.u32 %0, %1, %2, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
 
-enum { FFMA, FFMA2_UR, FFMA2_R, IMADW, IMADHI, IMADLO, LOP3, MUFU, FADD, FMNMX, MIX_F2_IW, MIX_F2_LOP, MIX_F2_MUFU, MIX_F2_FFMA, MIX_IW_LOP, MIX_F_LOP, MIX_2F2_LOP, MIX_SIM, N_MODES };
+enum { FFMA, FFMA2_UR, FFMA2_R, IMADW, IMADHI, IMADLO, LOP3, MUFU, FADD, FMNMX, MIX_F2_IW, MIX_F2_LOP, MIX_F2_MUFU, MIX_F2_FFMA, MIX_IW_LOP, MIX_F_LOP, MIX_2F2_LOP, MIX_SIM, MIX_CRITIC, N_MODES };
 const char* NAMES[] = {"FFMA R,R,UR,R", "FFMA2 pair x (broadcast R) x UR pair", "FFMA2 pair x R x R pair", "IMAD.WIDE.U32 R,R,imm", "IMAD.HI.U32", "IMAD (lo)",
                        "LOP3", "MUFU.EX2", "FADD", "FMNMX", "mix 1 FFMA2 : 1 IMAD.WIDE", "mix 1 FFMA2 : 1 LOP3", "mix 4 FFMA2 : 1 MUFU", "mix 1 FFMA2 : 1 FFMA",
                        "mix 1 IMAD.WIDE : 1 LOP3 (Philox round)", "mix 1 FFMA : 1 LOP3", "mix 2 FFMA2 : 1 LOP3",
-                       "mix of the fused kernel (15 FFMA2 : 22 scalar FP : 6 IMAD.WIDE : 13 ALU : 7 MUFU = 612 : 908 : 252 : 560 : 295)"};
+                       "mix of the fused kernel (15 FFMA2 : 22 scalar FP : 6 IMAD.WIDE : 13 ALU : 7 MUFU = 612 : 908 : 252 : 560 : 295)",
+                       "mix of the critic kernel without its SHFL / LDC (8 FFMA2 : 2 scalar FP : 5 ALU)"};
 // instructions issued per inner iteration (per thread) for each mode
 __host__ __device__ constexpr int per_iter(int m) {
-    return m == MIX_F2_MUFU ? 8 + 2 : m == MIX_SIM ? 63 : m == MIX_2F2_LOP ? 24 : m >= MIX_F2_IW ? 16 : 8;
+    return m == MIX_F2_MUFU ? 8 + 2 : m == MIX_SIM ? 63 : m == MIX_CRITIC ? 15 : m == MIX_2F2_LOP ? 24 : m >= MIX_F2_IW ? 16 : 8;
 }
 template <int MODE>
 __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b, u64 w2) {
@@ -62,6 +63,13 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b
                 for (int j = 0; j < 8; ++j) p[j] = fma2(pk(v[j], v[j]), w2, p[j]);
                 v[r & 7] = ex2(v[r & 7]);
                 v[(r + 4) & 7] = ex2(v[(r + 4) & 7]);
+            }
+            if (MODE == MIX_CRITIC) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p[j] = fma2(pk(v[j], v[j]), w2, p[j]);
+                v[0] = ffma(v[0], a, b); v[1] = fadd(v[1], a);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) x[j] = lop(x[j], y[j], 0x9E3779B9u);
             }
             if (MODE == MIX_SIM) {       // 63 instructions in the kernel's proportions, kinds interleaved
 #pragma unroll
