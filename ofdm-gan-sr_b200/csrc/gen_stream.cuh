@@ -21,6 +21,15 @@ constexpr int GSX_NG = 10;
 constexpr int GS_OUTF = 0, GS_DECF = 32, GS_BNW = 160, GS_ENCW = 256, GS_ENCB = 280, GS_BNB = 288, GS_DECB = 296, GS_OUTB = 300,
               GS_S0 = 302, GS_SLOTS = 320;
 
+// LOCKSTEP: a CTA-wide barrier between the stages of these passes.  They are ~100 KB of mostly straight-line code that every warp
+// runs once per work item: warps that drift apart fetch it from L2 over and over (`no_inst` was 40-45 % of the stall samples in
+// front of the FP instructions); kept within a stage of each other they share the SM's 32 KB instruction cache.  Only for kernels
+// whose warps ALL run the same sequence (k_gen_step); the control flow around every call site is CTA-uniform.
+template <bool LOCKSTEP>
+__device__ __forceinline__ void gs_stage_barrier() {
+    if (LOCKSTEP) __syncthreads();
+}
+
 // the thread's own 32-float slot of a resident tile, addressed in 16-byte chunks c = 0..7
 __device__ __forceinline__ float4 slot_ld(const float4* wsm, int lane, int c) { return wsm[lane * 8 + (c ^ (lane & 7))]; }
 __device__ __forceinline__ void slot_st(float4* wsm, int lane, int c, float4 v) { wsm[lane * 8 + (c ^ (lane & 7))] = v; }
@@ -45,7 +54,7 @@ __device__ __forceinline__ void unpark48(const float4* wsm, int lane, float (&a)
 // ---- forward.  x rows come from t_x; y rows are written to t_y; t_s is a scratch slot (free on return).
 // TAPE: returns a1 = lrelu(enc1), a2 = lrelu(bottleneck), sk = skip sum, z3pos (bit oc*8+q: dec1 pre-activation > 0).
 // WRITE_Y = false: the output layer is skipped (the caller already holds what it needs of y; t_y is left alone).
-template <bool TAPE, bool WRITE_Y = true>
+template <bool TAPE, bool WRITE_Y = true, bool LOCKSTEP = false>
 __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4* t_x, float4* t_y, float4* t_s, int lane,
                                        float (&a1)[4][8], float (&a2)[8][4], float (&sk)[4][8], uint32_t& z3pos) {
     // enc1: Conv1d(2->4, k3, s2, p1) + LeakyReLU, one input row per iteration
@@ -96,6 +105,7 @@ __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4
         const float4 v = slot_ld(t_s, lane, oc);
         a2[oc][0] = v.x; a2[oc][1] = v.y; a2[oc][2] = v.z; a2[oc][3] = v.w;
     }
+    gs_stage_barrier<LOCKSTEP>();
     // upsample x2 + dec1 Conv1d(8->4, k3, s1, p1) + LeakyReLU, folded; one output channel per iteration
     z3pos = 0;
 #pragma unroll 1
@@ -130,6 +140,7 @@ __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4
     for (int oc = 0; oc < 4; ++oc)
 #pragma unroll
         for (int q = 0; q < 8; ++q) sk[oc][q] += a1[oc][q];                      // additive skip (models/generator.py:199)
+    gs_stage_barrier<LOCKSTEP>();
     // upsample x2 + out_conv Conv1d(4->2, k3, s1, p1), folded; tanh; one output row per iteration, written to t_y
 #pragma unroll 1
     for (int oc = 0; oc < (WRITE_Y ? 2 : 0); ++oc) {
@@ -158,7 +169,7 @@ __device__ __forceinline__ void gs_fwd(const float* W, float slope, const float4
 // THREE_SLOTS (the fused generator step): on entry t_y already holds dz4 = upstream gradient * tanh' (the caller had y in registers
 // when it formed the upstream gradient), and t_dy IS the slot of the input rows: it is used as parking space like any other, and the
 // input rows are fetched again from x_glob (frames base .. of B) for the last gradient group.  One 4 KB tile per warp less.
-template <bool NEED_DX, bool THREE_SLOTS = false>
+template <bool NEED_DX, bool THREE_SLOTS = false, bool LOCKSTEP = false>
 __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4* t_x, float4* t_y, float4* t_dy, float4* t_p, int lane,
                                        float (&a1)[4][8], const float (&a2)[8][4], const float (&sk)[4][8], uint32_t z3pos, SAcc& acc,
                                        const float* x_glob = nullptr, int64_t base = 0, int64_t B = 0) {
@@ -202,6 +213,7 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
         }
         acc.add(0, warp_transpose_reduce(v, lane));
     }
+    gs_stage_barrier<LOCKSTEP>();
     // ---- dsk = out_conv^T(dz4) (one input channel per iteration, row -> t_y chunks 2ic, 2ic+1), dz3 = dsk . lrelu'(z3)
 #pragma unroll 1
     for (int ic = 0; ic < 4; ++ic) {
@@ -234,6 +246,7 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
         }
         bias_g[8 + oc] = s;
     }
+    gs_stage_barrier<LOCKSTEP>();
     // ---- dec1 folded weight gradient (4 groups, one per output channel) - no weights involved, unrolled
 #pragma unroll
     for (int grp = 0; grp < 4; ++grp) {
@@ -252,6 +265,7 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
             v[j] = a;
         }
         acc.add(1 + grp, warp_transpose_reduce(v, lane));
+        if (grp & 1) gs_stage_barrier<LOCKSTEP>();
     }
     // ---- dz2 = dec1^T(dz3) . lrelu'(a2): one input channel per iteration, raw row -> t_dy chunk ic
 #pragma unroll 1
@@ -285,6 +299,7 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
         }
         bias_g[ic] = s;
     }
+    gs_stage_barrier<LOCKSTEP>();
     // ---- bottleneck weight gradient (3 groups) - needs a1 back
     unpark48(t_p, lane, a1);
 #pragma unroll
@@ -303,6 +318,7 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
         }
         acc.add(5 + grp, warp_transpose_reduce(v, lane));
     }
+    gs_stage_barrier<LOCKSTEP>();
     // ---- dz1 = (dsk + bottleneck^T(dz2)) . lrelu'(a1): one input channel per iteration, raw row -> t_dy chunks 2ic, 2ic+1
     // (t_dy's dz2 rows are consumed: dz2 is in registers)
 #pragma unroll 1
@@ -333,6 +349,7 @@ __device__ __forceinline__ void gs_bwd(const float* W, float slope, const float4
 #pragma unroll
             for (int i = 0; i < 8; ++i) dz1[ic][i] = (dz1[ic][i] + dsk[ic][i]) * (a1[ic][i] > 0.f ? 1.0f : slope);
     }
+    gs_stage_barrier<LOCKSTEP>();
     // ---- enc1 weight + bias gradient (group 8)
     if (THREE_SLOTS) {                                           // t_dy's parked rows are consumed: bring the input rows back
         __syncwarp();

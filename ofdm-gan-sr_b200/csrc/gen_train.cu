@@ -26,29 +26,31 @@ struct GenStepArgs {
 // critic_stream.cuh).  THREE resident 4 KB tiles per warp - noisy (later parking space; refetched for the last gradient group) |
 // fake -> dz4 rows -> parked rows | clean -> scratch / parked rows - and <= 128 registers: 4 CTAs per SM, so the 512 tiles of a
 // 65,536-sample shard are ONE round (592 slots) instead of 1.15 rounds of 444.
-constexpr int GENSTEP_PER_SM = 4;
-constexpr size_t GENSTEP_SMEM = (size_t)3 * OG_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * OG_THREADS * sizeof(float);
+// The kernel runs as ONE 512-thread CTA per SM (16 warps = the same residency) with a barrier between the stages of an item: see
+// gs_stage_barrier.  Warps past the end of the batch run the item on all-dead lanes (every warp must reach every barrier).
+constexpr int GENSTEP_THREADS = 512, GENSTEP_WARPS = GENSTEP_THREADS / 32;
+constexpr int GENSTEP_PER_SM = 1;
+constexpr size_t GENSTEP_SMEM = (size_t)3 * GENSTEP_THREADS * 8 * sizeof(float4) + (size_t)GSX_NG * GENSTEP_THREADS * sizeof(float);
 
 template <bool HAVE_FAKE>
-__global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const __grid_constant__ GenStepArgs a) {
+__global__ void __launch_bounds__(GENSTEP_THREADS, GENSTEP_PER_SM) k_gen_step(const __grid_constant__ GenStepArgs a) {
     extern __shared__ float4 sm[];
-    float* sacc = reinterpret_cast<float*>(sm + 3 * OG_THREADS * 8);
+    float* sacc = reinterpret_cast<float*>(sm + 3 * GENSTEP_THREADS * 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* t_x = sm + warp * TILE4;
-    float4* t_y = sm + (NWARP + warp) * TILE4;
-    float4* t_p = sm + (2 * NWARP + warp) * TILE4;
+    float4* t_y = sm + (GENSTEP_WARPS + warp) * TILE4;
+    float4* t_p = sm + (2 * GENSTEP_WARPS + warp) * TILE4;
     const float* WG = c_g;
     const float* WD = c_d;
-    SAcc acc{sacc + threadIdx.x, OG_THREADS};
+    SAcc acc{sacc + threadIdx.x, GENSTEP_THREADS};
 #pragma unroll
-    for (int g = 0; g < GSX_NG; ++g) sacc[g * OG_THREADS + threadIdx.x] = 0.f;
+    for (int g = 0; g < GSX_NG; ++g) sacc[g * GENSTEP_THREADS + threadIdx.x] = 0.f;
     float s_d = 0.f, s_l1 = 0.f;
     const float rec_g = a.rec_w * 0.03125f;                      // rec_w / 32: l1_loss is a mean over B*32 elements
-    const int64_t ntiles = (a.B + OG_THREADS - 1) / OG_THREADS;
+    const int64_t ntiles = (a.B + GENSTEP_THREADS - 1) / GENSTEP_THREADS;
 #pragma unroll 1
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t base = t * OG_THREADS + warp * 32;
-        if (base >= a.B) continue;
+        const int64_t base = t * GENSTEP_THREADS + warp * 32;     // (>= B for the surplus warps of the last tile: all lanes dead)
         const bool live = base + lane < a.B;
         __syncwarp();
         tile_fill_f32(a.noisy, base, a.B, t_x, lane);
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
             __syncwarp();
             float a1[4][8], a2[8][4], sk[4][8];
             uint32_t z;
-            gs_fwd<false>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z);
+            gs_fwd<false, true, true>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z);
         }
         __syncwarp();
         if (!HAVE_FAKE && a.fake_out) {
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
             __syncwarp();
         }
         tile_fill_f32(a.clean, base, a.B, t_p, lane);
-        __syncwarp();
+        __syncthreads();
         // (2) critic on (fake, noisy): d(-adv_w * D)/d fake, + rec_w * sign(fake - clean)/32 = upstream gradient; times tanh'(z) =
         // 1 - y^2 while the y row is in registers -> dz4 rows, which replace the y rows in t_y
         {
@@ -76,8 +78,10 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
                 uint64_t m1, m2;
                 const float score = cs_score_only(WD, a.slope, t_y, t_x, acc, lane, m1, m2);
                 if (live) s_d += score;
+                __syncthreads();
                 cs_bwd_to_z1(WD, a.slope, live ? -a.adv_w : 0.f, m1, m2, dz1);
             }
+            __syncthreads();
 #pragma unroll 1
             for (int ic = 0; ic < 2; ++ic) {
                 float row[16], y[16], c[16];
@@ -98,12 +102,13 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
                 row_write(t_y, lane, ic, row);
             }
         }
+        __syncthreads();
         // (3) forward with tape (t_p is scratch again), backward
         {
             float a1[4][8], a2[8][4], sk[4][8];
             uint32_t z3pos;
-            gs_fwd<true, false>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z3pos);
-            gs_bwd<false, true>(WG, a.slope, t_x, t_y, t_x, t_p, lane, a1, a2, sk, z3pos, acc, a.noisy, base, a.B);
+            gs_fwd<true, false, true>(WG, a.slope, t_x, t_y, t_p, lane, a1, a2, sk, z3pos);
+            gs_bwd<false, true, true>(WG, a.slope, t_x, t_y, t_x, t_p, lane, a1, a2, sk, z3pos, acc, a.noisy, base, a.B);
         }
     }
     {
@@ -113,11 +118,11 @@ __global__ void __launch_bounds__(OG_THREADS, GENSTEP_PER_SM) k_gen_step(const _
     }
     __syncthreads();
     float* row = a.partials + (size_t)blockIdx.x * GS_SLOTS;
-    for (int s = threadIdx.x; s < GS_SLOTS; s += OG_THREADS) {
+    for (int s = threadIdx.x; s < GS_SLOTS; s += GENSTEP_THREADS) {
         const int grp = s >> 5, j = s & 31;
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < NWARP; ++w) t += sacc[grp * OG_THREADS + w * 32 + j];
+        for (int w = 0; w < GENSTEP_WARPS; ++w) t += sacc[grp * GENSTEP_THREADS + w * 32 + j];
         row[s] = t;
     }
 }
@@ -302,7 +307,7 @@ static int gen_step_impl(const float* clean_dev, const float* noisy_dev, const f
     slot = 0;
     if ((rc = upload_d(dparams521, slot, s))) return rc;
     if ((rc = upload_g(gparams258, slot, s))) return rc;
-    const int grid = grid_for(B_local, OG_THREADS, GENSTEP_PER_SM);
+    const int grid = grid_for(B_local, GENSTEP_THREADS, GENSTEP_PER_SM);
     void* partials = nullptr;
     if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
     GenStepArgs a{};
@@ -311,10 +316,10 @@ static int gen_step_impl(const float* clean_dev, const float* noisy_dev, const f
     a.partials = (float*)partials;
     if (fake_in_dev) {
         OG_CHECK(cudaFuncSetAttribute(k_gen_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
-        k_gen_step<true><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+        k_gen_step<true><<<grid, GENSTEP_THREADS, GENSTEP_SMEM, s>>>(a);
     } else {
         OG_CHECK(cudaFuncSetAttribute(k_gen_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
-        k_gen_step<false><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+        k_gen_step<false><<<grid, GENSTEP_THREADS, GENSTEP_SMEM, s>>>(a);
     }
     OG_CHECK(cudaGetLastError());
     k_finalize_gen<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
@@ -357,7 +362,7 @@ int ofdmgan_gen_train_ctr(const float* clean_dev, const float* noisy_dev, const 
     // ofdmgan_critic_train_ctr left it; G: ofdmgan_gen_fwd_f32 with the same device parameters built it) - copy it, skip the rebuild
     if ((rc = d_image_staged ? commit_d_image(slot, s) : upload_d(dparams521_dev, slot, s))) return rc;
     if ((rc = g_image_staged ? commit_g_image(slot, s) : upload_g(gparams258_dev, slot, s))) return rc;
-    const int grid = grid_for(B, OG_THREADS, GENSTEP_PER_SM);
+    const int grid = grid_for(B, GENSTEP_THREADS, GENSTEP_PER_SM);
     void *partials = nullptr, *arrivals = nullptr;
     if ((rc = scratch_for_slot(slot, (size_t)grid * GS_SLOTS * sizeof(float), 7, &partials))) return rc;
     if ((rc = scratch_for_slot(slot, 256, 9, &arrivals))) return rc;
@@ -373,7 +378,7 @@ int ofdmgan_gen_train_ctr(const float* clean_dev, const float* noisy_dev, const 
     a.B = B; a.slot = slot; a.slope = leaky_slope; a.adv_w = adv_weight; a.rec_w = rec_weight;
     a.partials = (float*)partials;
     OG_CHECK(cudaFuncSetAttribute(k_gen_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
-    k_gen_step<true><<<grid, OG_THREADS, GENSTEP_SMEM, s>>>(a);
+    k_gen_step<true><<<grid, GENSTEP_THREADS, GENSTEP_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
     k_gen_tail<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight, out_dev,
                                       gparams258_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, peers, rank,
