@@ -209,6 +209,50 @@ __global__ void __launch_bounds__(1024) k_critic_tail(const float* __restrict__ 
     for (int j = i; j < OG_D_IMG; j += blockDim.x) image[j] = d_img_entry(pnew, j);
 }
 
+// The same tail on ONE GPU (no exchange): a parameter's gradient is complete inside the block of its accumulator group, so every block
+// applies Adam to its own <= 28 parameters and writes their entries of the weight image right after its reduction - no hand-over to a
+// last block.  The ticket only decides who advances the step count (after every block has read it).  Bit-identical to k_critic_tail.
+__global__ void __launch_bounds__(1024) k_critic_tail1(const float* __restrict__ partials, int nblocks, double inv_b, double gp_weight,
+                                                       float* __restrict__ out, float* __restrict__ p, float* __restrict__ m,
+                                                       float* __restrict__ v, double lr, double b1, double b2, double eps,
+                                                       int32_t* __restrict__ step_dev, unsigned int* __restrict__ arrivals,
+                                                       float* __restrict__ image) {
+    __shared__ double red[32 * 32], total[32];
+    const int grp = blockIdx.x, j = threadIdx.x;
+    const int t = *step_dev + 1;
+    int i = -1;
+    float pi = 0.f, mi = 0.f, vi = 0.f;
+    if (j < 32) {
+        i = cs_param_of(grp, j);
+        if (i >= 0) { pi = p[i]; mi = m[i]; vi = v[i]; }
+    }
+    reduce_group_rows(partials, nblocks, CS_SLOTS, grp, red, total);
+    if (i >= 0) {
+        const float g = (float)(total[j] * inv_b);
+        out[i] = g;
+        const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);
+        adam_one(pi, mi, vi, g, c);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        d_img_scatter(image, i, pi);
+    }
+    if (grp == 1 && j == 0) {
+        float* stats = out + OFDMGAN_D_NPARAMS;
+        const double dr = total[CS_SREAL - 32] * inv_b, df = total[CS_SFAKE - 32] * inv_b, gp = total[CS_SGP - 32] * inv_b;
+        stats[0] = (float)(df - dr + gp_weight * gp);
+        stats[1] = (float)(dr - df);
+        stats[2] = (float)gp;
+        stats[3] = (float)dr;
+        stats[4] = (float)df;
+        stats[5] = 0.f;
+        stats[6] = 0.f;
+    }
+    __syncthreads();
+    if (j == 0 && atomicAdd(arrivals, 1u) == gridDim.x - 1) {   // every block has read the step count: advance it
+        *arrivals = 0u;
+        *step_dev = t;
+    }
+}
+
 }  // namespace og
 
 using namespace og;
@@ -332,8 +376,13 @@ int ofdmgan_critic_train_ctr(const float* clean_dev, const float* noisy_dev, con
     a.norms = nullptr;
     k_critic2<true><<<grid, OG_THREADS, 0, s>>>(a);
     OG_CHECK(cudaGetLastError());
-    k_critic_tail<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev, dparams521_dev,
-                                         m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, image, peers, rank, world);
+    if (world == 1)
+        k_critic_tail1<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev,
+                                              dparams521_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, image);
+    else
+        k_critic_tail<<<CS_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)gp_weight, out_dev,
+                                             dparams521_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, image,
+                                             peers, rank, world);
     OG_CHECK(cudaGetLastError());
     return commit_d_image(slot, s);
 }

@@ -130,6 +130,19 @@ __device__ __forceinline__ float d_img_entry(const float* __restrict__ p, int i)
     return p[DP_C2_W + (oc * 8 + 2 * i2 + h) * 3 + k];
 }
 
+// the inverse: write parameter i (new value v) to every entry of the D image that holds it (1 to 3 entries)
+__device__ __forceinline__ void d_img_scatter(float* __restrict__ img, int i, float v) {
+    img[i] = v;
+    if (i < DP_C1_B) {                                           // conv1.weight[oc][ic][k]
+        const int k = i % 3, ic = (i / 3) % 4, oc = i / 12;
+        img[DI2_C1 + (((oc >> 1) * 4 + ic) * 3 + k) * 2 + (oc & 1)] = v;
+    } else if (i >= DP_C2_W && i < DP_C2_B) {                    // conv2.weight[oc][ic][k]
+        const int e = i - DP_C2_W, k = e % 3, ic = (e / 3) % 8, oc = e / 24;
+        img[DI2_C2 + (((oc >> 1) * 8 + ic) * 3 + k) * 2 + (oc & 1)] = v;
+        img[DI2_C2T + ((oc * 4 + (ic >> 1)) * 3 + k) * 2 + (ic & 1)] = v;
+    }
+}
+
 static __global__ void prep_d_image(const float* __restrict__ p, float* __restrict__ img) {
     const int i = threadIdx.x + blockIdx.x * blockDim.x;
     if (i < OG_D_IMG) img[i] = d_img_entry(p, i);
