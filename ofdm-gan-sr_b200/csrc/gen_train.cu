@@ -214,6 +214,36 @@ __global__ void __launch_bounds__(1024) k_gen_tail(const float* __restrict__ par
     if (j == 0) *step_dev = t;
 }
 
+// The same tail on ONE GPU (as k_critic_tail1): every block applies Adam to the parameters of its own group right after its reduction;
+// the ticket only decides who advances the step count.  Bit-identical to k_gen_tail.
+__global__ void __launch_bounds__(1024) k_gen_tail1(const float* __restrict__ partials, int nblocks, double inv_b, double adv_w, double rec_w,
+                                                    float* __restrict__ out, float* __restrict__ p, float* __restrict__ m,
+                                                    float* __restrict__ v, double lr, double b1, double b2, double eps,
+                                                    int32_t* __restrict__ step_dev, unsigned int* __restrict__ arrivals) {
+    __shared__ double red[32 * 32], total[32];
+    const int grp = blockIdx.x, j = threadIdx.x;
+    const int t = *step_dev + 1;
+    reduce_group_rows(partials, nblocks, GS_SLOTS, grp, red, total);
+    if (j < 32) {
+        double gd;
+        const int i = gs_param_of(grp, j, total, gd);
+        if (i >= 0) {
+            const float g = (float)(gd * inv_b);
+            out[i] = g;
+            float pi = p[i], mi = m[i], vi = v[i];
+            const AdamCoef c = adam_coef_dev(lr, b1, b2, eps, t);
+            adam_one(pi, mi, vi, g, c);
+            p[i] = pi; m[i] = mi; v[i] = vi;
+        }
+    }
+    if (grp == 9 && j == 0) gs_write_stats(total, inv_b, adv_w, rec_w, out + OFDMGAN_G_NPARAMS);
+    __syncthreads();
+    if (j == 0 && atomicAdd(arrivals, 1u) == gridDim.x - 1) {   // every block has read the step count: advance it
+        *arrivals = 0u;
+        *step_dev = t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ generator backward (API)
 // what autograd needs for MiniGenerator.forward: dparams = sum_b backward(dy_b) and (optionally) dx
 // (four tiles per warp - x | dy | y | scratch - and up to 168 registers: 3 CTAs per SM)
@@ -380,9 +410,13 @@ int ofdmgan_gen_train_ctr(const float* clean_dev, const float* noisy_dev, const 
     OG_CHECK(cudaFuncSetAttribute(k_gen_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GENSTEP_SMEM));
     k_gen_step<true><<<grid, GENSTEP_THREADS, GENSTEP_SMEM, s>>>(a);
     OG_CHECK(cudaGetLastError());
-    k_gen_tail<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight, out_dev,
-                                      gparams258_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals, peers, rank,
-                                      world);
+    if (world == 1)
+        k_gen_tail1<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
+                                            out_dev, gparams258_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals);
+    else
+        k_gen_tail<<<GSX_NG, 1024, 0, s>>>((const float*)partials, grid, 1.0 / (double)B_global, (double)adv_weight, (double)rec_weight,
+                                           out_dev, gparams258_dev, m_dev, v_dev, lr, beta1, beta2, eps, step_dev, (unsigned int*)arrivals,
+                                           peers, rank, world);
     return (int)cudaGetLastError();
 }
 
